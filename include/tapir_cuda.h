@@ -1,0 +1,131 @@
+/*
+ * tapir_cuda.h -- C ABI of libtapir_cuda.so, the B200 (sm_100a) implementation of tapir's
+ * Townsend phylogenetic-informativeness hot path.
+ *
+ * The reference (faircloth-lab/tapir) is pure Python and has no FFI; the boundary this
+ * library replaces is the per-locus arithmetic that `worker()` performs through
+ * `tapir.compute` (citations relative to the reference checkout):
+ *
+ *   tapir/compute.py:46-48   get_townsend_pi            PI(t,i) = 16 r_i^2 t exp(-4 r_i t)
+ *   bin/tapir_compute.py:119 numpy.nansum(pi, axis=1)    -> pi_net[t]        (`net` table)
+ *   tapir/compute.py:76-79   get_net_pi_for_periods      -> pi_net[times]    (`discrete` table)
+ *   tapir/compute.py:50-52   get_integral_over_times     scipy quad == QUADPACK QAGS / GK21
+ *   tapir/compute.py:81-94   get_net_integral_for_epochs -> sum(integral), sum(error) (`interval`)
+ *   bin/tapir_compute.py:110 masked mean of the rates    -> mean_rate
+ *   README.rst:178-185       per-locus max(pi) over intervals -> argmax_epoch
+ *
+ * One call processes MANY loci packed as CSR (offsets, rates); the reference maps worker()
+ * over loci one at a time (bin/tapir_compute.py:159-164).
+ *
+ * Conventions: every entry point returns 0 on success or a negative TAPIR_E_* code and never
+ * throws or exits; tapir_cuda_last_error() gives the message.  The caller owns all host
+ * buffers; the library owns device memory and streams inside a context.  A context is bound to
+ * one device and is not thread-safe; distinct contexts are independent.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with TAPIR_E_CUDA.
+ */
+#ifndef TAPIR_CUDA_H
+#define TAPIR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAPIR_CUDA_ABI_VERSION 1
+
+/* error codes */
+#define TAPIR_OK 0
+#define TAPIR_E_INVALID (-1) /* bad argument (NULL, negative size, a >= b epoch, time index out of range) */
+#define TAPIR_E_CUDA (-2)    /* CUDA runtime / driver error, or no device */
+#define TAPIR_E_NOMEM (-3)   /* host or device allocation failed */
+#define TAPIR_E_STATE (-4)   /* call order error (compute before upload, ...) */
+
+/* tapir_problem.flags */
+#define TAPIR_WANT_PROFILE 1u /* copy pi_net[L*T] back to the host (it is always computed) */
+#define TAPIR_FP32_PROFILE 2u /* profile terms in FP32 with FP64 block accumulation (<=1e-5 mode) */
+
+#define TAPIR_MAX_EPOCHS 64
+#define TAPIR_MAX_TIMES 4096
+
+typedef struct tapir_cuda_ctx tapir_cuda_ctx;
+
+/* One batch of loci.  All pointers are HOST pointers for tapir_cuda_run / tapir_cuda_upload. */
+typedef struct tapir_problem {
+    int64_t n_loci;          /* L */
+    const int64_t *offsets;  /* [L+1], offsets[0] == 0, non-decreasing: CSR row pointers into rates */
+    const double *rates;     /* [offsets[L]] corrected site rates; NaN/Inf = culled site (skipped) */
+    int64_t n_grid;          /* T: the grid is t = 0..T-1, step 1 (compute.py:54-57, get_time(0,int(depth))) */
+    int32_t n_times;         /* K */
+    const int64_t *time_idx; /* [K] grid indices as numpy fancy indexing takes them: -T <= idx < T */
+    int32_t n_epochs;        /* E <= TAPIR_MAX_EPOCHS */
+    const double *epoch_ab;  /* [2E] a0,b0,a1,b1,... with a < b (compute.py:90) */
+    uint32_t flags;
+} tapir_problem;
+
+/* Result arrays (host pointers for run/download; device pointers from tapir_cuda_device_results).
+ * Any pointer may be NULL to skip that output. */
+typedef struct tapir_results {
+    double *pi_net;         /* [L*T]  net PI profile (only filled when TAPIR_WANT_PROFILE) */
+    double *pi_times;       /* [L*K]  pi_net at time_idx */
+    double *integral;       /* [L*E]  sum over finite sites of the QAGS integral */
+    double *abserr;         /* [L*E]  sum over finite sites of the QAGS error estimate */
+    double *max_pi;         /* [L]    max_t pi_net */
+    int64_t *argmax_t;      /* [L]    first t attaining it (numpy.argmax) */
+    int32_t *argmax_epoch;  /* [L]    first epoch (in the given order) with the largest integral */
+    double *mean_rate;      /* [L]    mean over non-NaN rates (NaN when there are none) */
+    int64_t *n_finite;      /* [L]    number of finite-rate sites (the sites that are integrated) */
+    int64_t *n_multi_panel; /* [L]    (site,epoch) pairs for which QAGS went beyond one GK21 panel */
+} tapir_results;
+
+/* Device-side timing of the last tapir_cuda_compute (CUDA events on the library's stream). */
+typedef struct tapir_timing {
+    float total_ms;    /* first launch -> last launch finished */
+    float profile_ms;  /* PI profile kernel */
+    float quad_ms;     /* GK21/QAGS epoch-integral kernel(s) */
+    float finalize_ms; /* per-locus reduction / picks / maxima kernel */
+    int32_t launches;  /* kernel launches issued */
+    int32_t reserved;
+} tapir_timing;
+
+int tapir_cuda_version(void);
+int tapir_cuda_device_count(int *count);
+/* message of the last failure on this thread (ctx may be NULL) */
+const char *tapir_cuda_last_error(const tapir_cuda_ctx *ctx);
+
+int tapir_cuda_create(int device, tapir_cuda_ctx **ctx);
+int tapir_cuda_destroy(tapir_cuda_ctx *ctx);
+
+/* pinned host memory for the CSR pack and the result arrays */
+int tapir_cuda_host_alloc(void **ptr, size_t bytes);
+int tapir_cuda_host_free(void *ptr);
+
+/* --- whole path with HOST buffers: H2D, kernels, D2H (chunked and overlapped) --- */
+int tapir_cuda_run(tapir_cuda_ctx *ctx, const tapir_problem *problem, const tapir_results *host_out);
+
+/* --- staged path: inputs resident in HBM, kernels timed on their own --- */
+int tapir_cuda_upload(tapir_cuda_ctx *ctx, const tapir_problem *problem);
+int tapir_cuda_compute(tapir_cuda_ctx *ctx, tapir_timing *timing /* may be NULL */);
+int tapir_cuda_download(tapir_cuda_ctx *ctx, const tapir_results *host_out);
+/* device pointers of the resident result arrays (valid until the next upload/destroy) */
+int tapir_cuda_device_results(tapir_cuda_ctx *ctx, tapir_results *device_ptrs);
+
+/* --- element-wise API parity with tapir.compute --- */
+/* get_townsend_pi(time, rates) -> out[T*S] row-major (T,S); NaN propagate as numpy does */
+int tapir_cuda_pi_matrix(tapir_cuda_ctx *ctx, const double *time, int64_t n_time, const double *rates,
+                         int64_t n_rates, double *out);
+/* vectorize(get_integral_over_times)(a, b, rates) -> integral[n], abserr[n], panels[n] (QAGS `last`) */
+int tapir_cuda_site_integrals(tapir_cuda_ctx *ctx, double a, double b, const double *rates, int64_t n,
+                              double *integral, double *abserr, int32_t *panels);
+
+/* --- measurement helpers used by bench.py --- */
+/* sustained FP64 FMA rate of this device, TFLOP/s (2 flop per DFMA), dependent-chain-free register kernel */
+int tapir_cuda_fp64_peak(tapir_cuda_ctx *ctx, double *tflops, float *ms);
+/* overwrite a buffer larger than L2 so the next timed step starts cold */
+int tapir_cuda_flush_l2(tapir_cuda_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAPIR_CUDA_H */

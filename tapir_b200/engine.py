@@ -1,0 +1,220 @@
+"""Batched multi-locus driver over libtapir_cuda (the GPU replacement for mapping
+``worker()`` over loci, bin/tapir_compute.py:159-164).
+
+Many loci are packed into one CSR pair ``(offsets int64[L+1], rates float64[nnz])`` in pinned
+host memory and handed to the C ABI in one call.  numpy is used for host arrays only; all
+arithmetic of the hot path happens in the CUDA library.  There is no CPU fallback.
+"""
+import ctypes
+import weakref
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Problem, Results, Timing, check
+
+
+@dataclass
+class BatchResult:
+    """Per-locus outputs of one batch (row l = locus l of the CSR pack)."""
+    pi_net: Optional[np.ndarray]   # (L, T) net PI profile, None unless requested
+    pi_times: np.ndarray           # (L, K) profile at --times
+    integral: np.ndarray           # (L, E) sum(integral) per epoch
+    abserr: np.ndarray             # (L, E) sum(error) per epoch
+    max_pi: np.ndarray             # (L,)
+    argmax_t: np.ndarray           # (L,) int64
+    argmax_epoch: np.ndarray       # (L,) int32, index into the epoch list (README.rst:178-185)
+    mean_rate: np.ndarray          # (L,)
+    n_finite: np.ndarray           # (L,) int64
+    n_multi_panel: np.ndarray      # (L,) int64
+
+
+def _free_pinned(lib, ptr):
+    lib.tapir_cuda_host_free(ptr)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory from tapir_cuda_host_alloc."""
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    nbytes = max(1, n * dtype.itemsize)
+    ptr = ctypes.c_void_p()
+    check(lib.tapir_cuda_host_alloc(ctypes.byref(ptr), nbytes))
+    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    weakref.finalize(buf, _free_pinned, lib, ptr.value)
+    return arr
+
+
+def pack_csr(loci: Sequence[np.ndarray], pinned: bool = True):
+    """Pack per-locus rate vectors into (offsets, rates).  NaN entries mark culled sites."""
+    lens = np.fromiter((len(x) for x in loci), dtype=np.int64, count=len(loci))
+    alloc = pinned_empty if pinned else np.empty
+    offsets = alloc(len(loci) + 1, np.int64)
+    offsets[0] = 0
+    np.cumsum(lens, out=offsets[1:])
+    rates = alloc(int(offsets[-1]), np.float64)
+    for l, x in enumerate(loci):
+        rates[offsets[l]:offsets[l + 1]] = x
+    return offsets, rates
+
+
+def partition_loci(site_counts: np.ndarray, n_parts: int):
+    """Size-balanced locus partition (longest-processing-time greedy, ties by index): returns a
+    list of index arrays, one per part, each sorted ascending so a part's CSR slice keeps the
+    original locus order."""
+    site_counts = np.asarray(site_counts, dtype=np.int64)
+    order = np.argsort(-site_counts, kind="stable")
+    loads = np.zeros(n_parts, dtype=np.int64)
+    parts = [[] for _ in range(n_parts)]
+    if len(site_counts) and (site_counts == site_counts[0]).all():
+        # uniform loci: contiguous blocks, no need for the greedy pass
+        bounds = np.linspace(0, len(site_counts), n_parts + 1).astype(np.int64)
+        return [np.arange(bounds[i], bounds[i + 1], dtype=np.int64) for i in range(n_parts)]
+    for idx in order:
+        p = int(np.argmin(loads))
+        parts[p].append(int(idx))
+        loads[p] += site_counts[idx] + 1
+    return [np.array(sorted(p), dtype=np.int64) for p in parts]
+
+
+class Engine:
+    """One CUDA context on one device."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        ctx = ctypes.c_void_p()
+        check(self._lib.tapir_cuda_create(device, ctypes.byref(ctx)))
+        self._ctx = ctx
+        self.device = device
+        self._resident = None
+        self._finalizer = weakref.finalize(self, self._lib.tapir_cuda_destroy, ctx)
+
+    def close(self):
+        self._finalizer()
+
+    # ---- helpers ----
+    @staticmethod
+    def _prep(offsets, rates, n_grid, times, epochs, want_profile, flags):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        rates = np.ascontiguousarray(rates, dtype=np.float64)
+        time_idx = np.ascontiguousarray(np.asarray(times, dtype=np.int64).reshape(-1))
+        epoch_ab = np.ascontiguousarray(np.asarray(epochs, dtype=np.float64).reshape(-1))
+        if epoch_ab.size % 2:
+            raise ValueError("epochs must be (start, stop) pairs")
+        p = Problem()
+        p.n_loci = offsets.size - 1
+        p.offsets = offsets.ctypes.data
+        p.rates = rates.ctypes.data if rates.size else None
+        p.n_grid = int(n_grid)
+        p.n_times = time_idx.size
+        p.time_idx = time_idx.ctypes.data if time_idx.size else None
+        p.n_epochs = epoch_ab.size // 2
+        p.epoch_ab = epoch_ab.ctypes.data if epoch_ab.size else None
+        p.flags = int(flags) | (_lib.WANT_PROFILE if want_profile else 0)
+        return p, (offsets, rates, time_idx, epoch_ab)
+
+    @staticmethod
+    def _alloc_results(L, T, K, E, want_profile, pinned):
+        alloc = pinned_empty if pinned else np.empty
+        res = BatchResult(
+            pi_net=alloc((L, T), np.float64) if want_profile else None,
+            pi_times=alloc((L, K), np.float64),
+            integral=alloc((L, E), np.float64),
+            abserr=alloc((L, E), np.float64),
+            max_pi=alloc((L,), np.float64),
+            argmax_t=alloc((L,), np.int64),
+            argmax_epoch=alloc((L,), np.int32),
+            mean_rate=alloc((L,), np.float64),
+            n_finite=alloc((L,), np.int64),
+            n_multi_panel=alloc((L,), np.int64),
+        )
+        r = Results()
+        for name in _lib.RESULT_FIELDS:
+            arr = getattr(res, name)
+            setattr(r, name, arr.ctypes.data if arr is not None and arr.size else None)
+        return res, r
+
+    # ---- whole path, host buffers in / host buffers out ----
+    def run(self, offsets, rates, n_grid, times, epochs, want_profile=True, flags=0, out: BatchResult = None,
+            pinned_results=False):
+        """H2D + kernels + D2H for one CSR batch.  Raises TapirCudaError on any failure."""
+        p, keep = self._prep(offsets, rates, n_grid, times, epochs, want_profile, flags)
+        if out is None:
+            res, r = self._alloc_results(p.n_loci, p.n_grid, p.n_times, p.n_epochs, want_profile, pinned_results)
+        else:
+            res, r = out, Results()
+            for name in _lib.RESULT_FIELDS:
+                arr = getattr(res, name)
+                setattr(r, name, arr.ctypes.data if arr is not None and arr.size else None)
+        check(self._lib.tapir_cuda_run(self._ctx, ctypes.byref(p), ctypes.byref(r)), self._ctx)
+        del keep
+        return res
+
+    # ---- staged path ----
+    def upload(self, offsets, rates, n_grid, times, epochs, want_profile=True, flags=0):
+        p, keep = self._prep(offsets, rates, n_grid, times, epochs, want_profile, flags)
+        check(self._lib.tapir_cuda_upload(self._ctx, ctypes.byref(p)), self._ctx)
+        self._resident = (p.n_loci, p.n_grid, p.n_times, p.n_epochs, want_profile)
+        del keep
+
+    def compute(self) -> Timing:
+        t = Timing()
+        check(self._lib.tapir_cuda_compute(self._ctx, ctypes.byref(t)), self._ctx)
+        return t
+
+    def download(self, out: BatchResult = None, pinned_results=False) -> BatchResult:
+        if self._resident is None:
+            raise _lib.TapirCudaError(_lib.TAPIR_E_STATE, "download before upload")
+        L, T, K, E, want_profile = self._resident
+        if out is None:
+            res, r = self._alloc_results(L, T, K, E, want_profile, pinned_results)
+        else:
+            res, r = out, Results()
+            for name in _lib.RESULT_FIELDS:
+                arr = getattr(res, name)
+                setattr(r, name, arr.ctypes.data if arr is not None and arr.size else None)
+        check(self._lib.tapir_cuda_download(self._ctx, ctypes.byref(r)), self._ctx)
+        return res
+
+    def device_results(self) -> Results:
+        r = Results()
+        check(self._lib.tapir_cuda_device_results(self._ctx, ctypes.byref(r)), self._ctx)
+        return r
+
+    # ---- element-wise parity API ----
+    def pi_matrix(self, time, rates):
+        time = np.ascontiguousarray(np.asarray(time, dtype=np.float64).reshape(-1))
+        rates = np.ascontiguousarray(np.asarray(rates, dtype=np.float64).reshape(-1))
+        out = np.empty((time.size, rates.size), dtype=np.float64)
+        check(self._lib.tapir_cuda_pi_matrix(self._ctx, time.ctypes.data, time.size, rates.ctypes.data, rates.size,
+                                             out.ctypes.data), self._ctx)
+        return out
+
+    def site_integrals(self, a, b, rates):
+        rates = np.ascontiguousarray(np.asarray(rates, dtype=np.float64).reshape(-1))
+        integ = np.empty(rates.size)
+        err = np.empty(rates.size)
+        panels = np.empty(rates.size, dtype=np.int32)
+        check(self._lib.tapir_cuda_site_integrals(self._ctx, float(a), float(b), rates.ctypes.data, rates.size,
+                                                  integ.ctypes.data, err.ctypes.data, panels.ctypes.data), self._ctx)
+        return integ, err, panels
+
+    # ---- measurement helpers ----
+    def fp64_peak(self):
+        tf, ms = ctypes.c_double(), ctypes.c_float()
+        check(self._lib.tapir_cuda_fp64_peak(self._ctx, ctypes.byref(tf), ctypes.byref(ms)), self._ctx)
+        return tf.value, ms.value
+
+    def flush_l2(self):
+        check(self._lib.tapir_cuda_flush_l2(self._ctx), self._ctx)
+
+
+def device_count() -> int:
+    n = ctypes.c_int()
+    lib = _lib.load()
+    rc = lib.tapir_cuda_device_count(ctypes.byref(n))
+    return n.value if rc == 0 else 0

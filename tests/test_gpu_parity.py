@@ -1,0 +1,225 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against
+ (1) golden vectors generated from the reference's own compute.py (tests/golden),
+ (2) the CPU oracle (oracle/quadpack_port.c) on seeded inputs,
+ (3) size-independent properties at larger sizes.
+Tolerances are BASELINE.json's: pi_net / pi_times / integral <= 1e-9 relative (FP64 mode) with a
+1e-290 absolute floor for sums that underflow, identical argmax epoch.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+FLOOR = 1e-290
+
+
+def rel(a, b, floor=FLOOR):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / (np.abs(b) + floor)))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from tapir_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_library_loaded_and_device_present():
+    from tapir_b200 import engine
+    assert engine.device_count() >= 1
+
+
+def test_cfg1_bundled_golden(eng, golden):
+    g, meta = golden
+    rates = g["cfg1/rates"]
+    off = np.array([0, rates.size], dtype=np.int64)
+    res = eng.run(off, rates, 174, meta["times"], meta["epochs"])
+    assert rel(res.pi_net[0], g["cfg1/pi_net"]) < RTOL
+    assert rel(res.pi_times[0], g["cfg1/pi_times"]) < RTOL
+    assert rel(res.integral[0], g["cfg1/integral"]) < RTOL
+    np.testing.assert_allclose(res.abserr[0], g["cfg1/error"], rtol=1e-6)
+    assert res.argmax_epoch[0] == 3                      # '164-174' 
+    assert res.argmax_t[0] == 173 and rel(res.max_pi[0], 0.0013947599572823488) < RTOL
+    assert rel(res.mean_rate[0], g["cfg1/mean_rate"]) < 1e-12
+    assert res.n_finite[0] == 100 and res.n_multi_panel[0] == 0
+
+
+def test_unit_shape_phydesign(eng, golden):
+    """tapir/tests/test_compute.py:44-71 through the GPU path (cf = 1, T = 174)."""
+    g, meta = golden
+    rates = g["bundled_rates"]
+    off = np.array([0, rates.size], dtype=np.int64)
+    spans = [list(map(int, s)) for s in g["unit/spans"]]
+    res = eng.run(off, rates, 174, [10, 20, 50], spans)
+    for k, want in enumerate(meta["phydesign_net_t10_20_50"]):
+        assert round(abs(res.pi_times[0, k] - want), 3) == 0
+    for k, want in enumerate(meta["phydesign_integrals"]):
+        assert round(abs(res.integral[0, k] - want), 4) == 0
+    assert rel(res.pi_net[0], g["unit/pi_net_sum"]) < RTOL
+    assert rel(res.integral[0], g["unit/sum_integral"]) < RTOL
+    assert res.n_multi_panel[0] >= 1                     # [20,100], site rate 0.1 needs > 1 panel
+
+
+@pytest.mark.parametrize("tag", ["synA", "synB"])
+def test_synthetic_golden(eng, golden, tag):
+    g, _ = golden
+    off, rates, T = g[tag + "/offsets"], g[tag + "/rates"], int(g[tag + "/T"])
+    res = eng.run(off, rates, T, g[tag + "/times"], g[tag + "/epochs"])
+    assert rel(res.pi_net, g[tag + "/pi_net"]) < RTOL
+    assert rel(res.pi_times, g[tag + "/pi_times"]) < RTOL
+    assert rel(res.integral, g[tag + "/integral"]) < RTOL
+    np.testing.assert_allclose(res.abserr, g[tag + "/error"], rtol=1e-6, atol=1e-300)
+    assert np.array_equal(res.argmax_epoch, np.argmax(g[tag + "/integral"], axis=1))
+    assert np.array_equal(res.argmax_t, np.argmax(g[tag + "/pi_net"], axis=1))
+    assert rel(res.mean_rate, g[tag + "/mean_rate"]) < 1e-12
+    finite = [int(np.isfinite(rates[off[l]:off[l + 1]]).sum()) for l in range(off.size - 1)]
+    assert list(res.n_finite) == finite
+
+
+@pytest.mark.parametrize("T", [1, 7, 174, 256, 300, 512, 1000, 1024, 1025, 2048, 2500, 5000])
+def test_profile_vs_oracle_all_tile_variants(eng, T):
+    from oracle import capi
+    from tapir_b200 import synthetic
+    rng = np.random.default_rng(100 + T)
+    loci = [synthetic.uce_rates(rng, n, max(T, 50), nan_frac=0.05) for n in (1, 31, 32, 33, 257, 700)]
+    loci.append(rng.uniform(0.0, 2.0, size=90))         # fast sites: deep underflow of q^t
+    from tapir_b200.engine import pack_csr
+    off, rates = pack_csr(loci, pinned=False)
+    epochs = [[0, 10], [3, 40]]
+    times = [0, T - 1, T // 2]
+    res = eng.run(off, rates, T, times, epochs)
+    pi_net, si, se = capi.batch(off, rates, T, epochs)
+    assert rel(res.pi_net, pi_net) < RTOL
+    assert rel(res.integral, si) < RTOL
+    np.testing.assert_allclose(res.abserr, se, rtol=1e-6, atol=1e-300)
+    assert np.array_equal(res.pi_times, res.pi_net[:, times])
+    assert np.array_equal(res.argmax_t, np.argmax(res.pi_net, axis=1))
+    assert np.array_equal(res.max_pi, np.max(res.pi_net, axis=1))
+    assert np.array_equal(res.argmax_epoch, np.argmax(si, axis=1))
+
+
+def test_split_sites_path(eng):
+    """Few loci with many sites: the (locus, tile) work is split over site ranges and reduced in a fixed order."""
+    from oracle import capi
+    from tapir_b200 import synthetic
+    rng = np.random.default_rng(7)
+    T = 1500
+    loci = [synthetic.uce_rates(rng, n, T, nan_frac=0.02) for n in (300000, 123457)]
+    from tapir_b200.engine import pack_csr
+    off, rates = pack_csr(loci, pinned=False)
+    res = eng.run(off, rates, T, [5, -1], synthetic.EPOCHS)
+    # oracle on a subset of grid points (the full profile would take minutes on one core)
+    for l in range(2):
+        lam = rates[off[l]:off[l + 1]]
+        lam = lam[np.isfinite(lam)]
+        for t in (0, 1, 5, 700, 1023, 1024, 1499):
+            want = float(np.sum(16 * lam * lam * t * np.exp(-4 * lam * t)))
+            assert abs(res.pi_net[l, t] - want) <= 1e-9 * abs(want) + FLOOR
+    res2 = eng.run(off, rates, T, [5, -1], synthetic.EPOCHS)
+    assert np.array_equal(res.pi_net, res2.pi_net) and np.array_equal(res.integral, res2.integral)  # deterministic
+    si, se, _ = capi.epochs(rates[off[1]:off[2]], synthetic.EPOCHS)
+    assert rel(res.integral[1], si) < RTOL
+    assert np.array_equal(res.pi_times[:, 1], res.pi_net[:, T - 1])
+
+
+def test_properties_cfg2_full_size(eng):
+    """BASELINE config 2 at full size: properties that need no CPU reference."""
+    from tapir_b200 import synthetic
+    off, rates, T = synthetic.build("cfg2")
+    res = eng.run(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+    L = off.size - 1
+    assert res.pi_net.shape == (L, T) and np.all(np.isfinite(res.pi_net)) and np.all(res.pi_net[:, 0] == 0.0)
+    # (a) site order does not matter beyond rounding; (b) additivity: a locus made of two loci's sites
+    perm = np.random.default_rng(0).permutation(500)
+    a, b = rates[:500], rates[500:1000]
+    off2 = np.array([0, 500, 1500], dtype=np.int64)
+    r2 = np.concatenate([a[perm], a, b])
+    res2 = eng.run(off2, r2, T, synthetic.TIMES, synthetic.EPOCHS)
+    assert rel(res2.pi_net[0], res.pi_net[0]) < 1e-12
+    assert rel(res2.pi_net[1], res.pi_net[0] + res.pi_net[1]) < 1e-12
+    assert rel(res2.integral[1], res.integral[0] + res.integral[1]) < 1e-12
+    # (c) scaling: PI(t; r) summed over sites vs a direct numpy evaluation on sampled loci
+    for l in (0, 1234, L - 1):
+        lam = rates[off[l]:off[l + 1]]
+        t = np.arange(T)[:, None]
+        want = np.sum(16 * lam**2 * t * np.exp(-4 * lam * t), axis=1)
+        assert rel(res.pi_net[l], want) < RTOL
+    assert np.array_equal(res.argmax_t, np.argmax(res.pi_net, axis=1))
+    assert np.array_equal(res.argmax_epoch, np.argmax(res.integral, axis=1))
+
+
+def test_edge_cases(eng):
+    from tapir_b200 import synthetic
+    from tapir_b200._lib import TapirCudaError
+    ep, tm = synthetic.EPOCHS, [0]
+    # empty batch
+    res = eng.run(np.zeros(1, np.int64), np.zeros(0), 100, tm, ep)
+    assert res.pi_net.shape == (0, 100)
+    # empty locus, all-NaN locus, all-zero locus, single site
+    nan = np.full(5, np.nan)
+    off = np.array([0, 0, 5, 9, 10], dtype=np.int64)
+    rates = np.concatenate([nan, np.zeros(4), [0.01]])
+    res = eng.run(off, rates, 100, tm, ep)
+    assert np.all(res.pi_net[:3] == 0.0) and np.all(res.integral[:3] == 0.0)
+    assert list(res.n_finite) == [0, 0, 4, 1]
+    assert np.isnan(res.mean_rate[0]) and np.isnan(res.mean_rate[1]) and res.mean_rate[2] == 0.0
+    t = np.arange(100)
+    assert rel(res.pi_net[3], 16 * 0.01**2 * t * np.exp(-4 * 0.01 * t)) < RTOL
+    # no times / no epochs / no grid
+    res = eng.run(off, rates, 100, [], [])
+    assert res.pi_times.shape == (4, 0) and res.integral.shape == (4, 0) and np.all(res.argmax_epoch == -1)
+    res = eng.run(off, rates, 0, [], ep)
+    assert res.pi_net.shape == (4, 0) and res.integral.shape == (4, 4)
+    # error behaviour mirrors the reference: a >= b asserts (compute.py:90), bad index raises (compute.py:78)
+    with pytest.raises(TapirCudaError):
+        eng.run(off, rates, 100, tm, [[10, 10]])
+    with pytest.raises(TapirCudaError):
+        eng.run(off, rates, 100, [100], ep)
+    with pytest.raises(TapirCudaError):
+        eng.run(np.array([0, 5, 3], dtype=np.int64), rates, 100, tm, ep)
+    # negative index wraps like numpy
+    res = eng.run(off, rates, 100, [-1, -100], ep)
+    assert np.array_equal(res.pi_times[:, 0], res.pi_net[:, 99]) and np.array_equal(res.pi_times[:, 1], res.pi_net[:, 0])
+
+
+def test_many_epochs_and_mixed_widths(eng):
+    from oracle import capi
+    rng = np.random.default_rng(5)
+    rates = np.concatenate([rng.gamma(0.5, 0.004, 400), [0.3, 1.5, 4.0]])
+    off = np.array([0, rates.size], dtype=np.int64)
+    epochs = [[i, i + w] for i, w in zip(range(0, 170, 9), [10, 3, 10, 25, 7] * 4)]
+    res = eng.run(off, rates, 50, [1], epochs, want_profile=False)
+    assert res.pi_net is None
+    si, se, _ = capi.epochs(rates, epochs)
+    assert rel(res.integral[0], si) < RTOL
+    np.testing.assert_allclose(res.abserr[0], se, rtol=1e-6, atol=1e-300)
+    assert res.argmax_epoch[0] == int(np.argmax(si))
+
+
+def test_elementwise_api(eng, golden):
+    g, _ = golden
+    t = np.arange(0, 174, dtype=np.float64)
+    pi = eng.pi_matrix(t, g["cfg1/rates"])
+    assert pi.shape == (174, 100) and rel(pi, g["cfg1/pi"], floor=1e-300) < 1e-14
+    for k, (a, b) in enumerate(g["unit/spans"]):
+        integ, err, panels = eng.site_integrals(a, b, g["bundled_rates"])
+        assert rel(integ, g["unit/site_integral"][k]) < RTOL
+        np.testing.assert_allclose(err, g["unit/site_error"][k], rtol=1e-6, atol=1e-300)
+    assert panels.max() > 1
+
+
+def test_staged_api_matches_run(eng):
+    from tapir_b200 import synthetic
+    off, rates, T = synthetic.build("cfg2", scale=0.02)
+    a = eng.run(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+    eng.upload(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+    tm = eng.compute()
+    assert tm.launches == 3 and tm.total_ms > 0
+    b = eng.download()
+    for name in ("pi_net", "pi_times", "integral", "abserr", "max_pi", "argmax_t", "argmax_epoch"):
+        assert np.array_equal(getattr(a, name), getattr(b, name))
