@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- Townsend-PI hot path on B200: site*timepoint PI evals/s and loci/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" is one pass of the whole hot path (PI profile + --times picks + GK21/QAGS epoch
+integrals + per-locus maxima) over one batch of synthetic loci.  At N = 1 the batch is
+BASELINE.json configs[1] (5,000 loci x 500 sites, 1,000-point grid, 4 epochs); at N > 1 every
+rank owns one such shard (weak scaling; loci are independent, bin/tapir_compute.py:159-164) and
+the small per-locus result vectors are gathered to rank 0 over NCCL.
+
+Printed keys (one JSON line, rank 0):
+  value    evals/s with inputs resident in HBM, kernels timed by CUDA events on the library's stream
+  e2e      the same metric through the C-ABI call with HOST buffers: pinned H2D + kernels + D2H
+  roofline FP64-pipe roofline of the dominant kernel (profile_kernel), see DESIGN.md
+  cpu_baseline  the reference's CPU path (numpy + scipy quad port, Pool(cpu_count-1)) on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "site*timepoint PI evals/sec"
+UNIT = "evals/s"
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's own algorithm (oracle port: numpy ufuncs + scipy.integrate.quad),
+# mapped over loci with multiprocessing.Pool(cpu_count()-1) as bin/tapir_compute.py:162-164 does.
+# --------------------------------------------------------------------------------------------
+_CPU_STATE = {}
+
+
+def _cpu_init(T, times, epochs):
+    from oracle import townsend_port as tp
+    _CPU_STATE["tp"] = tp
+    _CPU_STATE["tcol"] = tp.time_column(0, T)
+    _CPU_STATE["times"] = times
+    _CPU_STATE["epochs"] = epochs
+
+
+def _cpu_worker(lam):
+    import warnings
+    tp = _CPU_STATE["tp"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # returns the full (T,S) matrix through the pool pipe, as the reference's worker does
+        return tp.locus_worker(_CPU_STATE["tcol"], lam, _CPU_STATE["times"], _CPU_STATE["epochs"], keep_matrix=True)
+
+
+def cpu_reference_pass(offsets, rates, T, times, epochs, n_loci, pool):
+    loci = [rates[offsets[l]:offsets[l + 1]] for l in range(n_loci)]
+    t0 = time.perf_counter()
+    out = pool.map(_cpu_worker, loci)
+    dt = time.perf_counter() - t0
+    evals = int(offsets[n_loci] - offsets[0]) * T
+    return dt, evals, out
+
+
+def make_pool(T, times, epochs):
+    import multiprocessing as mp
+    workers = max(1, (os.cpu_count() or 2) - 1)
+    ctx = mp.get_context("fork")
+    return ctx.Pool(processes=workers, initializer=_cpu_init, initargs=(T, times, epochs)), workers
+
+
+def cpu_baseline(offsets, rates, T, times, epochs, budget_s=15.0):
+    """Bounded sample: calibrate on one pool round, then size the sample for ~budget_s seconds."""
+    pool, workers = make_pool(T, times, epochs)
+    try:
+        L = offsets.size - 1
+        n0 = min(L, workers)
+        dt0, _, _ = cpu_reference_pass(offsets, rates, T, times, epochs, n0, pool)
+        per_round = max(dt0, 1e-3)
+        n = int(min(L, max(n0, workers * int(budget_s / per_round))))
+        dt, evals, _ = cpu_reference_pass(offsets, rates, T, times, epochs, n, pool)
+    finally:
+        pool.close()
+        pool.join()
+    return {
+        "value": evals / dt, "unit": UNIT, "cores": workers, "kind": "port",
+        "loci_per_s": n / dt,
+        "sample": "first %d of %d loci of the same batch, %.1f s wall, Pool(%d) over numpy+scipy.quad port "
+                  "(oracle/townsend_port.py), full (T,S) matrix returned through the pool pipe as the reference does"
+                  % (n, L, dt, workers),
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.thread, self.idx = [], None, None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        # "under load": samples within 60 % of the busiest clock seen
+        hi = max(sm)
+        load = [x for x in sm if x >= 0.6 * hi]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured"
+    except OSError:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the CPU path alone, rank 0 only."""
+    if rank != 0:
+        return
+    from tapir_b200 import synthetic
+    off, rates, T = synthetic.build(args.workload)
+    times, epochs = synthetic.TIMES, synthetic.EPOCHS
+    pool, workers = make_pool(T, times, epochs)
+    L = off.size - 1
+    try:
+        # size one step for ~8 s so that steps + warmup finish within a few minutes
+        dt0, _, _ = cpu_reference_pass(off, rates, T, times, epochs, min(L, workers), pool)
+        n = int(min(L, max(workers, workers * int(8.0 / max(dt0, 1e-3)))))
+        for _ in range(args.warmup):
+            cpu_reference_pass(off, rates, T, times, epochs, min(n, workers), pool)
+        tot_t = tot_e = 0.0
+        for _ in range(args.steps):
+            dt, evals, _ = cpu_reference_pass(off, rates, T, times, epochs, n, pool)
+            tot_t += dt
+            tot_e += evals
+    finally:
+        pool.close()
+        pool.join()
+    value = tot_e / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "sample_loci_per_step": n, "timing": "host wall clock"},
+        "loci_per_s": n * args.steps / tot_t,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": "%d of %d loci per step, Pool(%d), numpy+scipy.quad port of tapir/compute.py" % (n, L, workers)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_name(w):
+    from tapir_b200 import synthetic
+    c = synthetic.CONFIGS[w]
+    if c["kind"] == "uniform":
+        return "%s: synthetic %d loci x %d sites, %d-point grid, 4 epochs, 4 times" % (w, c["n_loci"], c["n_sites"], c["T"])
+    return "%s: synthetic %d loci x ~%d sites (ragged %d-%d), %d-point grid, 4 epochs, 4 times" % (
+        w, c["n_loci"], c["mean_sites"], c["smin"], c["smax"], c["T"])
+
+
+def run_ours(args, rank, world, local_rank):
+    from tapir_b200 import synthetic
+    from tapir_b200.engine import Engine, pinned_empty
+
+    times, epochs = synthetic.TIMES, synthetic.EPOCHS
+    # every rank owns one shard of the global batch (same shape, different seed)
+    cfg = dict(synthetic.CONFIGS[args.workload])
+    cfg["seed"] = cfg["seed"] * 1000 + rank
+    synthetic.CONFIGS["_shard"] = cfg
+    off_np, rates_np, T = synthetic.build("_shard")
+    L, nnz = off_np.size - 1, rates_np.size
+    evals_rank = nnz * T
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(off_np, rates_np, T, times, epochs)   # before any CUDA call (fork safety)
+
+    dist = torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    eng = Engine(local_rank)
+    offsets = pinned_empty(off_np.shape, np.int64); offsets[:] = off_np
+    rates = pinned_empty(rates_np.shape, np.float64); rates[:] = rates_np
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- small-result gather over NCCL (N > 1): one packed [L, K+2E+4] matrix per rank ----
+    gather = None
+    if dist is not None:
+        K, E = len(times), len(epochs)
+
+        class _Dev:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+        def gather():
+            r = eng.device_results()
+            cols = [torch.as_tensor(_Dev(r.pi_times, (L, K), "<f8"), device="cuda"),
+                    torch.as_tensor(_Dev(r.integral, (L, E), "<f8"), device="cuda"),
+                    torch.as_tensor(_Dev(r.abserr, (L, E), "<f8"), device="cuda"),
+                    torch.as_tensor(_Dev(r.max_pi, (L, 1), "<f8"), device="cuda"),
+                    torch.as_tensor(_Dev(r.argmax_t, (L, 1), "<i8"), device="cuda").double(),
+                    torch.as_tensor(_Dev(r.argmax_epoch, (L, 1), "<i4"), device="cuda").double(),
+                    torch.as_tensor(_Dev(r.mean_rate, (L, 1), "<f8"), device="cuda")]
+            packed = torch.cat(cols, dim=1).contiguous()
+            dst = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
+            dist.gather(packed, dst, dst=0)
+            return dst
+
+    # ---- device-resident timing ----
+    eng.upload(offsets, rates, T, times, epochs, want_profile=True)
+    for _ in range(max(args.warmup, 3)):
+        eng.compute()
+        if gather:
+            gather()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    dev_ms, prof_ms, quad_ms, fin_ms, gather_ms, launches = 0.0, 0.0, 0.0, 0.0, 0.0, 0
+    for _ in range(args.steps):
+        eng.flush_l2()                      # untimed: the step starts with a cold L2
+        tm = eng.compute()                  # CUDA events on the library stream, synchronised on both sides
+        dev_ms += tm.total_ms; prof_ms += tm.profile_ms; quad_ms += tm.quad_ms; fin_ms += tm.finalize_ms
+        launches += tm.launches
+        if gather:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gather(); e1.record(); torch.cuda.synchronize()
+            gather_ms += e0.elapsed_time(e1)
+    barrier()
+    step_ms = (dev_ms + gather_ms) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public call: pinned host in, pinned host out ----
+    out = eng.run(offsets, rates, T, times, epochs, want_profile=True, pinned_results=True)   # allocates + warms
+    for _ in range(2):
+        eng.run(offsets, rates, T, times, epochs, want_profile=True, out=out)
+    h0, d0 = eng.transfer_bytes()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.run(offsets, rates, T, times, epochs, want_profile=True, out=out)
+        if gather:
+            dst = gather()
+            if rank == 0:
+                _ = [d.cpu() for d in dst]
+            torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    h1, d1 = eng.transfer_bytes()
+    checksum = float(out.integral.sum())
+
+    peak_tf, _ = eng.fp64_peak()
+
+    if dist is not None:
+        t = torch.tensor([step_ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, e2e_s = float(t[0]), float(t[1])
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    total_evals = evals_rank * world
+    total_loci = L * world
+    peaks, peak_src = measured_peaks()
+    prof_s = prof_ms / args.steps * 1e-3
+    achieved_tf = 2.0 * evals_rank / prof_s / 1e12        # one FP64 FMA per (site, timepoint): DESIGN.md
+    line = {
+        "metric": METRIC, "value": total_evals / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload) + (" per GPU" if world > 1 else ""),
+                   "loci_per_gpu": L, "grid": T, "epochs": epochs, "times": times,
+                   "cache": "L2 flushed (256 MB memset) before every timed step",
+                   "timing": "CUDA events on the launching stream per step, max over ranks",
+                   "parallelism": "locus-sharded x%d, NCCL gather of per-locus vectors" % world if world > 1 else "single GPU"},
+        "loci_per_s": total_loci / (step_ms * 1e-3),
+        "kernel_ms": {"profile": prof_ms / args.steps, "quad": quad_ms / args.steps, "finalize": fin_ms / args.steps,
+                      "gather": gather_ms / args.steps},
+        "roofline": {
+            "bound": "fp64", "kernel": "profile_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+            "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
+            "algorithmic": "2 flop (1 DFMA) per site*timepoint",
+            "hbm": {"achieved_gbs": 8.0 * nnz / prof_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src,
+                    "note": "rate stream, 8 B per site per time tile"},
+        },
+        "e2e": {"value": total_evals / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": (h1 - h0) // args.steps, "d2h_bytes_per_step": (d1 - d0) // args.steps,
+                "loci_per_s": total_loci / e2e_s, "timing": "host wall clock around tapir_cuda_run, pinned buffers"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "checksum": checksum,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,9 @@ int tapir_cuda_download(tapir_cuda_ctx *ctx, const tapir_results *host_out);
 /* device pointers of the resident result arrays (valid until the next upload/destroy) */
 int tapir_cuda_device_results(tapir_cuda_ctx *ctx, tapir_results *device_ptrs);
 
+/* bytes moved host->device / device->host by this context since creation (for bench.py's e2e accounting) */
+int tapir_cuda_transfer_bytes(tapir_cuda_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
+
 /* --- element-wise API parity with tapir.compute --- */
 /* get_townsend_pi(time, rates) -> out[T*S] row-major (T,S); NaN propagate as numpy does */
 int tapir_cuda_pi_matrix(tapir_cuda_ctx *ctx, const double *time, int64_t n_time, const double *rates,

@@ -106,6 +106,7 @@ struct tapir_cuda_ctx {
         d_n_multi;
     DevBuf d_scratch_a, d_scratch_b, d_scratch_c, d_flush;
     HostBuf h_stage;
+    uint64_t bytes_h2d = 0, bytes_d2h = 0;
 };
 
 namespace {
@@ -499,6 +500,7 @@ int tapir_cuda_upload(tapir_cuda_ctx* ctx, const tapir_problem* p)
     CU(ctx, ctx->d_n_multi.ensure(size_t(L) * 8 + 8));
 
     cudaStream_t st = ctx->stream;
+    ctx->bytes_h2d += size_t(plan.nnz) * 8 + b_prof + b_quad + b_ns + b_wb + b_qb + b_ti;
     if (plan.nnz) CU(ctx, cudaMemcpyAsync(ctx->d_rates.p, p->rates, size_t(plan.nnz) * 8, cudaMemcpyHostToDevice, st));
     if (b_prof) CU(ctx, cudaMemcpyAsync(ctx->d_prof_items.p, hs + o_prof, b_prof, cudaMemcpyHostToDevice, st));
     if (b_quad) CU(ctx, cudaMemcpyAsync(ctx->d_quad_items.p, hs + o_quad, b_quad, cudaMemcpyHostToDevice, st));
@@ -617,6 +619,7 @@ int tapir_cuda_download(tapir_cuda_ctx* ctx, const tapir_results* out)
     const size_t L = size_t(plan.L);
     auto copy = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t {
         if (!dst || bytes == 0) return cudaSuccess;
+        ctx->bytes_d2h += bytes;
         return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, st);
     };
     if (plan.flags & TAPIR_WANT_PROFILE) CU(ctx, copy(out->pi_net, ctx->d_pi_net, L * size_t(plan.T) * 8));
@@ -647,6 +650,14 @@ int tapir_cuda_device_results(tapir_cuda_ctx* ctx, tapir_results* d)
     d->mean_rate = ctx->d_mean_rate.as<double>();
     d->n_finite = ctx->d_n_finite.as<int64_t>();
     d->n_multi_panel = ctx->d_n_multi.as<int64_t>();
+    return TAPIR_OK;
+}
+
+int tapir_cuda_transfer_bytes(tapir_cuda_ctx* ctx, uint64_t* h2d, uint64_t* d2h)
+{
+    if (!ctx) return fail(nullptr, TAPIR_E_INVALID, "null context");
+    if (h2d) *h2d = ctx->bytes_h2d;
+    if (d2h) *d2h = ctx->bytes_d2h;
     return TAPIR_OK;
 }
 

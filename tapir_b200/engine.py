@@ -204,6 +204,11 @@ class Engine:
         return integ, err, panels
 
     # ---- measurement helpers ----
+    def transfer_bytes(self):
+        h2d, d2h = ctypes.c_uint64(), ctypes.c_uint64()
+        check(self._lib.tapir_cuda_transfer_bytes(self._ctx, ctypes.byref(h2d), ctypes.byref(d2h)), self._ctx)
+        return h2d.value, d2h.value
+
     def fp64_peak(self):
         tf, ms = ctypes.c_double(), ctypes.c_float()
         check(self._lib.tapir_cuda_fp64_peak(self._ctx, ctypes.byref(tf), ctypes.byref(ms)), self._ctx)

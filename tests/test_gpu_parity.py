@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-9
 FLOOR = 1e-290
+# sum(error) column: QUADPACK's estimate is resasc*min(1,(200|resk-resg|h/resasc)^1.5), i.e. it amplifies the
+# rounding of a cancelling difference; SURVEY 8d asks for "same order of magnitude (exact when single-panel)".
+ERR_RTOL = 1e-3
 
 
 def rel(a, b, floor=FLOOR):
@@ -42,7 +45,7 @@ def test_cfg1_bundled_golden(eng, golden):
     assert rel(res.pi_net[0], g["cfg1/pi_net"]) < RTOL
     assert rel(res.pi_times[0], g["cfg1/pi_times"]) < RTOL
     assert rel(res.integral[0], g["cfg1/integral"]) < RTOL
-    np.testing.assert_allclose(res.abserr[0], g["cfg1/error"], rtol=1e-6)
+    np.testing.assert_allclose(res.abserr[0], g["cfg1/error"], rtol=1e-9)
     assert res.argmax_epoch[0] == 3                      # '164-174' 
     assert res.argmax_t[0] == 173 and rel(res.max_pi[0], 0.0013947599572823488) < RTOL
     assert rel(res.mean_rate[0], g["cfg1/mean_rate"]) < 1e-12
@@ -73,10 +76,10 @@ def test_synthetic_golden(eng, golden, tag):
     assert rel(res.pi_net, g[tag + "/pi_net"]) < RTOL
     assert rel(res.pi_times, g[tag + "/pi_times"]) < RTOL
     assert rel(res.integral, g[tag + "/integral"]) < RTOL
-    np.testing.assert_allclose(res.abserr, g[tag + "/error"], rtol=1e-6, atol=1e-300)
+    np.testing.assert_allclose(res.abserr, g[tag + "/error"], rtol=ERR_RTOL, atol=1e-300)
     assert np.array_equal(res.argmax_epoch, np.argmax(g[tag + "/integral"], axis=1))
     assert np.array_equal(res.argmax_t, np.argmax(g[tag + "/pi_net"], axis=1))
-    assert rel(res.mean_rate, g[tag + "/mean_rate"]) < 1e-12
+    np.testing.assert_allclose(res.mean_rate, g[tag + "/mean_rate"], rtol=1e-12)   # inf == inf (the +Inf site)
     finite = [int(np.isfinite(rates[off[l]:off[l + 1]]).sum()) for l in range(off.size - 1)]
     assert list(res.n_finite) == finite
 
@@ -96,7 +99,7 @@ def test_profile_vs_oracle_all_tile_variants(eng, T):
     pi_net, si, se = capi.batch(off, rates, T, epochs)
     assert rel(res.pi_net, pi_net) < RTOL
     assert rel(res.integral, si) < RTOL
-    np.testing.assert_allclose(res.abserr, se, rtol=1e-6, atol=1e-300)
+    np.testing.assert_allclose(res.abserr, se, rtol=ERR_RTOL, atol=1e-300)
     assert np.array_equal(res.pi_times, res.pi_net[:, times])
     assert np.array_equal(res.argmax_t, np.argmax(res.pi_net, axis=1))
     assert np.array_equal(res.max_pi, np.max(res.pi_net, axis=1))
@@ -197,7 +200,7 @@ def test_many_epochs_and_mixed_widths(eng):
     assert res.pi_net is None
     si, se, _ = capi.epochs(rates, epochs)
     assert rel(res.integral[0], si) < RTOL
-    np.testing.assert_allclose(res.abserr[0], se, rtol=1e-6, atol=1e-300)
+    np.testing.assert_allclose(res.abserr[0], se, rtol=ERR_RTOL, atol=1e-300)
     assert res.argmax_epoch[0] == int(np.argmax(si))
 
 
@@ -206,11 +209,13 @@ def test_elementwise_api(eng, golden):
     t = np.arange(0, 174, dtype=np.float64)
     pi = eng.pi_matrix(t, g["cfg1/rates"])
     assert pi.shape == (174, 100) and rel(pi, g["cfg1/pi"], floor=1e-300) < 1e-14
+    most = 0
     for k, (a, b) in enumerate(g["unit/spans"]):
         integ, err, panels = eng.site_integrals(a, b, g["bundled_rates"])
         assert rel(integ, g["unit/site_integral"][k]) < RTOL
-        np.testing.assert_allclose(err, g["unit/site_error"][k], rtol=1e-6, atol=1e-300)
-    assert panels.max() > 1
+        np.testing.assert_allclose(err, g["unit/site_error"][k], rtol=ERR_RTOL, atol=1e-300)
+        most = max(most, int(panels.max()))
+    assert most == 2                                     # [20,100] at rate 0.1 bisects once (oracle: last = 2)
 
 
 def test_staged_api_matches_run(eng):
