@@ -79,10 +79,10 @@ def cpu_baseline(offsets, rates, T, times, epochs, budget_s=15.0):
     pool, workers = make_pool(T, times, epochs)
     try:
         L = offsets.size - 1
-        n0 = min(L, workers)
+        n0 = min(L, 4 * workers)
+        cpu_reference_pass(offsets, rates, T, times, epochs, min(L, workers), pool)      # fork + import warm-up
         dt0, _, _ = cpu_reference_pass(offsets, rates, T, times, epochs, n0, pool)
-        per_round = max(dt0, 1e-3)
-        n = int(min(L, max(n0, workers * int(budget_s / per_round))))
+        n = int(min(L, max(n0, n0 * budget_s / max(dt0, 1e-3))))
         dt, evals, _ = cpu_reference_pass(offsets, rates, T, times, epochs, n, pool)
     finally:
         pool.close()
@@ -100,56 +100,57 @@ def cpu_baseline(offsets, rates, T, times, epochs, budget_s=15.0):
 # clocks
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML every few ms on a host thread while the timed
+    region runs (a step is well under a millisecond, far below nvidia-smi's polling period)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.thread, self.idx = [], None, None, gpu_index
+    def __init__(self, gpu_index=0, period_s=0.002):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.mask, self.smax = [], 0, None
+        self._stop = threading.Event()
+        self.thread = None
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.idx
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[self.idx])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
             return
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        if not self.proc:
+        if self.nv is None or self.thread is None:
             return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        self._stop.set()
+        self.thread.join(timeout=2)
+        if not self.sm:
             return None
-        # "under load": samples within 60 % of the busiest clock seen
-        hi = max(sm)
-        load = [x for x in sm if x >= 0.6 * hi]
-        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        hi = max(self.sm)
+        load = [x for x in self.sm if x >= 0.6 * hi]    # "under load": within 60 % of the busiest clock seen
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": self.smax,
+                "reasons": sorted(k for k, bit in self.REASONS.items() if self.mask & bit),
+                "samples": len(self.sm), "source": "NVML, %.0f ms period, sampled over the timed loops" % (self.period * 1e3)}
 
 
 def measured_peaks():
@@ -172,8 +173,10 @@ def run_reference(args, rank, world):
     L = off.size - 1
     try:
         # size one step for ~8 s so that steps + warmup finish within a few minutes
-        dt0, _, _ = cpu_reference_pass(off, rates, T, times, epochs, min(L, workers), pool)
-        n = int(min(L, max(workers, workers * int(8.0 / max(dt0, 1e-3)))))
+        cpu_reference_pass(off, rates, T, times, epochs, min(L, workers), pool)           # fork + import warm-up
+        n0 = min(L, 4 * workers)
+        dt0, _, _ = cpu_reference_pass(off, rates, T, times, epochs, n0, pool)
+        n = int(min(L, max(n0, n0 * 8.0 / max(dt0, 1e-3))))
         for _ in range(args.warmup):
             cpu_reference_pass(off, rates, T, times, epochs, min(n, workers), pool)
         tot_t = tot_e = 0.0
@@ -284,7 +287,6 @@ def run_ours(args, rank, world, local_rank):
             gather_ms += e0.elapsed_time(e1)
     barrier()
     step_ms = (dev_ms + gather_ms) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public call: pinned host in, pinned host out ----
     out = eng.run(offsets, rates, T, times, epochs, want_profile=True, pinned_results=True)   # allocates + warms
@@ -302,6 +304,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps
     h1, d1 = eng.transfer_bytes()
+    clocks = sampler.stop() if rank == 0 else None
     checksum = float(out.integral.sum())
 
     peak_tf, _ = eng.fp64_peak()

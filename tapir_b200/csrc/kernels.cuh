@@ -8,12 +8,17 @@
 // The profile is evaluated as a blocked Vandermonde product instead of one exp per
 // (site, time): with t = T0 + hi*32 + lo,
 //        a q^t = [a e^{-c T0} q^lo] * [(q^32)^hi] = U[lo] * W[hi],
-// so one warp owns a 32 x H time tile of one locus, builds the two short power tables of 32
-// sites in shared memory (one exp per site plus DMUL chains), and then spends one FP64 FMA per
-// (site, time) in a register-blocked outer product.  All arithmetic is IEEE double.
+// so pi_net[lo,hi] / t = sum_s U[s][lo] W[s][hi] is a dense FP64 contraction over sites.  One warp
+// owns a 32 x H time tile of one locus, builds the two short power tables of 32 sites in shared
+// memory (one exp per site plus DMUL chains), and contracts them with the FP64 MMA
+// (mma.sync m8n8k4 -> DMMA.8x8x4): one FP64 FMA per (site, time), 256 per instruction.  DMMA and
+// DFMA share one pipe on B200 (tools/microbench/fp64_pipes.cu: 37.0 vs 36.6 TFLOP/s, not additive);
+// the MMA form is used because it needs 8x fewer issue slots and a third of the shared-memory
+// fetches of a register-blocked DFMA outer product.  All arithmetic is IEEE double.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "fastexp.cuh"
 #include "gk21.cuh"
 
 namespace tapir {
@@ -69,9 +74,9 @@ struct ProfArgs {
 
 template <int RH>
 struct ProfCfg {
-    static constexpr int H = 8 * RH;            // hi extent
+    static constexpr int H = 8 * RH;            // hi extent = RH n-tiles of the 8x8x4 FP64 MMA
     static constexpr int TT = kB * H;           // times per tile
-    static constexpr int WStride = H + 2;
+    static constexpr int WStride = (RH == 1) ? 12 : H + 2;
     static constexpr int WarpDoubles = 32 * (kUStride + WStride);
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
     // resident 4-warp CTAs per SM the register budget is sized for (shared memory allows 3 / 2 at RH = 4 / 8)
@@ -83,6 +88,29 @@ __device__ __forceinline__ void st_shared_v2(double* p, double x, double y)
     *reinterpret_cast<double2*>(p) = make_double2(x, y);
 }
 
+// D(8x8) += A(8x4, row) * B(4x8, col) in IEEE double on the FP64 MMA path (SASS: DMMA.8x8x4).
+// Fragment layout (PTX ISA, mma.m8n8k4 .f64): with g = lane >> 2 and k = lane & 3 a lane holds
+// A[g][k], B[k][g] and D[g][2k], D[g][2k+1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+
+// Row/column g of an MMA tile is mapped to a chunk of consecutive table entries so that one lane
+// fetches its fragments for all m- (n-) tiles with 16-byte loads; the chunk order is permuted so that
+// the 8 lanes of a quarter warp (k = 0..3, two values of g) touch 8 distinct 16-byte bank groups.
+__device__ __forceinline__ int chunk_pair(int g) { return (g & 4) | ((g & 1) << 1) | ((g >> 1) & 1); }  // 0 2 1 3 4 6 5 7
+__device__ __forceinline__ int chunk_quad(int g) { return ((g & 1) << 2) | (g >> 1); }                  // 0 4 1 5 2 6 3 7
+template <int RH>
+__device__ __forceinline__ int w_chunk(int g)
+{
+    if constexpr (RH == 4) return chunk_pair(g);
+    else if constexpr (RH == 2) return chunk_quad(g);
+    else return g;
+}
+
 // ------------------------------------------------------------------------------------------
 // PI profile
 // ------------------------------------------------------------------------------------------
@@ -91,15 +119,17 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
 {
     using Cfg = ProfCfg<RH>;
     constexpr int H = Cfg::H, TT = Cfg::TT, WS = Cfg::WStride, US = kUStride;
-    constexpr int NW = (RH >= 2) ? RH / 2 : 1;  // 16-byte W chunks per lane
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int lg = lane & 3, hg = lane >> 2;
+    const int fk = lane & 3, fg = lane >> 2;  // MMA fragment coordinates of this lane
     double* Us = smem + size_t(warp) * Cfg::WarpDoubles;
     double* Ws = Us + 32 * US;
     double* myU = Us + lane * US;  // generation phase: lane == site
     double* myW = Ws + lane * WS;
+    // fragment sources: site row fk (+4 per k-step); lo chunk = 4 entries, hi chunk = RH entries
+    const double* fragU = Us + fk * US + 4 * chunk_pair(fg);
+    const double* fragW = Ws + fk * WS + RH * w_chunk<RH>(fg);
 
     for (;;) {
         uint32_t it = 0;
@@ -110,11 +140,12 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
         const int64_t T0 = int64_t(item.tile) * TT;
         const double t0d = double(T0);
 
-        double acc[8][RH];
+        // acc[mt][nt][c]: lo = 4*chunk_pair(fg) + mt, hi = RH*w_chunk(2*fk + c) + nt
+        double acc[4][RH][2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < RH; ++j) acc[i][j] = 0.0;
+            for (int j = 0; j < RH; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         const double* rp = args.rates + item.site_begin;
         double lam_next = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
@@ -126,13 +157,14 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 lam_next = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
             }
             // ---- generation: this lane's site -> U[0..31], W[0..H-1] (power tables) ----
+            // rows of lanes >= cnt and of culled sites are U = 0, W = 1: they add exactly 0
             {
                 double a = 16.0 * (lam * lam);
                 const bool ok = (fabs(a) <= DBL_MAX) && (lane < cnt);  // NaN/Inf rate (or 16 r^2 overflow): culled
                 const double c = ok ? 4.0 * lam : 0.0;
                 a = ok ? a : 0.0;
-                const double q = exp(-c);
-                const double u0 = (T0 == 0) ? a : a * exp(-(c * t0d));
+                const double q = exp_full(-c);
+                const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
                 const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
                 const double qB = q16 * q16;  // q^32
                 double xa = u0, xb = u0 * q16;
@@ -167,77 +199,95 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 }
             }
             __syncwarp();
-            // ---- outer product: acc[lo][hi] += U[lo] * W[hi] over the chunk's sites ----
+            // ---- contraction over the chunk's sites: acc(lo,hi) += sum_s U[s][lo] * W[s][hi] ----
+            // 4 sites per k-step; fragments of step s+1 are fetched while the MMAs of step s issue
             {
-                const double2* up = reinterpret_cast<const double2*>(Us) + lg;
-                const double* wp = Ws + ((RH >= 2) ? hg * 2 : hg);
-#pragma unroll 2
-                for (int s = 0; s < cnt; ++s) {
-                    double u[8], w[RH];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const double2 v = up[s * (US / 2) + r * 4];
-                        u[2 * r] = v.x;
-                        u[2 * r + 1] = v.y;
-                    }
-                    if constexpr (RH >= 2) {
-#pragma unroll
-                        for (int r = 0; r < NW; ++r) {
-                            const double2 v = *reinterpret_cast<const double2*>(wp + s * WS + r * 16);
-                            w[2 * r] = v.x;
-                            w[2 * r + 1] = v.y;
-                        }
+                auto fetch = [&](double (&a)[4], double (&b)[RH], int step) {
+                    const double* up = fragU + step * (4 * US);
+                    const double* wp = fragW + step * (4 * WS);
+                    const double2 u01 = *reinterpret_cast<const double2*>(up);
+                    const double2 u23 = *reinterpret_cast<const double2*>(up + 2);
+                    a[0] = u01.x; a[1] = u01.y; a[2] = u23.x; a[3] = u23.y;
+                    if constexpr (RH == 1) {
+                        b[0] = wp[0];
                     } else {
-                        w[0] = wp[s * WS];
+#pragma unroll
+                        for (int r = 0; r < RH / 2; ++r) {
+                            const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
+                            b[2 * r] = v.x; b[2 * r + 1] = v.y;
+                        }
                     }
+                };
+                auto mma_step = [&](const double (&a)[4], const double (&b)[RH]) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < RH; ++j) acc[i][j] = fma(u[i], w[j], acc[i][j]);
+                        for (int j = 0; j < RH; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                };
+                const int nk = (cnt + 3) >> 2;  // 1..8 k-steps; rows past cnt are zero, so odd counts round up
+                double a0[4], b0[RH], a1[4], b1[RH];
+                fetch(a0, b0, 0);
+                for (int s = 0; s < nk; s += 2) {
+                    fetch(a1, b1, s + 1);
+                    mma_step(a0, b0);
+                    fetch(a0, b0, min(s + 2, 7));
+                    mma_step(a1, b1);
                 }
             }
             __syncwarp();
         }
 
-        // ---- epilogue ----
-        // register (i, j) holds lo = (i/2)*8 + lg*2 + (i&1), hi = (j/2)*16 + hg*2 + (j&1)   [RH>=2]
-        //                                                     hi = hg                         [RH==1]
+        // ---- epilogue: this lane holds 4 consecutive lo for each of its 2*RH hi ----
+        const int lo0 = 4 * chunk_pair(fg);
         if (item.slot >= 0) {
             // split locus: raw partial sums, reduced in a fixed order by finalize_kernel
             double* out = args.ws + size_t(item.slot) * TT;
 #pragma unroll
-            for (int j = 0; j < RH; ++j) {
-                const int hi = (RH >= 2) ? (j >> 1) * 16 + hg * 2 + (j & 1) : hg;
+            for (int j = 0; j < RH; ++j)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int lo = r * 8 + lg * 2;
-                    *reinterpret_cast<double2*>(out + hi * 32 + lo) = make_double2(acc[2 * r][j], acc[2 * r + 1][j]);
+                for (int c = 0; c < 2; ++c) {
+                    const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
+                    double* o = out + hi * 32 + lo0;
+                    *reinterpret_cast<double2*>(o) = make_double2(acc[0][j][c], acc[1][j][c]);
+                    *reinterpret_cast<double2*>(o + 2) = make_double2(acc[2][j][c], acc[3][j][c]);
                 }
-            }
         } else {
             const int64_t row = int64_t(item.locus) * args.T;
             double* out = args.pi_net + row;
             const bool vec_ok = ((row & 1) == 0);
             double best = -1.0;  // pi_net >= 0 always; first max wins
-            int64_t best_t = 0;
+            int best_i = 0;      // offset within the tile
+            const int64_t t_left = args.T - T0;
+            const int t_end = int(t_left < int64_t(TT) ? t_left : int64_t(TT));  // valid offsets of this tile
 #pragma unroll
-            for (int j = 0; j < RH; ++j) {
-                const int hi = (RH >= 2) ? (j >> 1) * 16 + hg * 2 + (j & 1) : hg;
+            for (int j = 0; j < RH; ++j)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int64_t t = T0 + hi * 32 + r * 8 + lg * 2;
-                    const double v0 = acc[2 * r][j] * double(t);
-                    const double v1 = acc[2 * r + 1][j] * double(t + 1);
-                    if (t + 1 < args.T && vec_ok) {
-                        *reinterpret_cast<double2*>(out + t) = make_double2(v0, v1);
+                for (int c = 0; c < 2; ++c) {
+                    const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
+                    const int o = hi * 32 + lo0;
+                    const double td = t0d + double(o);  // exact: integers far below 2^53
+                    double v[4];
+                    v[0] = acc[0][j][c] * td;
+                    v[1] = acc[1][j][c] * (td + 1.0);
+                    v[2] = acc[2][j][c] * (td + 2.0);
+                    v[3] = acc[3][j][c] * (td + 3.0);
+                    double* dst = out + T0 + o;
+                    if (o + 3 < t_end && vec_ok) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+                        *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
                     } else {
-                        if (t < args.T) out[t] = v0;
-                        if (t + 1 < args.T) out[t + 1] = v1;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (o + i < t_end) dst[i] = v[i];
                     }
-                    if (t < args.T && (v0 > best || (v0 == best && t < best_t))) { best = v0; best_t = t; }
-                    if (t + 1 < args.T && (v1 > best || (v1 == best && t + 1 < best_t))) { best = v1; best_t = t + 1; }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (o + i < t_end && (v[i] > best || (v[i] == best && o + i < best_i))) {
+                            best = v[i];
+                            best_i = o + i;
+                        }
                 }
-            }
+            int64_t best_t = T0 + best_i;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, off);
@@ -256,10 +306,20 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
 // ------------------------------------------------------------------------------------------
 // epoch integrals
 // ------------------------------------------------------------------------------------------
+// One (quad item, epoch) pair with at least one site whose first GK21 panel QAGS does not accept
+// (or whose arguments fall outside the factored fast path): the sites are marked in 8 ballots.
+struct FixEntry {
+    int32_t item;
+    int32_t slot;          // epoch slot within the batch
+    uint32_t mask[kQuadBlock / 32];
+};
+
 struct QuadArgs {
     const double* rates;
     const QuadItem* items;
-    double* qpart;   // [n_items][2*e_total + 4]: integral[e], abserr[e] ..., rate_sum, n_notnan, n_finite, n_multi
+    double* qpart;       // [n_items][2*e_total + 4]: integral[e], abserr[e] ..., rate_sum, n_notnan, n_finite, n_multi
+    FixEntry* fix;       // [n_items * kEpochsPerLaunch] worst case
+    uint32_t* fix_count; // entries appended by this launch (zeroed before it)
     int32_t n_items;
 };
 
@@ -270,7 +330,7 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
                                                 double& resasc)
 {
     const double hl = eb.half[e];
-    const double A0 = a * exp(-(c * eb.center[e]));
+    const double A0 = a * exp_bounded(-(c * eb.center[e]));  // |c * centre| <= 600 on this path
     const double fc = A0 * eb.center[e];
     double fv1[10], fv2[10];
     double resk = c_wgk[10] * fc;
@@ -303,9 +363,13 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
     abserr = gk_error(resk, resg, hl, resabs, resasc);
 }
 
-__global__ void __launch_bounds__(kQuadBlock) quad_kernel(const QuadArgs args, const EpochBatch eb)
+// First GK21 panel of every (site, epoch) of the batch, one thread per site.  A site whose panel is what
+// QAGS returns (the overwhelmingly common case) is summed here; the others contribute 0 and
+// are handed to quad_fix_kernel through the FixEntry list.
+__global__ void __launch_bounds__(kQuadBlock, 2) quad_kernel(const QuadArgs args, const EpochBatch eb)
 {
     __shared__ double red[kQuadBlock / 32][2 * kEpochsPerLaunch + 4];
+    __shared__ uint32_t flagged[kEpochsPerLaunch][kQuadBlock / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const QuadItem item = args.items[blockIdx.x];
     const bool active = tid < item.count;
@@ -317,51 +381,49 @@ __global__ void __launch_bounds__(kQuadBlock) quad_kernel(const QuadArgs args, c
     // fast path: all exponent arguments stay well inside the normal range and every node value is >= 0
     const bool fast = fin && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
     double D[10], R[10];
-    double n_multi = 0.0;
-    for (int e = 0; e < eb.n; ++e) {
-        double result = 0.0, abserr = 0.0;
-        if (fin) {
-            double resabs, resasc;
-            if (fast) {
-                if (eb.new_half[e]) {
-                    const double y = c * eb.half[e];
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) {
-                        D[j] = exp(-(y * c_xgk[j]));
-                        R[j] = __drcp_rn(D[j]);
-                    }
-                }
-                gk21_shared_exp(eb, e, a, c, D, R, result, abserr, resabs, resasc);
-            } else {
-                gk21_direct(eb.a[e], eb.b[e], a, c, &result, &abserr, &resabs, &resasc);
+    for (int e = 0; e < kEpochsPerLaunch; ++e) {
+        if (e >= eb.n) break;
+        double result = 0.0, abserr = 0.0;
+        bool redo = fin && !fast;
+        if (fast) {
+            double resabs, resasc;
+            if (eb.new_half[e]) {
+                const double y = c * eb.half[e];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
             }
+            gk21_shared_exp(eb, e, a, c, D, R, result, abserr, resabs, resasc);
             if (!qags_first_panel_final(result, abserr, resabs, resasc)) {
-                int last;
-                qags_device(eb.a[e], eb.b[e], a, c, &result, &abserr, &last);
-                if (last > 1) n_multi += 1.0;
+                redo = true;
+                result = 0.0;
+                abserr = 0.0;
             }
         }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, redo);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             result += __shfl_down_sync(0xffffffffu, result, off);
             abserr += __shfl_down_sync(0xffffffffu, abserr, off);
         }
-        if (lane == 0) { red[warp][2 * e] = result; red[warp][2 * e + 1] = abserr; }
+        if (lane == 0) {
+            red[warp][2 * e] = result;
+            red[warp][2 * e + 1] = abserr;
+            flagged[e][warp] = ballot;
+        }
     }
     {
-        double rs = notnan ? lam : 0.0, nn = notnan ? 1.0 : 0.0, nf = fin ? 1.0 : 0.0, nm = n_multi;
+        double rs = notnan ? lam : 0.0, nn = notnan ? 1.0 : 0.0, nf = fin ? 1.0 : 0.0;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             rs += __shfl_down_sync(0xffffffffu, rs, off);
             nn += __shfl_down_sync(0xffffffffu, nn, off);
             nf += __shfl_down_sync(0xffffffffu, nf, off);
-            nm += __shfl_down_sync(0xffffffffu, nm, off);
         }
         if (lane == 0) {
             red[warp][2 * kEpochsPerLaunch + 0] = rs;
             red[warp][2 * kEpochsPerLaunch + 1] = nn;
             red[warp][2 * kEpochsPerLaunch + 2] = nf;
-            red[warp][2 * kEpochsPerLaunch + 3] = nm;
         }
     }
     __syncthreads();
@@ -372,16 +434,66 @@ __global__ void __launch_bounds__(kQuadBlock) quad_kernel(const QuadArgs args, c
 #pragma unroll
         for (int w = 0; w < kQuadBlock / 32; ++w) s += red[w][tid];
         out[2 * eb.col[tid >> 1] + (tid & 1)] = s;
-    } else if (tid >= 32 && tid < 36) {
+    } else if (tid >= 32 && tid < 36 && eb.first) {
         const int k = tid - 32;
         double s = 0.0;
+        if (k < 3) {
 #pragma unroll
-        for (int w = 0; w < kQuadBlock / 32; ++w) s += red[w][2 * kEpochsPerLaunch + k];
-        if (k == 3) {
-            // multi-panel count accumulates over epoch batches; the other three are batch-independent
-            if (eb.first) out[2 * eb.e_total + 3] = s; else out[2 * eb.e_total + 3] += s;
-        } else if (eb.first) {
-            out[2 * eb.e_total + k] = s;
+            for (int w = 0; w < kQuadBlock / 32; ++w) s += red[w][2 * kEpochsPerLaunch + k];
+        }
+        out[2 * eb.e_total + k] = s;  // k == 3: multi-panel count, accumulated by quad_fix_kernel
+    } else if (tid >= 64 && tid < 64 + eb.n) {
+        const int e = tid - 64;
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < kQuadBlock / 32; ++w) any |= flagged[e][w];
+        if (any) {
+            FixEntry* fe = args.fix + atomicAdd(args.fix_count, 1u);
+            fe->item = int32_t(blockIdx.x);
+            fe->slot = e;
+#pragma unroll
+            for (int w = 0; w < kQuadBlock / 32; ++w) fe->mask[w] = flagged[e][w];
+        }
+    }
+}
+
+// Full QAGS (bisection + epsilon extrapolation, gk21.cuh) for the flagged sites.  One warp per
+// FixEntry, so every (item, epoch) cell of qpart has a single writer and a fixed summation order.
+__global__ void __launch_bounds__(128) quad_fix_kernel(const QuadArgs args, const EpochBatch eb)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = *args.fix_count;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const int row = 2 * eb.e_total + 4;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += warps) {
+        const FixEntry fe = args.fix[k];
+        const QuadItem item = args.items[fe.item];
+        double si = 0.0, se = 0.0, nm = 0.0;
+        for (int w = 0; w < kQuadBlock / 32; ++w) {
+            const uint32_t m = fe.mask[w];
+            if (m == 0) continue;
+            double result = 0.0, abserr = 0.0, multi = 0.0;
+            if ((m >> lane) & 1u) {
+                const double lam = __ldg(args.rates + item.site_begin + w * 32 + lane);
+                int last;
+                qags_device(eb.a[fe.slot], eb.b[fe.slot], 16.0 * (lam * lam), 4.0 * lam, &result, &abserr, &last);
+                multi = last > 1 ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                result += __shfl_down_sync(0xffffffffu, result, off);
+                abserr += __shfl_down_sync(0xffffffffu, abserr, off);
+                multi += __shfl_down_sync(0xffffffffu, multi, off);
+            }
+            si += result;
+            se += abserr;
+            nm += multi;
+        }
+        if (lane == 0) {
+            double* out = args.qpart + size_t(fe.item) * row;
+            out[2 * eb.col[fe.slot]] += si;
+            out[2 * eb.col[fe.slot] + 1] += se;
+            if (nm != 0.0) atomicAdd(out + 2 * eb.e_total + 3, nm);  // small integers: exact in any order
         }
     }
 }
@@ -527,21 +639,37 @@ __global__ void site_integrals_kernel(double a, double b, const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-// measurement helper: register-resident DFMA throughput
+// measurement helper: FP64 pipe peak.  A register-resident 8x4 outer-product of independent DFMAs
+// (64 per iteration, no memory traffic); tools/microbench/fp64_pipes.cu shows this form reaches the
+// pipe's 64 FMA/clk/SM while a plain x = fma(x, m, b) chain stops ~13 % short of it.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double m, double b)
+__global__ void __launch_bounds__(128) fp64_peak_kernel(double* sink, int iters, const double* seed)
 {
-    double x[16];
+    double acc[8][4], u0[8], w0[4], u1[8], w1[4];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) x[k] = double(threadIdx.x + k) * 1e-3;
-    for (int i = 0; i < iters; ++i) {
+    for (int i = 0; i < 8; ++i) { u0[i] = seed[i] + threadIdx.x; u1[i] = seed[8 + i] * 0.5; }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = fma(x[k], m, b);
+    for (int j = 0; j < 4; ++j) { w0[j] = seed[16 + j]; w1[j] = seed[20 + j] + threadIdx.x; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(u0[i], w0[j], acc[i][j]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(u1[i], w1[j], acc[i][j]);
     }
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s += x[k];
-    if (s == 123.456) sink[0] = s;  // never true; keeps the chain alive
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j];
+    if (s == 123.456) sink[0] = s;  // never true; keeps the accumulators alive
 }
 
 }  // namespace tapir

@@ -100,7 +100,7 @@ struct tapir_cuda_ctx {
     // inputs / work lists
     DevBuf d_rates, d_prof_items, d_quad_items, d_nsplit, d_ws_base, d_qitem_begin, d_time_idx, d_counter;
     // intermediates
-    DevBuf d_ws, d_tile_max, d_tile_arg, d_qpart;
+    DevBuf d_ws, d_tile_max, d_tile_arg, d_qpart, d_fix;
     // results
     DevBuf d_pi_net, d_pi_times, d_integral, d_abserr, d_max_pi, d_argmax_t, d_argmax_epoch, d_mean_rate, d_n_finite,
         d_n_multi;
@@ -333,7 +333,7 @@ int tapir_cuda_destroy(tapir_cuda_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_rates,     &ctx->d_prof_items, &ctx->d_quad_items, &ctx->d_nsplit,    &ctx->d_ws_base,
                       &ctx->d_qitem_begin, &ctx->d_time_idx, &ctx->d_counter,    &ctx->d_ws,        &ctx->d_tile_max,
-                      &ctx->d_tile_arg,  &ctx->d_qpart,      &ctx->d_pi_net,     &ctx->d_pi_times,  &ctx->d_integral,
+                      &ctx->d_tile_arg,  &ctx->d_qpart,      &ctx->d_fix,        &ctx->d_pi_net,     &ctx->d_pi_times,  &ctx->d_integral,
                       &ctx->d_abserr,    &ctx->d_max_pi,     &ctx->d_argmax_t,   &ctx->d_argmax_epoch, &ctx->d_mean_rate,
                       &ctx->d_n_finite,  &ctx->d_n_multi,    &ctx->d_scratch_a,  &ctx->d_scratch_b, &ctx->d_scratch_c,
                       &ctx->d_flush};
@@ -488,6 +488,7 @@ int tapir_cuda_upload(tapir_cuda_ctx* ctx, const tapir_problem* p)
     CU(ctx, ctx->d_tile_max.ensure(size_t(L) * plan.n_tiles * 8 + 8));
     CU(ctx, ctx->d_tile_arg.ensure(size_t(L) * plan.n_tiles * 8 + 8));
     CU(ctx, ctx->d_qpart.ensure(size_t(n_quad) * qrow * 8 + 8));
+    CU(ctx, ctx->d_fix.ensure(size_t(n_quad) * kEpochsPerLaunch * sizeof(FixEntry) + 8));
     CU(ctx, ctx->d_pi_net.ensure(size_t(L) * plan.T * 8 + 16));
     CU(ctx, ctx->d_pi_times.ensure(size_t(L) * plan.K * 8 + 8));
     CU(ctx, ctx->d_integral.ensure(size_t(L) * plan.E * 8 + 8));
@@ -523,8 +524,9 @@ int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
     int launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev[0], st));
     if (plan.L > 0) {
+        CU(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, st));
         if (plan.n_prof_items > 0 && plan.T > 0) {
-            CU(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 4, st));
+
             ProfArgs pa;
             pa.rates = ctx->d_rates.as<double>();
             pa.items = ctx->d_prof_items.as<ProfItem>();
@@ -552,11 +554,17 @@ int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
             qa.rates = ctx->d_rates.as<double>();
             qa.items = ctx->d_quad_items.as<QuadItem>();
             qa.qpart = ctx->d_qpart.as<double>();
+            qa.fix = ctx->d_fix.as<FixEntry>();
             qa.n_items = int32_t(plan.n_quad_items);
+            int k = 0;
             for (const EpochBatch& eb : plan.batches) {
+                // one counter per batch (d_counter[1..]); slot 0 is the profile kernel's work queue head
+                qa.fix_count = ctx->d_counter.as<uint32_t>() + 1 + k++;
                 quad_kernel<<<unsigned(plan.n_quad_items), kQuadBlock, 0, st>>>(qa, eb);
                 CU(ctx, cudaGetLastError());
-                ++launches;
+                quad_fix_kernel<<<unsigned(ctx->sm_count * 4), 128, 0, st>>>(qa, eb);
+                CU(ctx, cudaGetLastError());
+                launches += 2;
             }
         }
         CU(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -724,12 +732,16 @@ int tapir_cuda_fp64_peak(tapir_cuda_ctx* ctx, double* tflops, float* ms_out)
     if (rc) return rc;
     if (!tflops) return fail(ctx, TAPIR_E_INVALID, "null pointer");
     CU(ctx, ctx->d_counter.ensure(256));
+    CU(ctx, ctx->d_scratch_a.ensure(32 * 8));
     cudaStream_t st = ctx->stream;
-    const int iters = 8192, blocks = ctx->sm_count * 8, threads = 256;
+    double seed[32];
+    for (int i = 0; i < 32; ++i) seed[i] = 1.0 + 1e-3 * i;
+    CU(ctx, cudaMemcpyAsync(ctx->d_scratch_a.p, seed, sizeof seed, cudaMemcpyHostToDevice, st));
+    const int iters = 4096, blocks = ctx->sm_count * 4, threads = 128;
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         CU(ctx, cudaEventRecord(ctx->ev[0], st));
-        fp64_peak_kernel<<<blocks, threads, 0, st>>>(ctx->d_counter.as<double>() + 8, iters, 0.999999, 1e-9);
+        fp64_peak_kernel<<<blocks, threads, 0, st>>>(ctx->d_counter.as<double>() + 8, iters, ctx->d_scratch_a.as<double>());
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaEventRecord(ctx->ev[1], st));
         CU(ctx, cudaStreamSynchronize(st));
@@ -737,7 +749,7 @@ int tapir_cuda_fp64_peak(tapir_cuda_ctx* ctx, double* tflops, float* ms_out)
         CU(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
         if (rep > 0 && ms < best) best = ms;
     }
-    const double flops = 2.0 * 16.0 * double(iters) * double(blocks) * double(threads);
+    const double flops = 2.0 * 64.0 * double(iters) * double(blocks) * double(threads);
     *tflops = flops / (double(best) * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
     return TAPIR_OK;

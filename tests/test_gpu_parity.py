@@ -224,7 +224,28 @@ def test_staged_api_matches_run(eng):
     a = eng.run(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
     eng.upload(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
     tm = eng.compute()
-    assert tm.launches == 3 and tm.total_ms > 0
+    assert tm.launches == 4 and tm.total_ms > 0       # profile, quad, quad_fix, finalize
     b = eng.download()
     for name in ("pi_net", "pi_times", "integral", "abserr", "max_pi", "argmax_t", "argmax_epoch"):
         assert np.array_equal(getattr(a, name), getattr(b, name))
+
+
+def test_bisection_heavy_loci_are_deterministic(eng):
+    """Every site needs the full QAGS (fast rates, epochs starting at 0): all 8 ballots of a 256-site block are
+    set, several blocks per locus, two epoch batches (E > 8)."""
+    from oracle import capi
+    rng = np.random.default_rng(11)
+    loci = [rng.uniform(0.3, 3.0, size=700), rng.uniform(0.0, 0.5, size=300), np.array([-0.01, 0.2, np.inf, 5.0])]
+    from tapir_b200.engine import pack_csr
+    off, rates = pack_csr(loci, pinned=False)
+    epochs = [[0, 10], [32, 42], [5, 300], [0, 1], [1, 2], [2, 3], [3, 4], [4, 5], [5, 6], [0, 50]]
+    a = eng.run(off, rates, 64, [3], epochs, want_profile=False)
+    b = eng.run(off, rates, 64, [3], epochs, want_profile=False)
+    assert np.array_equal(a.integral, b.integral) and np.array_equal(a.abserr, b.abserr)
+    assert np.array_equal(a.n_multi_panel, b.n_multi_panel) and a.n_multi_panel[0] > 700
+    for l in range(3):
+        lam = rates[off[l]:off[l + 1]]
+        si, se, nm = capi.epochs(lam[np.isfinite(lam)], epochs)
+        assert rel(a.integral[l], si) < RTOL
+        np.testing.assert_allclose(a.abserr[l], se, rtol=ERR_RTOL, atol=1e-300)
+        assert a.n_multi_panel[l] == int(nm.sum())
