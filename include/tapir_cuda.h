@@ -118,6 +118,8 @@ int tapir_cuda_transfer_bytes(tapir_cuda_ctx *ctx, uint64_t *h2d, uint64_t *d2h)
 /* get_townsend_pi(time, rates) -> out[T*S] row-major (T,S); NaN propagate as numpy does */
 int tapir_cuda_pi_matrix(tapir_cuda_ctx *ctx, const double *time, int64_t n_time, const double *rates,
                          int64_t n_rates, double *out);
+/* numpy.nansum(pi, axis=1) of a row-major (n_rows, n_cols) matrix (compute.py:78, bin/tapir_compute.py:119) */
+int tapir_cuda_nansum_rows(tapir_cuda_ctx *ctx, const double *matrix, int64_t n_rows, int64_t n_cols, double *out);
 /* vectorize(get_integral_over_times)(a, b, rates) -> integral[n], abserr[n], panels[n] (QAGS `last`) */
 int tapir_cuda_site_integrals(tapir_cuda_ctx *ctx, double a, double b, const double *rates, int64_t n,
                               double *integral, double *abserr, int32_t *panels);

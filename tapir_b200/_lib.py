@@ -69,6 +69,7 @@ SYMBOLS = {
     "tapir_cuda_device_results": (ctypes.c_int, [_vp, ctypes.POINTER(Results)]),
     "tapir_cuda_transfer_bytes": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "tapir_cuda_pi_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "tapir_cuda_nansum_rows": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "tapir_cuda_site_integrals": (ctypes.c_int, [_vp, _dbl, _dbl, _vp, _i64, _vp, _vp, _vp]),
     "tapir_cuda_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(_dbl), ctypes.POINTER(ctypes.c_float)]),
     "tapir_cuda_flush_l2": (ctypes.c_int, [_vp]),

@@ -6,7 +6,7 @@
 //
 //   exp_bounded(x)        |x| <= 700            one scaling, no checks               17 FP64 ops
 //   exp_pm_bounded(z)     0 <= z <= 700         e^-z and e^+z from one reduction     21 FP64 ops for both
-//   exp_full(x)           any x (NaN -> NaN)    clamped, two-step scaling            ~22 FP64 ops
+//   exp_full(x)           any x (NaN -> NaN)    clamped, two-step scaling, Estrin    ~26 FP64 ops, depth ~12
 //
 // Method: k = rint(x log2 e); r = x - k ln2 (Cody-Waite, ln2 split so that k*ln2_hi is exact);
 // e^r by the degree-13 Taylor polynomial on |r| <= ln2/2 (truncation < 4e-18); result scaled by
@@ -31,11 +31,22 @@ constexpr double kLog2e = 1.4426950408889634;
 constexpr double kLn2Hi = 0x1.62e42fee00000p-1;   // 33 significant bits: k * kLn2Hi is exact for |k| < 2^20
 constexpr double kLn2Lo = 0x1.a39ef35793c76p-33;
 constexpr double kMagic = 6755399441055744.0;     // 1.5 * 2^52: adding it rounds to nearest integer
-// 1/n!
+// 1/n!  (host: constexpr; device: the same values in constant memory, so that they are constant-bank operands of
+// the DFMAs instead of 64-bit immediates that cost two UMOVs per use)
+#if defined(__CUDA_ARCH__)
+#define TAPIR_FX_C(n) ::tapir::fx::d_coef[n]
+#else
+#define TAPIR_FX_C(n) ::tapir::fx::h_coef[n]
+#endif
 constexpr double c2 = 0.5, c3 = 0.16666666666666666, c4 = 0.041666666666666664, c5 = 0.008333333333333333,
                  c6 = 0.001388888888888889, c7 = 0.0001984126984126984, c8 = 2.48015873015873e-05,
                  c9 = 2.7557319223985893e-06, c10 = 2.755731922398589e-07, c11 = 2.505210838544172e-08,
                  c12 = 2.08767569878681e-09, c13 = 1.6059043836821613e-10;
+
+static const double h_coef[14] = {1.0, 1.0, c2, c3, c4, c5, c6, c7, c8, c9, c10, c11, c12, c13};
+#if defined(__CUDACC__)
+__device__ __constant__ double d_coef[14] = {1.0, 1.0, c2, c3, c4, c5, c6, c7, c8, c9, c10, c11, c12, c13};
+#endif
 
 TAPIR_HD double fma_(double a, double b, double c)
 {
@@ -78,12 +89,29 @@ TAPIR_HD double reduce(double x, double kd) { return fma_(kd, -kLn2Lo, fma_(kd, 
 // e^r on |r| <= 0.35
 TAPIR_HD double poly(double r)
 {
-    double p = c13;
-    p = fma_(p, r, c12); p = fma_(p, r, c11); p = fma_(p, r, c10); p = fma_(p, r, c9);
-    p = fma_(p, r, c8);  p = fma_(p, r, c7);  p = fma_(p, r, c6);  p = fma_(p, r, c5);
-    p = fma_(p, r, c4);  p = fma_(p, r, c3);  p = fma_(p, r, c2);
+    double p = TAPIR_FX_C(13);
+    p = fma_(p, r, TAPIR_FX_C(12)); p = fma_(p, r, TAPIR_FX_C(11)); p = fma_(p, r, TAPIR_FX_C(10));
+    p = fma_(p, r, TAPIR_FX_C(9));  p = fma_(p, r, TAPIR_FX_C(8));  p = fma_(p, r, TAPIR_FX_C(7));
+    p = fma_(p, r, TAPIR_FX_C(6));  p = fma_(p, r, TAPIR_FX_C(5));  p = fma_(p, r, TAPIR_FX_C(4));
+    p = fma_(p, r, TAPIR_FX_C(3));  p = fma_(p, r, TAPIR_FX_C(2));
     p = fma_(p, r, 1.0);
     return fma_(p, r, 1.0);
+}
+
+// the same polynomial in Estrin form: 3 more operations, dependent depth 6 instead of 14 (for callers
+// that have a single exponential in flight per thread)
+TAPIR_HD double poly_estrin(double r)
+{
+    // e^r = 1 + (r + r^2 P(r)),  P = c2 + c3 r + ... + c13 r^11 evaluated pairwise
+    const double r2 = r * r;
+    const double p0 = fma_(TAPIR_FX_C(3), r, TAPIR_FX_C(2)), p1 = fma_(TAPIR_FX_C(5), r, TAPIR_FX_C(4));
+    const double p2 = fma_(TAPIR_FX_C(7), r, TAPIR_FX_C(6)), p3 = fma_(TAPIR_FX_C(9), r, TAPIR_FX_C(8));
+    const double p4 = fma_(TAPIR_FX_C(11), r, TAPIR_FX_C(10)), p5 = fma_(TAPIR_FX_C(13), r, TAPIR_FX_C(12));
+    const double r4 = r2 * r2;
+    const double q0 = fma_(p1, r2, p0), q1 = fma_(p3, r2, p2), q2 = fma_(p5, r2, p4);
+    const double r8 = r4 * r4;
+    const double P = fma_(q2, r8, fma_(q1, r4, q0));
+    return 1.0 + fma_(r2, P, r);
 }
 }  // namespace fx
 
@@ -96,6 +124,31 @@ TAPIR_HD double exp_bounded(double x)
     return fx::poly(fx::reduce(x, kd)) * fx::pow2i(ki);
 }
 
+// N independent exp_bounded evaluations advanced in lock step, so that the N dependent Horner chains are
+// interleaved in the instruction stream (the compiler otherwise emits them one after the other and every
+// DFMA waits out the 8-cycle latency of the previous one)
+template <int N>
+TAPIR_HD void exp_bounded_n(const double (&x)[N], double (&y)[N])
+{
+    double r[N], p[N];
+    int ki[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double kd;
+        fx::round_int(x[i] * fx::kLog2e, kd, ki[i]);
+        r[i] = fx::reduce(x[i], kd);
+        p[i] = TAPIR_FX_C(13);
+    }
+#pragma unroll
+    for (int k = 12; k >= 2; --k)
+#pragma unroll
+        for (int i = 0; i < N; ++i) p[i] = fx::fma_(p[i], r[i], TAPIR_FX_C(k));
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = fx::fma_(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = fx::fma_(p[i], r[i], 1.0) * fx::pow2i(ki[i]);
+}
+
 // (e^-z, e^+z) for 0 <= z <= 700 from one range reduction: e^{+/-r} = E(r^2) +/- r O(r^2)
 TAPIR_HD void exp_pm_bounded(double z, double& em, double& ep)
 {
@@ -105,12 +158,12 @@ TAPIR_HD void exp_pm_bounded(double z, double& em, double& ep)
     round_int(z * kLog2e, kd, ki);
     const double r = reduce(z, kd);
     const double s = r * r;
-    double ev = c12, od = c13;
-    ev = fma_(ev, s, c10); od = fma_(od, s, c11);
-    ev = fma_(ev, s, c8);  od = fma_(od, s, c9);
-    ev = fma_(ev, s, c6);  od = fma_(od, s, c7);
-    ev = fma_(ev, s, c4);  od = fma_(od, s, c5);
-    ev = fma_(ev, s, c2);  od = fma_(od, s, c3);
+    double ev = TAPIR_FX_C(12), od = TAPIR_FX_C(13);
+    ev = fma_(ev, s, TAPIR_FX_C(10)); od = fma_(od, s, TAPIR_FX_C(11));
+    ev = fma_(ev, s, TAPIR_FX_C(8));  od = fma_(od, s, TAPIR_FX_C(9));
+    ev = fma_(ev, s, TAPIR_FX_C(6));  od = fma_(od, s, TAPIR_FX_C(7));
+    ev = fma_(ev, s, TAPIR_FX_C(4));  od = fma_(od, s, TAPIR_FX_C(5));
+    ev = fma_(ev, s, TAPIR_FX_C(2));  od = fma_(od, s, TAPIR_FX_C(3));
     ev = fma_(ev, s, 1.0); od = fma_(od, s, 1.0);
     ep = fma_(od, r, ev) * pow2i(ki);
     em = fma_(od, -r, ev) * pow2i(-ki);
@@ -123,7 +176,7 @@ TAPIR_HD double exp_full(double x)
     double kd;
     int ki;
     fx::round_int(xc * fx::kLog2e, kd, ki);
-    const double p = fx::poly(fx::reduce(xc, kd));
+    const double p = fx::poly_estrin(fx::reduce(xc, kd));
     const int k1 = ki >> 1;
     const double v = (p * fx::pow2i(k1)) * fx::pow2i(ki - k1);
     return (x != x) ? x : v;

@@ -41,7 +41,7 @@ struct QuadItem {      // up to kQuadBlock consecutive sites of one locus
 };
 
 constexpr int kQuadBlock = 256;
-constexpr int kEpochsPerLaunch = 8;
+constexpr int kEpochsPerLaunch = 4;
 constexpr int kProfWarps = 4;  // warps per CTA of the profile kernel (warps are autonomous)
 constexpr int kB = 32;         // lo extent of a time tile
 constexpr int kUStride = kB + 2;
@@ -324,22 +324,24 @@ struct QuadArgs {
 };
 
 // GK21 on one epoch with the exponentials factored as e^{-c(centre -/+ h x_j)} = E0 * e^{+/- c h x_j}:
-// D[j] = e^{-c h x_j} and R[j] = 1/D[j] are shared by all epochs of equal half-length.
-__device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, double a, double c, const double (&D)[10],
+// D[j] = e^{-c h x_j} and R[j] = e^{+c h x_j} are shared by all epochs of equal half-length, and the
+// common factor A0 = a E0 is applied once to the sums (every dqk21 quantity is homogeneous of degree one
+// in the node values, and A0 >= 1e-270 on this path, so nothing under- or overflows differently).
+// Node values are >= 0 here, so dqk21's resabs sum equals resk's.
+// `scale` = a e^{-c centre} h (>= 0).
+__device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, double scale, const double (&D)[10],
                                                 const double (&R)[10], double& result, double& abserr, double& resabs,
                                                 double& resasc)
 {
-    const double hl = eb.half[e];
-    const double A0 = a * exp_bounded(-(c * eb.center[e]));  // |c * centre| <= 600 on this path
-    const double fc = A0 * eb.center[e];
+    const double fc = eb.center[e];
     double fv1[10], fv2[10];
     double resk = c_wgk[10] * fc;
     double resg = 0.0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int jt = 2 * j + 1;
-        const double f1 = (A0 * eb.tm[e][jt]) * R[jt];
-        const double f2 = (A0 * eb.tp[e][jt]) * D[jt];
+        const double f1 = eb.tm[e][jt] * R[jt];
+        const double f2 = eb.tp[e][jt] * D[jt];
         fv1[jt] = f1; fv2[jt] = f2;
         const double fsum = f1 + f2;
         resg += c_wg[j] * fsum;
@@ -348,8 +350,8 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int jt = 2 * j;
-        const double f1 = (A0 * eb.tm[e][jt]) * R[jt];
-        const double f2 = (A0 * eb.tp[e][jt]) * D[jt];
+        const double f1 = eb.tm[e][jt] * R[jt];
+        const double f2 = eb.tp[e][jt] * D[jt];
         fv1[jt] = f1; fv2[jt] = f2;
         resk += c_wgk[jt] * (f1 + f2);
     }
@@ -357,103 +359,142 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
     double rasc = c_wgk[10] * fabs(fc - reskh);
 #pragma unroll
     for (int j = 0; j < 10; ++j) rasc += c_wgk[j] * (fabs(fv1[j] - reskh) + fabs(fv2[j] - reskh));
-    result = resk * hl;
-    resabs = fabs(resk) * fabs(hl);  // every node value is >= 0, so dqk21's resabs sum is resk's sum
-    resasc = rasc * fabs(hl);
-    abserr = gk_error(resk, resg, hl, resabs, resasc);
+    result = resk * scale;
+    resabs = result;
+    resasc = rasc * scale;
+    // dqk21's error heuristic: err = resasc * min(1, (200 e0 / resasc)^1.5), then raised to the rounding
+    // floor 50 eps resabs.  Whether the floor wins is decided without the divide and the square root:
+    // resasc (n/resasc)^1.5 <= floor  <=>  n^3 <= floor^2 resasc, compared in units of resk (scaled by a
+    // power of two taken from resk's exponent so that neither side can overflow or underflow to a tie).
+    const double e0 = fabs(resk - resg);
+    const double unit = __hiloint2double((2046 - ((__double2hiint(resk) >> 20) & 0x7ff)) << 20, 0);  // ~ 1 / resk
+    const double n = (200.0 * e0) * unit, ra = rasc * unit, fl = ((kEpmach * 50.0) * resk) * unit;
+    if (resabs > kUflow / (50.0 * kEpmach) && (ra == 0.0 || e0 == 0.0)) {
+        abserr = fmax((kEpmach * 50.0) * resabs, e0 * scale);
+    } else if (resabs > kUflow / (50.0 * kEpmach) && n < ra && (n * n) * n <= (fl * fl) * ra) {
+        abserr = (kEpmach * 50.0) * resabs;
+    } else {
+        abserr = gk_error(resk, resg, scale, resabs, resasc);
+    }
 }
 
-// First GK21 panel of every (site, epoch) of the batch, one thread per site.  A site whose panel is what
-// QAGS returns (the overwhelmingly common case) is summed here; the others contribute 0 and
-// are handed to quad_fix_kernel through the FixEntry list.
+// First GK21 panel of every (site, epoch) of the batch, one thread per site of a 256-site item.  A site
+// whose panel is what QAGS returns (the overwhelmingly common case) is summed here; the
+// others contribute 0 and are handed to quad_fix_kernel through the FixEntry list.
+// Persistent blocks: the next item's rates are fetched while the current item is integrated, and the
+// per-item sums are formed column-wise in shared memory in a fixed order.
+constexpr int kQuadCols = 2 * kEpochsPerLaunch + 3;  // integral/abserr per epoch, rate sum, #not-NaN, #finite
+
+// NE = eb.n (1..kEpochsPerLaunch) is a template parameter so that the whole per-site computation is one
+// straight-line block the scheduler can interleave (the NE exponentials of the common factors in particular).
+template <int NE>
 __global__ void __launch_bounds__(kQuadBlock, 2) quad_kernel(const QuadArgs args, const EpochBatch eb)
 {
-    __shared__ double red[kQuadBlock / 32][2 * kEpochsPerLaunch + 4];
+    __shared__ double cols[kQuadCols][kQuadBlock];
     __shared__ uint32_t flagged[kEpochsPerLaunch][kQuadBlock / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const QuadItem item = args.items[blockIdx.x];
-    const bool active = tid < item.count;
-    const double lam = active ? __ldg(args.rates + item.site_begin + tid) : __longlong_as_double(0x7ff8000000000000LL);
-    const bool notnan = active && (lam == lam);
-    const bool fin = active && (fabs(lam) <= DBL_MAX);
-    const double a = 16.0 * (lam * lam);
-    const double c = 4.0 * lam;
-    // fast path: all exponent arguments stay well inside the normal range and every node value is >= 0
-    const bool fast = fin && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
-    double D[10], R[10];
+    const int stride = gridDim.x;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    int it = blockIdx.x;
+    if (it >= args.n_items) return;
+    QuadItem item = args.items[it];
+    QuadItem item_next = item;
+    if (it + stride < args.n_items) item_next = args.items[it + stride];
+    double lam = tid < item.count ? __ldg(args.rates + item.site_begin + tid) : qnan;
+    const int row = 2 * eb.e_total + 4;
+
+    for (; it < args.n_items; it += stride) {
+        // ---- prefetch: rates of the next item, descriptor of the one after ----
+        double lam_next = qnan;
+        QuadItem item_after = item_next;
+        if (it + stride < args.n_items) {
+            if (tid < item_next.count) lam_next = __ldg(args.rates + item_next.site_begin + tid);
+            if (it + 2 * stride < args.n_items) item_after = args.items[it + 2 * stride];
+        }
+
+        const bool active = tid < item.count;
+        const bool notnan = active && (lam == lam);
+        const bool fin = active && (fabs(lam) <= DBL_MAX);
+        const double a = 16.0 * (lam * lam);
+        const double c = 4.0 * lam;
+        // fast path: all exponent arguments stay well inside the normal range and every node value is >= 0
+        const bool fast = fin && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
+        const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps the arithmetic of idle lanes finite
+        // common factors a e^{-c centre} h of all epochs first: independent chains
+        double scale[NE > 0 ? NE : 1];
+        if constexpr (NE > 0) {
+            double xs[NE];
 #pragma unroll
-    for (int e = 0; e < kEpochsPerLaunch; ++e) {
-        if (e >= eb.n) break;
-        double result = 0.0, abserr = 0.0;
-        bool redo = fin && !fast;
-        if (fast) {
-            double resabs, resasc;
+            for (int e = 0; e < NE; ++e) xs[e] = -(cs * eb.center[e]);  // |c * centre| <= 600 on this path
+            exp_bounded_n<NE>(xs, scale);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) scale[e] = (as * scale[e]) * eb.half[e];
+        }
+        double D[10], R[10];
+        uint32_t redo_bits = 0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
             if (eb.new_half[e]) {
-                const double y = c * eb.half[e];
+                const double y = cs * eb.half[e];
 #pragma unroll
                 for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
             }
-            gk21_shared_exp(eb, e, a, c, D, R, result, abserr, resabs, resasc);
-            if (!qags_first_panel_final(result, abserr, resabs, resasc)) {
-                redo = true;
-                result = 0.0;
-                abserr = 0.0;
+            double result, abserr, resabs, resasc;
+            gk21_shared_exp(eb, e, scale[e], D, R, result, abserr, resabs, resasc);
+            const bool keep = fast && qags_first_panel_final(result, abserr, resabs, resasc);
+            cols[2 * e][tid] = keep ? result : 0.0;
+            cols[2 * e + 1][tid] = keep ? abserr : 0.0;
+            redo_bits |= (fin && !keep) ? (1u << e) : 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const uint32_t ballot = __ballot_sync(0xffffffffu, (redo_bits >> e) & 1u);
+            if (lane == 0) flagged[e][warp] = ballot;
+        }
+        if (eb.first) {
+            cols[2 * kEpochsPerLaunch + 0][tid] = notnan ? lam : 0.0;
+            cols[2 * kEpochsPerLaunch + 1][tid] = notnan ? 1.0 : 0.0;
+            cols[2 * kEpochsPerLaunch + 2][tid] = fin ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        // ---- column sums: warp w owns columns w, w + 8, w + 16; fixed order ----
+        double* out = args.qpart + size_t(it) * row;
+#pragma unroll
+        for (int rep = 0; rep < (kQuadCols + 7) / 8; ++rep) {
+            const int col = warp + 8 * rep;
+            const bool is_stat = col >= 2 * kEpochsPerLaunch;
+            const bool wanted = col < kQuadCols && (is_stat ? eb.first != 0 : col < 2 * NE);
+            if (wanted) {  // warp-uniform
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < kQuadBlock / 32; ++k) v += cols[col][lane + 32 * k];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                if (lane == 0) {
+                    if (is_stat) out[2 * eb.e_total + (col - 2 * kEpochsPerLaunch)] = v;
+                    else out[2 * eb.col[col >> 1] + (col & 1)] = v;
+                }
             }
         }
-        const uint32_t ballot = __ballot_sync(0xffffffffu, redo);
+        if (tid < NE) {
+            const int e = tid;
+            uint32_t any = 0;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            result += __shfl_down_sync(0xffffffffu, result, off);
-            abserr += __shfl_down_sync(0xffffffffu, abserr, off);
-        }
-        if (lane == 0) {
-            red[warp][2 * e] = result;
-            red[warp][2 * e + 1] = abserr;
-            flagged[e][warp] = ballot;
-        }
-    }
-    {
-        double rs = notnan ? lam : 0.0, nn = notnan ? 1.0 : 0.0, nf = fin ? 1.0 : 0.0;
+            for (int w = 0; w < kQuadBlock / 32; ++w) any |= flagged[e][w];
+            if (any) {
+                FixEntry* fe = args.fix + atomicAdd(args.fix_count, 1u);
+                fe->item = it;
+                fe->slot = e;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            rs += __shfl_down_sync(0xffffffffu, rs, off);
-            nn += __shfl_down_sync(0xffffffffu, nn, off);
-            nf += __shfl_down_sync(0xffffffffu, nf, off);
+                for (int w = 0; w < kQuadBlock / 32; ++w) fe->mask[w] = flagged[e][w];
+            }
+        } else if (tid == 32 && eb.first) {
+            out[2 * eb.e_total + 3] = 0.0;  // multi-panel count, accumulated by quad_fix_kernel
         }
-        if (lane == 0) {
-            red[warp][2 * kEpochsPerLaunch + 0] = rs;
-            red[warp][2 * kEpochsPerLaunch + 1] = nn;
-            red[warp][2 * kEpochsPerLaunch + 2] = nf;
-        }
-    }
-    __syncthreads();
-    const int row = 2 * eb.e_total + 4;
-    double* out = args.qpart + size_t(blockIdx.x) * row;
-    if (tid < 2 * eb.n) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kQuadBlock / 32; ++w) s += red[w][tid];
-        out[2 * eb.col[tid >> 1] + (tid & 1)] = s;
-    } else if (tid >= 32 && tid < 36 && eb.first) {
-        const int k = tid - 32;
-        double s = 0.0;
-        if (k < 3) {
-#pragma unroll
-            for (int w = 0; w < kQuadBlock / 32; ++w) s += red[w][2 * kEpochsPerLaunch + k];
-        }
-        out[2 * eb.e_total + k] = s;  // k == 3: multi-panel count, accumulated by quad_fix_kernel
-    } else if (tid >= 64 && tid < 64 + eb.n) {
-        const int e = tid - 64;
-        uint32_t any = 0;
-#pragma unroll
-        for (int w = 0; w < kQuadBlock / 32; ++w) any |= flagged[e][w];
-        if (any) {
-            FixEntry* fe = args.fix + atomicAdd(args.fix_count, 1u);
-            fe->item = int32_t(blockIdx.x);
-            fe->slot = e;
-#pragma unroll
-            for (int w = 0; w < kQuadBlock / 32; ++w) fe->mask[w] = flagged[e][w];
-        }
+        __syncthreads();
+        item = item_next;
+        item_next = item_after;
+        lam = lam_next;
     }
 }
 
@@ -621,6 +662,24 @@ __global__ void pi_matrix_kernel(const double* __restrict__ time, int64_t n_time
         const double x = -__dmul_rn(__dmul_rn(4.0, r), t);
         out[i] = __dmul_rn(a, exp(x));
     }
+}
+
+// numpy.nansum(pi, axis=1) of a row-major (n_rows, n_cols) matrix: one warp per row, NaN terms skipped
+// (compute.py:78, bin/tapir_compute.py:119).
+__global__ void nansum_rows_kernel(const double* __restrict__ m, int64_t n_rows, int64_t n_cols, double* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n_rows) return;
+    const double* p = m + row * n_cols;
+    double s = 0.0;
+    for (int64_t j = lane; j < n_cols; j += 32) {
+        const double v = p[j];
+        s += (v == v) ? v : 0.0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) out[row] = s;
 }
 
 __global__ void site_integrals_kernel(double a, double b, const double* __restrict__ rates, int64_t n,

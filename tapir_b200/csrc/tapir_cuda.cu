@@ -560,7 +560,14 @@ int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
             for (const EpochBatch& eb : plan.batches) {
                 // one counter per batch (d_counter[1..]); slot 0 is the profile kernel's work queue head
                 qa.fix_count = ctx->d_counter.as<uint32_t>() + 1 + k++;
-                quad_kernel<<<unsigned(plan.n_quad_items), kQuadBlock, 0, st>>>(qa, eb);
+                const unsigned qgrid = unsigned(std::min<int64_t>(plan.n_quad_items, int64_t(ctx->sm_count) * 2));
+                switch (eb.n) {
+                    case 0: quad_kernel<0><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;  // rate statistics only
+                    case 1: quad_kernel<1><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;
+                    case 2: quad_kernel<2><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;
+                    case 3: quad_kernel<3><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;
+                    default: quad_kernel<4><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;
+                }
                 CU(ctx, cudaGetLastError());
                 quad_fix_kernel<<<unsigned(ctx->sm_count * 4), 128, 0, st>>>(qa, eb);
                 CU(ctx, cudaGetLastError());
@@ -697,6 +704,27 @@ int tapir_cuda_pi_matrix(tapir_cuda_ctx* ctx, const double* time, int64_t n_time
                                                         n_rates, ctx->d_scratch_c.as<double>());
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(out, ctx->d_scratch_c.p, size_t(n) * 8, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    return TAPIR_OK;
+}
+
+int tapir_cuda_nansum_rows(tapir_cuda_ctx* ctx, const double* matrix, int64_t n_rows, int64_t n_cols, double* out)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (n_rows < 0 || n_cols < 0) return fail(ctx, TAPIR_E_INVALID, "negative size");
+    if (n_rows == 0) return TAPIR_OK;
+    if (!out || (n_cols > 0 && !matrix)) return fail(ctx, TAPIR_E_INVALID, "null pointer");
+    const size_t n = size_t(n_rows) * size_t(n_cols);
+    CU(ctx, ctx->d_scratch_c.ensure(n * 8 + 8));
+    CU(ctx, ctx->d_scratch_a.ensure(size_t(n_rows) * 8));
+    cudaStream_t st = ctx->stream;
+    if (n) CU(ctx, cudaMemcpyAsync(ctx->d_scratch_c.p, matrix, n * 8, cudaMemcpyHostToDevice, st));
+    const int64_t blocks = (n_rows * 32 + 255) / 256;
+    nansum_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(ctx->d_scratch_c.as<double>(), n_rows, n_cols,
+                                                         ctx->d_scratch_a.as<double>());
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out, ctx->d_scratch_a.p, size_t(n_rows) * 8, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     return TAPIR_OK;
 }

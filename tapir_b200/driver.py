@@ -1,0 +1,155 @@
+"""Batched multi-locus driver: tapir_compute.py's main() and worker() (bin/tapir_compute.py:84-177) with
+the per-locus numpy/scipy body replaced by ONE device pass over all loci.
+
+The command line, the glob rules, the output directory rule, the Tree_*.newick side file, the rewritten
+*.rates JSON and the sqlite database are the reference's.  ``--multiprocessing`` is accepted and means
+"parse the rate files with a thread pool"; the arithmetic always runs on the GPU.
+"""
+import argparse
+import os
+import sys
+from subprocess import PIPE, Popen
+
+import numpy
+
+from . import base, compute, db
+
+
+def get_args(argv=None):
+    """Same options as bin/tapir_compute.py:18-53."""
+    parser = argparse.ArgumentParser(description="""tapir:  compute the
+            phylogenetic informativeness of DNA loci""")
+    parser.add_argument('alignments', help="The folder of alignments", action=base.FullPaths, type=base.is_dir)
+    parser.add_argument('tree', help="The input tree", action=base.FullPaths)
+    required = parser.add_argument_group("required arguments")
+    required.add_argument('--times', help="""Comma-separated list of start
+        times of interest (MYA)""", type=base.get_list_from_ints, required=True)
+    required.add_argument('--intervals', help="""Comma-separated list of
+        interval ranges of interest (i,e. in MYA)""", type=base.get_list_from_ranges, required=True)
+    parser.add_argument('--tree-format', help="The format of the tree", dest='tree_format',
+                        choices=['nexus', 'newick'], default='newick')
+    parser.add_argument('--output', help="The path to the output directory", default=os.getcwd(),
+                        action=base.FullPaths, type=base.is_dir)
+    parser.add_argument('--hyphy', help="The path to hyphy (if not in $PATH)", default="hyphy2")
+    parser.add_argument('--template', help="""Path to the hypy
+        temlate file if in non-standard location""", default=None)
+    parser.add_argument('--threshold', help="""Minimum number of taxa without
+        a gap for a site to be considered informative""", default=3, type=int)
+    parser.add_argument('--multiprocessing', help="""Enable parallel
+        calculation of rates""", default=False, action='store_true')
+    parser.add_argument('--site-rates', default=False, action='store_true',
+                        help="Use previously calculated site rates")
+    parser.add_argument('--subset-pi-map-file', help="""Calculate PI for a
+        subset of sites. If specified, this should be a tab-delimited file
+        with the alignment file name in the 1st column, the start of the
+        interval (0-offset) in the 2nd column, and the end of the interval in
+        the 3rd column.""")
+    return parser.parse_args(argv)
+
+
+def welcome_message():
+    lines = ["tapir: high-throughput estimates of", "phylogenetic informativeness", "",
+             "(c) 2011 Brant Faircloth, Jonathan Chang,", "Mike Alfaro", "",
+             "PhyDesign was created by the Townsend Lab", "(http://phydesign.townsend.yale.edu)", "",
+             "When using tapir, please cite:", "",
+             "  - J.P. Townsend, 2007. Profiling", "    phylogenetic informativeness. Systematic",
+             "    Biology, 56(2), 222-231.", "",
+             "  - Pond, S.L.K., Frost, S.D.W., and S.V. Muse,", "    2005. Hyphy: hypothesis testing using",
+             "    phylogenies. Bioinformatics, 21(5), 676-9.", "",
+             "PI arithmetic: tapir_b200 (libtapir_cuda, sm_100a)"]
+    bar = "    " + "*" * 51
+    body = "\n".join("    * {0:<47s} *".format(x) for x in [""] + lines + [""])
+    return "\n" + bar + "\n" + body + "\n" + bar + "\n\n"
+
+
+def load_rates(params):
+    """The host half of worker() (bin/tapir_compute.py:90-108): run HyPhy when asked to, read the rate
+    JSON, cull uninformative sites, apply the subset slice.  Returns (alignment, rates)."""
+    (_time_vector, hyphy, template, towrite, output, correction, alignment, _times, _epochs, threshold, subsets) = params
+    sys.stdout.write(".")
+    sys.stdout.flush()
+    if towrite:
+        try:
+            proc = Popen([hyphy, template], stdin=PIPE, stdout=PIPE)
+        except OSError as err:
+            if err.errno == 2:
+                raise Exception("hyphy not found")
+            raise Exception("couldn't communicate with hyphy: {0}".format(err))
+        stdout, _ = proc.communicate(towrite.encode())
+        if stdout.decode(errors="replace").startswith("Error"):
+            raise Exception("hyphy error: {0}".format(stdout))
+        rates = compute.parse_site_rates(output, correction=correction)
+        good_sites = compute.get_informative_sites(alignment, threshold)
+        rates = compute.cull_uninformative_rates(rates, good_sites)
+    else:
+        rates = compute.parse_site_rates(output, correction=correction)
+    alignment_basename = os.path.basename(alignment)
+    if alignment_basename in subsets:
+        rates = rates[subsets[alignment_basename][0]:subsets[alignment_basename][1]]
+    return alignment, rates
+
+
+def worker(params):
+    """Single-locus form with the reference's signature and 7-tuple result (bin/tapir_compute.py:84-123)."""
+    alignment, rates = load_rates(params)
+    time_vector, times, epochs = params[0], params[7], params[8]
+    return compute.compute_loci([rates], time_vector, times, epochs, names=[alignment], keep_matrix=True)[0]
+
+
+def run_batch(params, threads=1):
+    """All loci of a run: host-side ingest (optionally threaded), then ONE device pass."""
+    if not params:
+        return []
+    if threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            loaded = list(pool.map(load_rates, params))
+    else:
+        loaded = [load_rates(p) for p in params]
+    time_vector, times, epochs = params[0][0], params[0][7], params[0][8]
+    return compute.compute_loci([r for _, r in loaded], time_vector, times, epochs, names=[a for a, _ in loaded])
+
+
+def get_hyphy_conf():
+    """Path of the HyPhy batch template; the template itself ships with the reference package
+    (tapir/data/models_and_rates.bf) and is out of scope here: point --template (or $TAPIR_HYPHY_TEMPLATE) at it."""
+    return os.environ.get("TAPIR_HYPHY_TEMPLATE", "models_and_rates.bf")
+
+
+def main(argv=None):
+    args = get_args(argv)
+    print(welcome_message())
+    args.output = base.create_unique_dir(args.output)
+    tree_depth, correction, tree = compute.correct_branch_lengths(args.tree, args.tree_format, d=args.output)
+    time_vector = compute.get_time(0, int(tree_depth))
+    subset_pi = dict()
+    if args.subset_pi_map_file:
+        subset_pi = dict(base.parse_subset_map_file(args.subset_pi_map_file))
+    params = []
+    template = args.template if args.template else get_hyphy_conf()
+    if not args.site_rates:
+        print("\nEstimating site rates and PI for files:")
+        for alignment in base.get_files(args.alignments, '*.nex,*.nexus'):
+            output = os.path.join(args.output, os.path.basename(alignment) + '.rates')
+            towrite = "\n".join([alignment, tree, output])
+            params.append([time_vector, args.hyphy, template, towrite, output, correction, alignment,
+                           args.times, args.intervals, args.threshold, subset_pi])
+    else:
+        print("Estimating PI for files (--site-rate option):")
+        for rate_file in base.get_files(args.alignments, '*.rates'):
+            params.append([time_vector, args.hyphy, template, None, rate_file, correction, rate_file,
+                           args.times, args.intervals, args.threshold, subset_pi])
+    threads = max(1, (os.cpu_count() or 2) - 1) if args.multiprocessing else 1
+    pis = run_batch(params, threads=threads)
+    db_name = os.path.join(args.output, 'phylogenetic-informativeness.sqlite')
+    sys.stdout.write("\nStoring results in {0}...".format(db_name))
+    sys.stdout.flush()
+    conn, c = db.create_probe_db(db_name)
+    db.insert_pi_data(conn, c, pis)
+    conn.commit()
+    sys.stdout.write("DONE")
+    sys.stdout.flush()
+    print("\n")
+    c.close()
+    conn.close()
+    return 0

@@ -194,6 +194,15 @@ class Engine:
                                              out.ctypes.data), self._ctx)
         return out
 
+    def nansum_rows(self, matrix):
+        matrix = np.ascontiguousarray(matrix, dtype=np.float64)
+        if matrix.ndim != 2:
+            raise ValueError("nansum_rows expects a 2-D array")
+        out = np.empty(matrix.shape[0], dtype=np.float64)
+        check(self._lib.tapir_cuda_nansum_rows(self._ctx, matrix.ctypes.data if matrix.size else None, matrix.shape[0],
+                                               matrix.shape[1], out.ctypes.data), self._ctx)
+        return out
+
     def site_integrals(self, a, b, rates):
         rates = np.ascontiguousarray(np.asarray(rates, dtype=np.float64).reshape(-1))
         integ = np.empty(rates.size)

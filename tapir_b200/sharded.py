@@ -1,0 +1,87 @@
+"""Locus-sharded execution over the GPUs of one box: one process per GPU (torch.distributed), every rank
+computes a size-balanced subset of the loci independently, and only the small per-locus result vectors
+are gathered to rank 0 (the reference's equivalent is Pool.map over loci, bin/tapir_compute.py:159-164).
+
+torch is used for the process group only (NCCL over NVLink on GPUs, gloo in the CPU tests); the
+arithmetic is whatever ``compute_fn`` does -- Engine.run in the product; the gloo tests pass a CPU stand-in.
+"""
+import numpy as np
+
+from .engine import BatchResult, partition_loci
+
+SMALL_FIELDS = ("pi_times", "integral", "abserr", "max_pi", "argmax_t", "argmax_epoch", "mean_rate", "n_finite",
+                "n_multi_panel")
+
+
+def shard_csr(offsets, rates, index):
+    """CSR slice holding the loci `index` (ascending) -> (offsets_p, rates_p)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    lens = offsets[index + 1] - offsets[index]
+    off_p = np.zeros(index.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=off_p[1:])
+    rates_p = np.empty(int(off_p[-1]), dtype=np.float64)
+    for j, l in enumerate(index):
+        rates_p[off_p[j]:off_p[j + 1]] = rates[offsets[l]:offsets[l + 1]]
+    return off_p, rates_p
+
+
+def pack_small(res: BatchResult):
+    """All per-locus vectors of a BatchResult as one float64 matrix [L, K + 2E + 6] (integers < 2^53 exact)."""
+    cols = [res.pi_times, res.integral, res.abserr, res.max_pi[:, None], res.argmax_t[:, None].astype(np.float64),
+            res.argmax_epoch[:, None].astype(np.float64), res.mean_rate[:, None], res.n_finite[:, None].astype(np.float64),
+            res.n_multi_panel[:, None].astype(np.float64)]
+    return np.ascontiguousarray(np.concatenate(cols, axis=1))
+
+
+def unpack_small(m, K, E, pi_net=None):
+    o = K + 2 * E
+    return BatchResult(pi_net=pi_net, pi_times=m[:, :K].copy(), integral=m[:, K:K + E].copy(),
+                       abserr=m[:, K + E:o].copy(), max_pi=m[:, o].copy(), argmax_t=m[:, o + 1].astype(np.int64),
+                       argmax_epoch=m[:, o + 2].astype(np.int32), mean_rate=m[:, o + 3].copy(),
+                       n_finite=m[:, o + 4].astype(np.int64), n_multi_panel=m[:, o + 5].astype(np.int64))
+
+
+def run_sharded(compute_fn, offsets, rates, n_grid, times, epochs, group=None, gather_profile=False, device=None):
+    """Every rank calls this with the SAME full CSR batch.  Rank r computes partition r with
+    ``compute_fn(offsets_p, rates_p, n_grid, times, epochs) -> BatchResult``; rank 0 returns the BatchResult
+    of the whole batch in the original locus order (db ids follow that order, tapir/db.py:47-49), the
+    other ranks return None.  Without torch.distributed (group is None and no default group) it is a
+    plain single-device call."""
+    import torch
+    import torch.distributed as dist
+
+    offsets = np.asarray(offsets, dtype=np.int64)
+    L = offsets.size - 1
+    K, E = len(times), len(epochs)
+    if not (dist.is_available() and dist.is_initialized()):
+        return compute_fn(offsets, rates, n_grid, times, epochs)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = partition_loci(offsets[1:] - offsets[:-1], world)
+    mine = parts[rank]
+    off_p, rates_p = shard_csr(offsets, rates, mine)
+    res = compute_fn(off_p, rates_p, n_grid, times, epochs)
+
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" and device is None else (device or "cpu")
+    width = K + 2 * E + 6
+    pad = max(len(p) for p in parts)
+
+    def gather(local, ncols):
+        buf = torch.zeros((pad, ncols), dtype=torch.float64, device=dev)
+        if local.shape[0]:
+            buf[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+        dst = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, dst, dst=0, group=group)
+        return [d.cpu().numpy() for d in dst] if rank == 0 else None
+
+    small = gather(pack_small(res), width)
+    prof = gather(res.pi_net, int(n_grid)) if gather_profile and res.pi_net is not None else None
+    if rank != 0:
+        return None
+    merged = np.empty((L, width), dtype=np.float64)
+    pi_net = np.empty((L, int(n_grid)), dtype=np.float64) if prof is not None else None
+    for r, idx in enumerate(parts):            # un-permute to the original locus order
+        merged[idx] = small[r][:idx.size]
+        if pi_net is not None:
+            pi_net[idx] = prof[r][:idx.size]
+    return unpack_small(merged, K, E, pi_net)

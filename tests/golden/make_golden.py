@@ -72,6 +72,10 @@ def synthetic_loci(seed, n_loci, smin, smax, T, nan_frac=0.05, zero_frac=0.3, fa
     return loci
 
 
+class Py2Dict(dict):
+    iteritems = dict.items
+
+
 def main():
     ref = load_reference_compute()
     out = {}
@@ -87,6 +91,7 @@ def main():
     tv = ref.get_time(0, int(depth))
     rates = ref.parse_site_rates(rate_json, cf, test=True)
     mean_rate, pi, pi_net, pi_times, pi_epochs = ref_worker(ref, tv, rates, TIMES, EPOCHS)
+    cfg1 = (rates, mean_rate, pi, pi_net, Py2Dict(pi_times), Py2Dict(pi_epochs))
     out["cfg1/rates"] = rates
     out["cfg1/mean_rate"] = numpy.float64(mean_rate)
     out["cfg1/pi"] = pi
@@ -137,6 +142,33 @@ def main():
         out[tag + "/error"] = numpy.array(ers)
         out[tag + "/mean_rate"] = numpy.array(means)
     numpy.savez_compressed(os.path.join(HERE, "reference_golden.npz"), **out)
+    # --- the reference's data fixtures the host-side tests read (small text files, copied verbatim)
+    import shutil
+    os.makedirs(os.path.join(HERE, "ref-data"), exist_ok=True)
+    for name in ["test-uniform-draw-weights.rates.json", "chr1_918.nex", "informativeness_cutoff.nex", "Euteleost.tree"]:
+        shutil.copyfile(os.path.join(TD, name), os.path.join(HERE, "ref-data", name))
+    # --- the reference's sqlite sink run on the config-1 worker result: DDL + every row it writes
+    #     (tapir/db.py is imported unmodified; its py2 dict.iteritems is supplied by a dict subclass)
+    import sqlite3
+    import tempfile
+    spec = importlib.util.spec_from_file_location("ref_db", os.path.join(REF, "tapir", "db.py"))
+    ref_db = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_db)
+
+    tmp = os.path.join(tempfile.mkdtemp(), "ref.sqlite")
+    conn, c = ref_db.create_probe_db(tmp)
+    ref_db.insert_pi_data(conn, c, [("/some/dir/locus-one.rates",) + cfg1])
+    conn.commit()
+    db_golden = {
+        "ddl": [r[0] for r in conn.execute("SELECT sql FROM sqlite_master WHERE type='table' ORDER BY name")],
+        "loci": conn.execute("SELECT * FROM loci").fetchall(),
+        "net": conn.execute("SELECT * FROM net ORDER BY time").fetchall(),
+        "discrete": conn.execute("SELECT * FROM discrete ORDER BY time").fetchall(),
+        "interval": conn.execute("SELECT * FROM interval ORDER BY interval").fetchall(),
+    }
+    conn.close()
+    with open(os.path.join(HERE, "reference_db_golden.json"), "w") as fh:
+        json.dump(db_golden, fh, indent=1)
     meta = {
         "numpy": numpy.__version__, "scipy": scipy.__version__, "python": sys.version.split()[0],
         "epochs": EPOCHS, "times": TIMES,

