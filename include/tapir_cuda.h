@@ -111,6 +111,11 @@ int tapir_cuda_download(tapir_cuda_ctx *ctx, const tapir_results *host_out);
 /* device pointers of the resident result arrays (valid until the next upload/destroy) */
 int tapir_cuda_device_results(tapir_cuda_ctx *ctx, tapir_results *device_ptrs);
 
+/* serial != 0: run the profile and the epoch-integral kernels back to back on one stream instead of
+ * concurrently on two (per-kernel tapir_timing fields are only exact in this mode; also set by
+ * TAPIR_CUDA_SERIAL_KERNELS=1 in the environment at context creation) */
+int tapir_cuda_set_serial_kernels(tapir_cuda_ctx *ctx, int serial);
+
 /* bytes moved host->device / device->host by this context since creation (for bench.py's e2e accounting) */
 int tapir_cuda_transfer_bytes(tapir_cuda_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
 

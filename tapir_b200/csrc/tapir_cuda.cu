@@ -54,6 +54,12 @@ struct DevBuf {
     T* as() const { return static_cast<T*>(p); }
 };
 
+struct DevView {  // a slice of a DevBuf
+    void* p = nullptr;
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
 struct HostBuf {  // pinned staging
     void* p = nullptr;
     size_t cap = 0;
@@ -85,27 +91,47 @@ struct Plan {
     int32_t TT = 1024, n_tiles = 1;
     int64_t n_prof_items = 0, n_quad_items = 0, ws_rows = 0;
     std::vector<EpochBatch> batches;
+    size_t small_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, small_bytes = 0;  // layout of d_small / h_small
     bool valid = false;
 };
 
 }  // namespace
 
+// One in-flight batch (or chunk of a batch): its own streams, device buffers and pinned staging, so that
+// two lanes can overlap H2D, kernels and D2H of consecutive chunks.
+struct Lane {
+    cudaStream_t stream = nullptr;    // copies, profile, finalize
+    cudaStream_t stream_q = nullptr;  // epoch-integral kernels, concurrent with the profile kernel
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    Plan plan;
+    // inputs: the rate stream, and ONE buffer holding every work list (a single H2D copy per batch)
+    DevBuf d_rates, d_work, d_counter;
+    DevView d_prof_items, d_quad_items, d_nsplit, d_ws_base, d_qitem_begin, d_time_idx;
+    // intermediates
+    DevBuf d_ws, d_tile_max, d_tile_arg, d_qpart, d_fix;
+    // results: the profile, and ONE buffer holding every small per-locus vector (a single D2H copy per batch)
+    DevBuf d_pi_net, d_small;
+    DevView d_pi_times, d_integral, d_abserr, d_max_pi, d_argmax_t, d_argmax_epoch, d_mean_rate, d_n_finite, d_n_multi;
+    HostBuf h_stage, h_small;
+    // host destination of the small vectors of the batch in flight (scattered after the D2H copy lands)
+    tapir_results pending_out = {};
+    int64_t pending_row0 = 0;
+    bool pending = false;
+    DevBuf* all_bufs[10] = {&d_rates, &d_work, &d_counter, &d_ws, &d_tile_max, &d_tile_arg, &d_qpart, &d_fix, &d_pi_net, &d_small};
+};
+
+constexpr int kLanes = 2;
+
 struct tapir_cuda_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int serial_kernels = 0;  // 1: profile and integral kernels on one stream (per-kernel timing is then exact)
     std::string last_error;
-    Plan plan;
-    // inputs / work lists
-    DevBuf d_rates, d_prof_items, d_quad_items, d_nsplit, d_ws_base, d_qitem_begin, d_time_idx, d_counter;
-    // intermediates
-    DevBuf d_ws, d_tile_max, d_tile_arg, d_qpart, d_fix;
-    // results
-    DevBuf d_pi_net, d_pi_times, d_integral, d_abserr, d_max_pi, d_argmax_t, d_argmax_epoch, d_mean_rate, d_n_finite,
-        d_n_multi;
-    DevBuf d_scratch_a, d_scratch_b, d_scratch_c, d_flush;
-    HostBuf h_stage;
+    Lane lanes[kLanes];
+    cudaStream_t stream = nullptr;  // == lanes[0].stream; used by the element-wise / measurement entry points
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    DevBuf d_scratch_a, d_scratch_b, d_scratch_c, d_flush, d_counter;
     uint64_t bytes_h2d = 0, bytes_d2h = 0;
 };
 
@@ -161,7 +187,7 @@ int choose_rh(int64_t T)
 }
 
 template <int RH>
-cudaError_t launch_profile(tapir_cuda_ctx* ctx, const ProfArgs& pa, int64_t n_items)
+cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, int64_t n_items)
 {
     using Cfg = ProfCfg<RH>;
     static bool configured[64] = {false};
@@ -180,7 +206,7 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, const ProfArgs& pa, int64_t n_it
     const int64_t need = (n_items + kProfWarps - 1) / kProfWarps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    profile_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ctx->stream>>>(pa);
+    profile_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
     return cudaGetLastError();
 }
 
@@ -315,8 +341,20 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
                     prop.major, prop.minor);
     }
     ctx->sm_count = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    {
+        const char* env = getenv("TAPIR_CUDA_SERIAL_KERNELS");
+        ctx->serial_kernels = (env && env[0] == '1') ? 1 : 0;
+    }
+    e = cudaSuccess;
+    for (Lane& ln : ctx->lanes) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.stream_q, cudaStreamNonBlocking);
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ln.ev[i]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_join, cudaEventDisableTiming);
+    }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    ctx->stream = ctx->lanes[0].stream;
     if (e != cudaSuccess) {
         tapir_cuda_destroy(ctx);
         cudaGetLastError();
@@ -330,18 +368,23 @@ int tapir_cuda_destroy(tapir_cuda_ctx* ctx)
 {
     if (!ctx) return TAPIR_OK;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_rates,     &ctx->d_prof_items, &ctx->d_quad_items, &ctx->d_nsplit,    &ctx->d_ws_base,
-                      &ctx->d_qitem_begin, &ctx->d_time_idx, &ctx->d_counter,    &ctx->d_ws,        &ctx->d_tile_max,
-                      &ctx->d_tile_arg,  &ctx->d_qpart,      &ctx->d_fix,        &ctx->d_pi_net,     &ctx->d_pi_times,  &ctx->d_integral,
-                      &ctx->d_abserr,    &ctx->d_max_pi,     &ctx->d_argmax_t,   &ctx->d_argmax_epoch, &ctx->d_mean_rate,
-                      &ctx->d_n_finite,  &ctx->d_n_multi,    &ctx->d_scratch_a,  &ctx->d_scratch_b, &ctx->d_scratch_c,
-                      &ctx->d_flush};
+    for (Lane& ln : ctx->lanes) {
+        if (ln.stream) cudaStreamSynchronize(ln.stream);
+        if (ln.stream_q) cudaStreamSynchronize(ln.stream_q);
+        for (DevBuf* b : ln.all_bufs) b->release();
+        ln.h_stage.release();
+        ln.h_small.release();
+        for (auto& ev : ln.ev)
+            if (ev) cudaEventDestroy(ev);
+        if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
+        if (ln.ev_join) cudaEventDestroy(ln.ev_join);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+        if (ln.stream_q) cudaStreamDestroy(ln.stream_q);
+    }
+    DevBuf* bufs[] = {&ctx->d_scratch_a, &ctx->d_scratch_b, &ctx->d_scratch_c, &ctx->d_flush, &ctx->d_counter};
     for (DevBuf* b : bufs) b->release();
-    ctx->h_stage.release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
     return TAPIR_OK;
@@ -371,20 +414,23 @@ int tapir_cuda_host_free(void* ptr)
     return TAPIR_OK;
 }
 
-int tapir_cuda_upload(tapir_cuda_ctx* ctx, const tapir_problem* p)
-{
-    int rc = bind(ctx);
-    if (rc) return rc;
-    ctx->plan.valid = false;
-    if ((rc = validate(ctx, p)) != TAPIR_OK) return rc;
+}  // extern "C"
 
-    Plan& plan = ctx->plan;
-    plan.L = p->n_loci;
+namespace {
+
+// Build the work lists of loci [l0, l1) of an already validated problem on lane `ln` and start their H2D copies.
+int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l0, int64_t l1, bool sync)
+{
+    ln.plan.valid = false;
+    Plan& plan = ln.plan;
+    const int64_t* off = &p->offsets[l0];       // off[0..L]; site indices are taken relative to off[0]
+    const int64_t base = (l1 > l0) ? off[0] : 0;
+    plan.L = l1 - l0;
     plan.T = p->n_grid;
     plan.K = p->n_times;
     plan.E = p->n_epochs;
     plan.flags = p->flags;
-    plan.nnz = plan.L ? p->offsets[plan.L] : 0;
+    plan.nnz = plan.L ? off[plan.L] - base : 0;
     plan.rh = choose_rh(std::max<int64_t>(plan.T, 1));
     plan.TT = 32 * 8 * plan.rh;
     plan.n_tiles = int32_t(std::max<int64_t>(1, (plan.T + plan.TT - 1) / plan.TT));
@@ -405,7 +451,7 @@ int tapir_cuda_upload(tapir_cuda_ctx* ctx, const tapir_problem* p)
     std::vector<int64_t> ws_base(L), qitem_begin(L + 1);
     int64_t n_prof = 0, n_quad = 0, ws_rows = 0;
     for (int64_t l = 0; l < L; ++l) {
-        const int64_t s = p->offsets[l + 1] - p->offsets[l];
+        const int64_t s = off[l + 1] - off[l];
         if (s > INT32_MAX) return fail(ctx, TAPIR_E_INVALID, "locus %lld has too many sites", (long long)l);
         int64_t ns = (s + chunk_sites - 1) / chunk_sites;
         if (ns < 1) ns = 1;
@@ -430,16 +476,16 @@ int tapir_cuda_upload(tapir_cuda_ctx* ctx, const tapir_problem* p)
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_prof = 0, o_quad = o_prof + al(b_prof), o_ns = o_quad + al(b_quad), o_wb = o_ns + al(b_ns),
                  o_qb = o_wb + al(b_wb), o_ti = o_qb + al(b_qb), total = o_ti + al(b_ti);
-    CU(ctx, ctx->h_stage.ensure(total));
-    char* hs = ctx->h_stage.as<char>();
+    CU(ctx, ln.h_stage.ensure(total));
+    char* hs = ln.h_stage.as<char>();
     ProfItem* pi = reinterpret_cast<ProfItem*>(hs + o_prof);
     QuadItem* qi = reinterpret_cast<QuadItem*>(hs + o_quad);
     {
         int64_t k = 0, q = 0;
         bool ragged = false;
         for (int64_t l = 0; l < L; ++l) {
-            const int64_t s0 = p->offsets[l], s = p->offsets[l + 1] - s0;
-            if (l && s != p->offsets[1] - p->offsets[0]) ragged = true;
+            const int64_t s0 = off[l] - base, s = off[l + 1] - off[l];
+            if (l && s != off[1] - off[0]) ragged = true;
             const int64_t ns = nsplit[l];
             // equal site ranges rounded to multiples of 32
             const int64_t per = ns > 1 ? (((s + ns - 1) / ns + 31) / 32) * 32 : s;
@@ -476,105 +522,118 @@ int tapir_cuda_upload(tapir_cuda_ctx* ctx, const tapir_problem* p)
 
     // ---- device buffers ----
     const size_t qrow = size_t(2 * plan.E + 4);
-    CU(ctx, ctx->d_rates.ensure(size_t(plan.nnz) * 8 + 8));
-    CU(ctx, ctx->d_prof_items.ensure(b_prof + 8));
-    CU(ctx, ctx->d_quad_items.ensure(b_quad + 8));
-    CU(ctx, ctx->d_nsplit.ensure(b_ns + 8));
-    CU(ctx, ctx->d_ws_base.ensure(b_wb + 8));
-    CU(ctx, ctx->d_qitem_begin.ensure(b_qb));
-    CU(ctx, ctx->d_time_idx.ensure(b_ti + 8));
-    CU(ctx, ctx->d_counter.ensure(256));
-    CU(ctx, ctx->d_ws.ensure(size_t(ws_rows) * plan.TT * 8 + 8));
-    CU(ctx, ctx->d_tile_max.ensure(size_t(L) * plan.n_tiles * 8 + 8));
-    CU(ctx, ctx->d_tile_arg.ensure(size_t(L) * plan.n_tiles * 8 + 8));
-    CU(ctx, ctx->d_qpart.ensure(size_t(n_quad) * qrow * 8 + 8));
-    CU(ctx, ctx->d_fix.ensure(size_t(n_quad) * kEpochsPerLaunch * sizeof(FixEntry) + 8));
-    CU(ctx, ctx->d_pi_net.ensure(size_t(L) * plan.T * 8 + 16));
-    CU(ctx, ctx->d_pi_times.ensure(size_t(L) * plan.K * 8 + 8));
-    CU(ctx, ctx->d_integral.ensure(size_t(L) * plan.E * 8 + 8));
-    CU(ctx, ctx->d_abserr.ensure(size_t(L) * plan.E * 8 + 8));
-    CU(ctx, ctx->d_max_pi.ensure(size_t(L) * 8 + 8));
-    CU(ctx, ctx->d_argmax_t.ensure(size_t(L) * 8 + 8));
-    CU(ctx, ctx->d_argmax_epoch.ensure(size_t(L) * 4 + 8));
-    CU(ctx, ctx->d_mean_rate.ensure(size_t(L) * 8 + 8));
-    CU(ctx, ctx->d_n_finite.ensure(size_t(L) * 8 + 8));
-    CU(ctx, ctx->d_n_multi.ensure(size_t(L) * 8 + 8));
+    const size_t Ls = size_t(L), Ks = size_t(plan.K), Es = size_t(plan.E);
+    const size_t small_sizes[9] = {Ls * Ks * 8, Ls * Es * 8, Ls * Es * 8, Ls * 8, Ls * 8, Ls * 8, Ls * 8, Ls * 8, Ls * 4};
+    plan.small_bytes = 0;
+    for (int i = 0; i < 9; ++i) {
+        plan.small_off[i] = plan.small_bytes;
+        plan.small_bytes += al(small_sizes[i]);
+    }
+    CU(ctx, ln.d_rates.ensure(size_t(plan.nnz) * 8 + 8));
+    CU(ctx, ln.d_work.ensure(total + 8));
+    CU(ctx, ln.d_counter.ensure(256));
+    CU(ctx, ln.d_ws.ensure(size_t(ws_rows) * plan.TT * 8 + 8));
+    CU(ctx, ln.d_tile_max.ensure(size_t(L) * plan.n_tiles * 8 + 8));
+    CU(ctx, ln.d_tile_arg.ensure(size_t(L) * plan.n_tiles * 8 + 8));
+    CU(ctx, ln.d_qpart.ensure(size_t(n_quad) * qrow * 8 + 8));
+    CU(ctx, ln.d_fix.ensure(size_t(n_quad) * kEpochsPerLaunch * sizeof(FixEntry) + 8));
+    CU(ctx, ln.d_pi_net.ensure(size_t(L) * plan.T * 8 + 16));
+    CU(ctx, ln.d_small.ensure(plan.small_bytes + 8));
+    CU(ctx, ln.h_small.ensure(plan.small_bytes + 8));
+    {
+        char* w = ln.d_work.as<char>();
+        ln.d_prof_items.p = w + o_prof;
+        ln.d_quad_items.p = w + o_quad;
+        ln.d_nsplit.p = w + o_ns;
+        ln.d_ws_base.p = w + o_wb;
+        ln.d_qitem_begin.p = w + o_qb;
+        ln.d_time_idx.p = w + o_ti;
+        char* r = ln.d_small.as<char>();
+        DevView* views[9] = {&ln.d_pi_times, &ln.d_integral,  &ln.d_abserr,   &ln.d_max_pi,      &ln.d_argmax_t,
+                             &ln.d_mean_rate, &ln.d_n_finite, &ln.d_n_multi, &ln.d_argmax_epoch};
+        for (int i = 0; i < 9; ++i) views[i]->p = r + plan.small_off[i];
+    }
 
-    cudaStream_t st = ctx->stream;
-    ctx->bytes_h2d += size_t(plan.nnz) * 8 + b_prof + b_quad + b_ns + b_wb + b_qb + b_ti;
-    if (plan.nnz) CU(ctx, cudaMemcpyAsync(ctx->d_rates.p, p->rates, size_t(plan.nnz) * 8, cudaMemcpyHostToDevice, st));
-    if (b_prof) CU(ctx, cudaMemcpyAsync(ctx->d_prof_items.p, hs + o_prof, b_prof, cudaMemcpyHostToDevice, st));
-    if (b_quad) CU(ctx, cudaMemcpyAsync(ctx->d_quad_items.p, hs + o_quad, b_quad, cudaMemcpyHostToDevice, st));
-    if (b_ns) CU(ctx, cudaMemcpyAsync(ctx->d_nsplit.p, hs + o_ns, b_ns, cudaMemcpyHostToDevice, st));
-    if (b_wb) CU(ctx, cudaMemcpyAsync(ctx->d_ws_base.p, hs + o_wb, b_wb, cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaMemcpyAsync(ctx->d_qitem_begin.p, hs + o_qb, b_qb, cudaMemcpyHostToDevice, st));
-    if (b_ti) CU(ctx, cudaMemcpyAsync(ctx->d_time_idx.p, hs + o_ti, b_ti, cudaMemcpyHostToDevice, st));
-    CU(ctx, cudaStreamSynchronize(st));
+    cudaStream_t st = ln.stream;
+    ctx->bytes_h2d += size_t(plan.nnz) * 8 + total;
+    if (plan.nnz) CU(ctx, cudaMemcpyAsync(ln.d_rates.p, p->rates + base, size_t(plan.nnz) * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaMemcpyAsync(ln.d_work.p, hs, total, cudaMemcpyHostToDevice, st));
+    if (sync) CU(ctx, cudaStreamSynchronize(st));
     plan.valid = true;
     return TAPIR_OK;
 }
 
-int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
+// Launch the kernels of the lane's resident batch.  Unless ctx->serial_kernels is set, the epoch-integral
+// kernels run on the lane's second stream, concurrently with the profile kernel, and join before finalize.
+int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
-    Plan& plan = ctx->plan;
+    Plan& plan = ln.plan;
     if (!plan.valid) return fail(ctx, TAPIR_E_STATE, "tapir_cuda_compute called before a successful tapir_cuda_upload");
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ln.stream;
+    const bool fork = !ctx->serial_kernels && plan.L > 0 && plan.n_quad_items > 0 && plan.n_prof_items > 0 && plan.T > 0;
+    cudaStream_t sq = fork ? ln.stream_q : st;
     int launches = 0;
-    CU(ctx, cudaEventRecord(ctx->ev[0], st));
+    CU(ctx, cudaEventRecord(ln.ev[0], st));
     if (plan.L > 0) {
-        CU(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, st));
+        CU(ctx, cudaMemsetAsync(ln.d_counter.p, 0, 256, st));
+        if (fork) {
+            CU(ctx, cudaEventRecord(ln.ev_fork, st));
+            CU(ctx, cudaStreamWaitEvent(sq, ln.ev_fork, 0));
+        }
         if (plan.n_prof_items > 0 && plan.T > 0) {
 
             ProfArgs pa;
-            pa.rates = ctx->d_rates.as<double>();
-            pa.items = ctx->d_prof_items.as<ProfItem>();
-            pa.counter = ctx->d_counter.as<uint32_t>();
-            pa.pi_net = ctx->d_pi_net.as<double>();
-            pa.ws = ctx->d_ws.as<double>();
-            pa.tile_max = ctx->d_tile_max.as<double>();
-            pa.tile_arg = ctx->d_tile_arg.as<int64_t>();
+            pa.rates = ln.d_rates.as<double>();
+            pa.items = ln.d_prof_items.as<ProfItem>();
+            pa.counter = ln.d_counter.as<uint32_t>();
+            pa.pi_net = ln.d_pi_net.as<double>();
+            pa.ws = ln.d_ws.as<double>();
+            pa.tile_max = ln.d_tile_max.as<double>();
+            pa.tile_arg = ln.d_tile_arg.as<int64_t>();
             pa.T = plan.T;
             pa.n_items = int32_t(plan.n_prof_items);
             pa.n_tiles = plan.n_tiles;
             cudaError_t e = cudaSuccess;
             switch (plan.rh) {
-                case 1: e = launch_profile<1>(ctx, pa, plan.n_prof_items); break;
-                case 2: e = launch_profile<2>(ctx, pa, plan.n_prof_items); break;
-                case 4: e = launch_profile<4>(ctx, pa, plan.n_prof_items); break;
-                default: e = launch_profile<8>(ctx, pa, plan.n_prof_items); break;
+                case 1: e = launch_profile<1>(ctx, ln, pa, plan.n_prof_items); break;
+                case 2: e = launch_profile<2>(ctx, ln, pa, plan.n_prof_items); break;
+                case 4: e = launch_profile<4>(ctx, ln, pa, plan.n_prof_items); break;
+                default: e = launch_profile<8>(ctx, ln, pa, plan.n_prof_items); break;
             }
             CU(ctx, e);
             ++launches;
         }
-        CU(ctx, cudaEventRecord(ctx->ev[1], st));
+        CU(ctx, cudaEventRecord(ln.ev[1], st));
         if (plan.n_quad_items > 0) {
             QuadArgs qa;
-            qa.rates = ctx->d_rates.as<double>();
-            qa.items = ctx->d_quad_items.as<QuadItem>();
-            qa.qpart = ctx->d_qpart.as<double>();
-            qa.fix = ctx->d_fix.as<FixEntry>();
+            qa.rates = ln.d_rates.as<double>();
+            qa.items = ln.d_quad_items.as<QuadItem>();
+            qa.qpart = ln.d_qpart.as<double>();
+            qa.fix = ln.d_fix.as<FixEntry>();
             qa.n_items = int32_t(plan.n_quad_items);
             int k = 0;
             for (const EpochBatch& eb : plan.batches) {
                 // one counter per batch (d_counter[1..]); slot 0 is the profile kernel's work queue head
-                qa.fix_count = ctx->d_counter.as<uint32_t>() + 1 + k++;
+                qa.fix_count = ln.d_counter.as<uint32_t>() + 1 + k++;
                 const unsigned qgrid = unsigned(std::min<int64_t>(plan.n_quad_items, int64_t(ctx->sm_count) * 2));
                 switch (eb.n) {
-                    case 0: quad_kernel<0><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;  // rate statistics only
-                    case 1: quad_kernel<1><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;
-                    case 2: quad_kernel<2><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;
-                    case 3: quad_kernel<3><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;
-                    default: quad_kernel<4><<<qgrid, kQuadBlock, 0, st>>>(qa, eb); break;
+                    case 0: quad_kernel<0><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;  // rate statistics only
+                    case 1: quad_kernel<1><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;
+                    case 2: quad_kernel<2><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;
+                    case 3: quad_kernel<3><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;
+                    default: quad_kernel<4><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;
                 }
                 CU(ctx, cudaGetLastError());
-                quad_fix_kernel<<<unsigned(ctx->sm_count * 4), 128, 0, st>>>(qa, eb);
+                quad_fix_kernel<<<unsigned(ctx->sm_count * 4), 128, 0, sq>>>(qa, eb);
                 CU(ctx, cudaGetLastError());
                 launches += 2;
             }
         }
-        CU(ctx, cudaEventRecord(ctx->ev[2], st));
+        if (fork) {
+            CU(ctx, cudaEventRecord(ln.ev_join, sq));
+            CU(ctx, cudaStreamWaitEvent(st, ln.ev_join, 0));
+        }
+        CU(ctx, cudaEventRecord(ln.ev[2], st));
         {
             FinalArgs fa;
             fa.n_loci = plan.L;
@@ -583,88 +642,116 @@ int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
             fa.n_tiles = plan.T > 0 ? plan.n_tiles : 0;
             fa.K = plan.T > 0 ? plan.K : 0;
             fa.E = plan.E;
-            fa.nsplit = ctx->d_nsplit.as<int32_t>();
-            fa.ws_base = ctx->d_ws_base.as<int64_t>();
-            fa.qitem_begin = ctx->d_qitem_begin.as<int64_t>();
-            fa.time_idx = ctx->d_time_idx.as<int64_t>();
-            fa.ws = ctx->d_ws.as<double>();
-            fa.tile_max = ctx->d_tile_max.as<double>();
-            fa.tile_arg = ctx->d_tile_arg.as<int64_t>();
-            fa.qpart = ctx->d_qpart.as<double>();
-            fa.pi_net = ctx->d_pi_net.as<double>();
-            fa.pi_times = ctx->d_pi_times.as<double>();
-            fa.integral = ctx->d_integral.as<double>();
-            fa.abserr = ctx->d_abserr.as<double>();
-            fa.max_pi = ctx->d_max_pi.as<double>();
-            fa.argmax_t = ctx->d_argmax_t.as<int64_t>();
-            fa.argmax_epoch = ctx->d_argmax_epoch.as<int32_t>();
-            fa.mean_rate = ctx->d_mean_rate.as<double>();
-            fa.n_finite = ctx->d_n_finite.as<int64_t>();
-            fa.n_multi = ctx->d_n_multi.as<int64_t>();
+            fa.nsplit = ln.d_nsplit.as<int32_t>();
+            fa.ws_base = ln.d_ws_base.as<int64_t>();
+            fa.qitem_begin = ln.d_qitem_begin.as<int64_t>();
+            fa.time_idx = ln.d_time_idx.as<int64_t>();
+            fa.ws = ln.d_ws.as<double>();
+            fa.tile_max = ln.d_tile_max.as<double>();
+            fa.tile_arg = ln.d_tile_arg.as<int64_t>();
+            fa.qpart = ln.d_qpart.as<double>();
+            fa.pi_net = ln.d_pi_net.as<double>();
+            fa.pi_times = ln.d_pi_times.as<double>();
+            fa.integral = ln.d_integral.as<double>();
+            fa.abserr = ln.d_abserr.as<double>();
+            fa.max_pi = ln.d_max_pi.as<double>();
+            fa.argmax_t = ln.d_argmax_t.as<int64_t>();
+            fa.argmax_epoch = ln.d_argmax_epoch.as<int32_t>();
+            fa.mean_rate = ln.d_mean_rate.as<double>();
+            fa.n_finite = ln.d_n_finite.as<int64_t>();
+            fa.n_multi = ln.d_n_multi.as<int64_t>();
             const int64_t blocks = (plan.L * 32 + 127) / 128;
             finalize_kernel<<<unsigned(blocks), 128, 0, st>>>(fa);
             CU(ctx, cudaGetLastError());
             ++launches;
         }
     } else {
-        CU(ctx, cudaEventRecord(ctx->ev[1], st));
-        CU(ctx, cudaEventRecord(ctx->ev[2], st));
+        CU(ctx, cudaEventRecord(ln.ev[1], st));
+        CU(ctx, cudaEventRecord(ln.ev[2], st));
     }
-    CU(ctx, cudaEventRecord(ctx->ev[3], st));
-    CU(ctx, cudaStreamSynchronize(st));
+    CU(ctx, cudaEventRecord(ln.ev[3], st));
+    if (sync || timing) CU(ctx, cudaStreamSynchronize(st));
     if (timing) {
         memset(timing, 0, sizeof *timing);
-        CU(ctx, cudaEventElapsedTime(&timing->total_ms, ctx->ev[0], ctx->ev[3]));
-        CU(ctx, cudaEventElapsedTime(&timing->profile_ms, ctx->ev[0], ctx->ev[1]));
-        CU(ctx, cudaEventElapsedTime(&timing->quad_ms, ctx->ev[1], ctx->ev[2]));
-        CU(ctx, cudaEventElapsedTime(&timing->finalize_ms, ctx->ev[2], ctx->ev[3]));
+        CU(ctx, cudaEventElapsedTime(&timing->total_ms, ln.ev[0], ln.ev[3]));
+        CU(ctx, cudaEventElapsedTime(&timing->profile_ms, ln.ev[0], ln.ev[1]));
+        CU(ctx, cudaEventElapsedTime(&timing->quad_ms, ln.ev[1], ln.ev[2]));
+        CU(ctx, cudaEventElapsedTime(&timing->finalize_ms, ln.ev[2], ln.ev[3]));
         timing->launches = launches;
     }
     return TAPIR_OK;
 }
 
-int tapir_cuda_download(tapir_cuda_ctx* ctx, const tapir_results* out)
+// After the lane's D2H copy has landed in h_small: scatter the small vectors into the caller's arrays.
+int lane_finish(tapir_cuda_ctx* ctx, Lane& ln)
 {
-    int rc = bind(ctx);
-    if (rc) return rc;
-    const Plan& plan = ctx->plan;
-    if (!plan.valid) return fail(ctx, TAPIR_E_STATE, "tapir_cuda_download called before upload/compute");
-    if (!out) return fail(ctx, TAPIR_E_INVALID, "null results");
-    cudaStream_t st = ctx->stream;
-    const size_t L = size_t(plan.L);
-    auto copy = [&](void* dst, const DevBuf& src, size_t bytes) -> cudaError_t {
-        if (!dst || bytes == 0) return cudaSuccess;
-        ctx->bytes_d2h += bytes;
-        return cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, st);
-    };
-    if (plan.flags & TAPIR_WANT_PROFILE) CU(ctx, copy(out->pi_net, ctx->d_pi_net, L * size_t(plan.T) * 8));
-    CU(ctx, copy(out->pi_times, ctx->d_pi_times, L * size_t(plan.T > 0 ? plan.K : 0) * 8));
-    CU(ctx, copy(out->integral, ctx->d_integral, L * size_t(plan.E) * 8));
-    CU(ctx, copy(out->abserr, ctx->d_abserr, L * size_t(plan.E) * 8));
-    CU(ctx, copy(out->max_pi, ctx->d_max_pi, L * 8));
-    CU(ctx, copy(out->argmax_t, ctx->d_argmax_t, L * 8));
-    CU(ctx, copy(out->argmax_epoch, ctx->d_argmax_epoch, L * 4));
-    CU(ctx, copy(out->mean_rate, ctx->d_mean_rate, L * 8));
-    CU(ctx, copy(out->n_finite, ctx->d_n_finite, L * 8));
-    CU(ctx, copy(out->n_multi_panel, ctx->d_n_multi, L * 8));
-    CU(ctx, cudaStreamSynchronize(st));
+    CU(ctx, cudaStreamSynchronize(ln.stream));
+    if (!ln.pending) return TAPIR_OK;
+    ln.pending = false;
+    const Plan& plan = ln.plan;
+    const tapir_results& out = ln.pending_out;
+    const size_t L = size_t(plan.L), r0 = size_t(ln.pending_row0);
+    const size_t K = size_t(plan.T > 0 ? plan.K : 0), E = size_t(plan.E);
+    const char* h = ln.h_small.as<char>();
+    void* dst[9] = {out.pi_times, out.integral, out.abserr, out.max_pi, out.argmax_t, out.mean_rate, out.n_finite,
+                    out.n_multi_panel, out.argmax_epoch};
+    const size_t row_bytes[9] = {K * 8, E * 8, E * 8, 8, 8, 8, 8, 8, 4};
+    for (int i = 0; i < 9; ++i)
+        if (dst[i] && L * row_bytes[i]) memcpy(static_cast<char*>(dst[i]) + r0 * row_bytes[i], h + plan.small_off[i], L * row_bytes[i]);
     return TAPIR_OK;
 }
+
+// Start copying the lane's results to the host: the profile straight into rows [l0, l0 + L) of the caller's
+// array, the small vectors as one block into pinned staging (lane_finish scatters them).
+int lane_download(tapir_cuda_ctx* ctx, Lane& ln, const tapir_results* out, int64_t l0, bool sync)
+{
+    const Plan& plan = ln.plan;
+    if (!plan.valid) return fail(ctx, TAPIR_E_STATE, "tapir_cuda_download called before upload/compute");
+    if (!out) return fail(ctx, TAPIR_E_INVALID, "null results");
+    cudaStream_t st = ln.stream;
+    const size_t L = size_t(plan.L);
+    if ((plan.flags & TAPIR_WANT_PROFILE) && out->pi_net && L * size_t(plan.T)) {
+        const size_t row = size_t(plan.T) * 8;
+        ctx->bytes_d2h += L * row;
+        CU(ctx, cudaMemcpyAsync(reinterpret_cast<char*>(out->pi_net) + size_t(l0) * row, ln.d_pi_net.p, L * row,
+                                cudaMemcpyDeviceToHost, st));
+    }
+    if (plan.small_bytes) {
+        ctx->bytes_d2h += plan.small_bytes;
+        CU(ctx, cudaMemcpyAsync(ln.h_small.p, ln.d_small.p, plan.small_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    ln.pending_out = *out;
+    ln.pending_row0 = l0;
+    ln.pending = true;
+    return sync ? lane_finish(ctx, ln) : TAPIR_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int tapir_cuda_device_results(tapir_cuda_ctx* ctx, tapir_results* d)
 {
     if (!ctx || !d) return fail(ctx, TAPIR_E_INVALID, "null argument");
-    if (!ctx->plan.valid) return fail(ctx, TAPIR_E_STATE, "no resident batch");
-    d->pi_net = ctx->d_pi_net.as<double>();
-    d->pi_times = ctx->d_pi_times.as<double>();
-    d->integral = ctx->d_integral.as<double>();
-    d->abserr = ctx->d_abserr.as<double>();
-    d->max_pi = ctx->d_max_pi.as<double>();
-    d->argmax_t = ctx->d_argmax_t.as<int64_t>();
-    d->argmax_epoch = ctx->d_argmax_epoch.as<int32_t>();
-    d->mean_rate = ctx->d_mean_rate.as<double>();
-    d->n_finite = ctx->d_n_finite.as<int64_t>();
-    d->n_multi_panel = ctx->d_n_multi.as<int64_t>();
+    const Lane& ln = ctx->lanes[0];
+    if (!ln.plan.valid) return fail(ctx, TAPIR_E_STATE, "no resident batch");
+    d->pi_net = ln.d_pi_net.as<double>();
+    d->pi_times = ln.d_pi_times.as<double>();
+    d->integral = ln.d_integral.as<double>();
+    d->abserr = ln.d_abserr.as<double>();
+    d->max_pi = ln.d_max_pi.as<double>();
+    d->argmax_t = ln.d_argmax_t.as<int64_t>();
+    d->argmax_epoch = ln.d_argmax_epoch.as<int32_t>();
+    d->mean_rate = ln.d_mean_rate.as<double>();
+    d->n_finite = ln.d_n_finite.as<int64_t>();
+    d->n_multi_panel = ln.d_n_multi.as<int64_t>();
+    return TAPIR_OK;
+}
+
+int tapir_cuda_set_serial_kernels(tapir_cuda_ctx* ctx, int serial)
+{
+    if (!ctx) return fail(nullptr, TAPIR_E_INVALID, "null context");
+    ctx->serial_kernels = serial ? 1 : 0;
     return TAPIR_OK;
 }
 
@@ -676,12 +763,68 @@ int tapir_cuda_transfer_bytes(tapir_cuda_ctx* ctx, uint64_t* h2d, uint64_t* d2h)
     return TAPIR_OK;
 }
 
-int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* problem, const tapir_results* host_out)
+int tapir_cuda_upload(tapir_cuda_ctx* ctx, const tapir_problem* p)
 {
-    int rc = tapir_cuda_upload(ctx, problem);
+    int rc = bind(ctx);
     if (rc) return rc;
-    if ((rc = tapir_cuda_compute(ctx, nullptr)) != TAPIR_OK) return rc;
-    return tapir_cuda_download(ctx, host_out);
+    ctx->lanes[0].plan.valid = false;
+    if ((rc = validate(ctx, p)) != TAPIR_OK) return rc;
+    return lane_upload(ctx, ctx->lanes[0], p, 0, p->n_loci, true);
+}
+
+int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    return lane_compute(ctx, ctx->lanes[0], timing, true);
+}
+
+int tapir_cuda_download(tapir_cuda_ctx* ctx, const tapir_results* out)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    return lane_download(ctx, ctx->lanes[0], out, 0, true);
+}
+
+// Whole path with host buffers.  Large batches are cut into chunks of loci that alternate between the two
+// lanes, so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k (PCIe is
+// full duplex; a step of this path moves ~3x more bytes out than in).
+int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_results* host_out)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    for (Lane& ln : ctx->lanes) ln.plan.valid = false;
+    if ((rc = validate(ctx, p)) != TAPIR_OK) return rc;
+    if (!host_out) return fail(ctx, TAPIR_E_INVALID, "null results");
+    const int64_t L = p->n_loci;
+    const int64_t nnz = L ? p->offsets[L] : 0;
+    const double bytes = double(nnz) * 8.0 + ((p->flags & TAPIR_WANT_PROFILE) ? double(L) * double(p->n_grid) * 8.0 : 0.0);
+    int64_t n_chunks = int64_t(bytes / double(12 << 20));
+    n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, 16));
+    if (L < 64 * n_chunks) n_chunks = 1;  // few (possibly huge) loci: one pass, split over sites instead
+    int64_t l0 = 0;
+    for (int64_t k = 0; k < n_chunks; ++k) {
+        // chunk boundaries at equal shares of the sites
+        int64_t l1 = L;
+        if (k + 1 < n_chunks) {
+            const int64_t want = nnz / n_chunks * (k + 1);
+            l1 = std::lower_bound(p->offsets + l0, p->offsets + L, want) - p->offsets;
+            l1 = std::max(l1, l0 + 1);
+            l1 = std::min(l1, L - (n_chunks - 1 - k));
+        }
+        Lane& ln = ctx->lanes[k % kLanes];
+        if (k >= kLanes && (rc = lane_finish(ctx, ln)) != TAPIR_OK) break;  // its previous chunk (and its staging) is done
+        if ((rc = lane_upload(ctx, ln, p, l0, l1, false)) != TAPIR_OK) break;
+        if ((rc = lane_compute(ctx, ln, nullptr, false)) != TAPIR_OK) break;
+        if ((rc = lane_download(ctx, ln, host_out, l0, false)) != TAPIR_OK) break;
+        l0 = l1;
+    }
+    for (Lane& ln : ctx->lanes) {
+        const int rc2 = lane_finish(ctx, ln);
+        if (rc == TAPIR_OK) rc = rc2;
+    }
+    if (n_chunks > 1) ctx->lanes[0].plan.valid = false;  // the resident data is one chunk, not the batch
+    return rc;
 }
 
 int tapir_cuda_pi_matrix(tapir_cuda_ctx* ctx, const double* time, int64_t n_time, const double* rates, int64_t n_rates,

@@ -212,7 +212,14 @@ class Engine:
                                                   integ.ctypes.data, err.ctypes.data, panels.ctypes.data), self._ctx)
         return integ, err, panels
 
+    def run_fn(self, offsets, rates, n_grid, times, epochs):
+        """compute_fn for sharded.run_sharded: one CSR slice -> BatchResult with the profile."""
+        return self.run(offsets, rates, n_grid, times, epochs, want_profile=True)
+
     # ---- measurement helpers ----
+    def set_serial_kernels(self, serial: bool):
+        check(self._lib.tapir_cuda_set_serial_kernels(self._ctx, 1 if serial else 0), self._ctx)
+
     def transfer_bytes(self):
         h2d, d2h = ctypes.c_uint64(), ctypes.c_uint64()
         check(self._lib.tapir_cuda_transfer_bytes(self._ctx, ctypes.byref(h2d), ctypes.byref(d2h)), self._ctx)
