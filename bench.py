@@ -231,6 +231,7 @@ def workload_name(w):
 
 def run_ours(args, rank, world, local_rank):
     from tapir_b200 import synthetic
+    from tapir_b200 import sharded
     from tapir_b200.engine import Engine, pinned_empty
 
     times, epochs = synthetic.TIMES, synthetic.EPOCHS
@@ -261,28 +262,24 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             dist.barrier()
 
-    # ---- small-result gather over NCCL (N > 1): one packed [L, K+2E+4] matrix per rank ----
+    # ---- small-result gather over NCCL (N > 1): the library keeps every per-locus vector in ONE device block,
+    #      so a step's gather is a single NCCL call on that block (no packing kernels)
     gather = None
     if dist is not None:
-        K, E = len(times), len(epochs)
-
         class _Dev:
-            def __init__(self, ptr, shape, typestr):
-                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        state = {}
 
         def gather():
-            r = eng.device_results()
-            cols = [torch.as_tensor(_Dev(r.pi_times, (L, K), "<f8"), device="cuda"),
-                    torch.as_tensor(_Dev(r.integral, (L, E), "<f8"), device="cuda"),
-                    torch.as_tensor(_Dev(r.abserr, (L, E), "<f8"), device="cuda"),
-                    torch.as_tensor(_Dev(r.max_pi, (L, 1), "<f8"), device="cuda"),
-                    torch.as_tensor(_Dev(r.argmax_t, (L, 1), "<i8"), device="cuda").double(),
-                    torch.as_tensor(_Dev(r.argmax_epoch, (L, 1), "<i4"), device="cuda").double(),
-                    torch.as_tensor(_Dev(r.mean_rate, (L, 1), "<f8"), device="cuda")]
-            packed = torch.cat(cols, dim=1).contiguous()
-            dst = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
-            dist.gather(packed, dst, dst=0)
-            return dst
+            ptr, nbytes, _ = eng.device_small_block()
+            if state.get("ptr") != (ptr, nbytes):
+                state["ptr"] = (ptr, nbytes)
+                state["src"] = torch.as_tensor(_Dev(ptr, nbytes // 8), device="cuda")
+                state["dst"] = [torch.empty_like(state["src"]) for _ in range(world)] if rank == 0 else None
+            dist.gather(state["src"], state["dst"], dst=0)
+            return state["dst"]
 
     # ---- device-resident timing ----
     eng.upload(offsets, rates, T, times, epochs, want_profile=True)
@@ -328,7 +325,10 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.steps):
         eng.run(offsets, rates, T, times, epochs, want_profile=True, out=out)
         if gather:
-            dst = gather()
+            # the step's results are on the host already (tapir_cuda_run); the per-locus vectors go through NCCL
+            packed = torch.from_numpy(sharded.pack_small(out)).cuda()
+            dst = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
+            dist.gather(packed, dst, dst=0)
             if rank == 0:
                 _ = [d.cpu() for d in dst]
             torch.cuda.synchronize()

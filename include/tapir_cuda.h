@@ -111,6 +111,11 @@ int tapir_cuda_download(tapir_cuda_ctx *ctx, const tapir_results *host_out);
 /* device pointers of the resident result arrays (valid until the next upload/destroy) */
 int tapir_cuda_device_results(tapir_cuda_ctx *ctx, tapir_results *device_ptrs);
 
+/* The small per-locus result vectors of the resident batch live in ONE device block (this is what a multi-GPU
+ * driver gathers): *block / *bytes describe it, section_offset[i] is the byte offset of, in order,
+ * pi_times, integral, abserr, max_pi, argmax_t, mean_rate, n_finite, n_multi_panel, argmax_epoch. */
+int tapir_cuda_device_small_block(tapir_cuda_ctx *ctx, void **block, size_t *bytes, size_t section_offset[9]);
+
 /* serial != 0: run the profile and the epoch-integral kernels back to back on one stream instead of
  * concurrently on two (per-kernel tapir_timing fields are only exact in this mode; also set by
  * TAPIR_CUDA_SERIAL_KERNELS=1 in the environment at context creation) */

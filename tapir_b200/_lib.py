@@ -67,6 +67,8 @@ SYMBOLS = {
     "tapir_cuda_compute": (ctypes.c_int, [_vp, ctypes.POINTER(Timing)]),
     "tapir_cuda_download": (ctypes.c_int, [_vp, ctypes.POINTER(Results)]),
     "tapir_cuda_device_results": (ctypes.c_int, [_vp, ctypes.POINTER(Results)]),
+    "tapir_cuda_device_small_block": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_size_t),
+                                                     ctypes.POINTER(ctypes.c_size_t * 9)]),
     "tapir_cuda_set_serial_kernels": (ctypes.c_int, [_vp, ctypes.c_int]),
     "tapir_cuda_transfer_bytes": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "tapir_cuda_pi_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),

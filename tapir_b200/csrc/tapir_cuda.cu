@@ -748,6 +748,17 @@ int tapir_cuda_device_results(tapir_cuda_ctx* ctx, tapir_results* d)
     return TAPIR_OK;
 }
 
+int tapir_cuda_device_small_block(tapir_cuda_ctx* ctx, void** block, size_t* bytes, size_t section_offset[9])
+{
+    if (!ctx || !block || !bytes || !section_offset) return fail(ctx, TAPIR_E_INVALID, "null argument");
+    const Lane& ln = ctx->lanes[0];
+    if (!ln.plan.valid) return fail(ctx, TAPIR_E_STATE, "no resident batch");
+    *block = ln.d_small.p;
+    *bytes = ln.plan.small_bytes;
+    for (int i = 0; i < 9; ++i) section_offset[i] = ln.plan.small_off[i];
+    return TAPIR_OK;
+}
+
 int tapir_cuda_set_serial_kernels(tapir_cuda_ctx* ctx, int serial)
 {
     if (!ctx) return fail(nullptr, TAPIR_E_INVALID, "null context");

@@ -185,6 +185,16 @@ class Engine:
         check(self._lib.tapir_cuda_device_results(self._ctx, ctypes.byref(r)), self._ctx)
         return r
 
+    SMALL_SECTIONS = ("pi_times", "integral", "abserr", "max_pi", "argmax_t", "mean_rate", "n_finite", "n_multi_panel",
+                      "argmax_epoch")
+
+    def device_small_block(self):
+        """(device pointer, bytes, {section: byte offset}) of the block holding every small per-locus vector."""
+        ptr, nbytes, offs = ctypes.c_void_p(), ctypes.c_size_t(), (ctypes.c_size_t * 9)()
+        check(self._lib.tapir_cuda_device_small_block(self._ctx, ctypes.byref(ptr), ctypes.byref(nbytes),
+                                                      ctypes.byref(offs)), self._ctx)
+        return ptr.value, nbytes.value, dict(zip(self.SMALL_SECTIONS, list(offs)))
+
     # ---- element-wise parity API ----
     def pi_matrix(self, time, rates):
         time = np.ascontiguousarray(np.asarray(time, dtype=np.float64).reshape(-1))

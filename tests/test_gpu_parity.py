@@ -268,3 +268,25 @@ def test_chunked_run_equals_single_pass(eng):
     c = eng.download()
     eng.set_serial_kernels(False)
     assert np.array_equal(b.pi_net, c.pi_net) and np.array_equal(b.integral, c.integral)
+
+
+def test_device_small_block_holds_every_small_vector(eng):
+    """The block a multi-GPU driver gathers (one NCCL call) is exactly the small result vectors."""
+    import torch
+    from tapir_b200 import synthetic
+    off, rates, T = synthetic.build("cfg2", scale=0.01)
+    eng.upload(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+    eng.compute()
+    res = eng.download()
+    ptr, nbytes, sec = eng.device_small_block()
+
+    class _Dev:
+        __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    raw = torch.as_tensor(_Dev(), device="cuda").cpu().numpy()
+    L = off.size - 1
+    for name in eng.SMALL_SECTIONS:
+        want = np.ascontiguousarray(getattr(res, name))
+        got = raw[sec[name]:sec[name] + want.nbytes].view(want.dtype).reshape(want.shape)
+        assert np.array_equal(got, want, equal_nan=True), name
+    assert L == 50
