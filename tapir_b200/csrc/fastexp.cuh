@@ -70,6 +70,21 @@ TAPIR_HD double pow2i(int k)
 #endif
 }
 
+// p * 2^k by adding k to p's exponent field: exact while p and the result are normal numbers (the bounded
+// variants guarantee it); one integer add instead of building 2^k and an FP64 multiply
+TAPIR_HD double scale_pow2(double p, int k)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    uint64_t bits;
+    std::memcpy(&bits, &p, sizeof bits);
+    bits += uint64_t(int64_t(k)) << 52;
+    std::memcpy(&p, &bits, sizeof p);
+    return p;
+#endif
+}
+
 // integer nearest to t (|t| < 2^31) as both double and int
 TAPIR_HD void round_int(double t, double& kd, int& ki)
 {
@@ -121,7 +136,7 @@ TAPIR_HD double exp_bounded(double x)
     double kd;
     int ki;
     fx::round_int(x * fx::kLog2e, kd, ki);
-    return fx::poly(fx::reduce(x, kd)) * fx::pow2i(ki);
+    return fx::scale_pow2(fx::poly(fx::reduce(x, kd)), ki);
 }
 
 // N independent exp_bounded evaluations advanced in lock step, so that the N dependent Horner chains are
@@ -146,7 +161,7 @@ TAPIR_HD void exp_bounded_n(const double (&x)[N], double (&y)[N])
 #pragma unroll
     for (int i = 0; i < N; ++i) p[i] = fx::fma_(p[i], r[i], 1.0);
 #pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = fx::fma_(p[i], r[i], 1.0) * fx::pow2i(ki[i]);
+    for (int i = 0; i < N; ++i) y[i] = fx::scale_pow2(fx::fma_(p[i], r[i], 1.0), ki[i]);
 }
 
 // (e^-z, e^+z) for 0 <= z <= 700 from one range reduction: e^{+/-r} = E(r^2) +/- r O(r^2)
@@ -165,8 +180,8 @@ TAPIR_HD void exp_pm_bounded(double z, double& em, double& ep)
     ev = fma_(ev, s, TAPIR_FX_C(4));  od = fma_(od, s, TAPIR_FX_C(5));
     ev = fma_(ev, s, TAPIR_FX_C(2));  od = fma_(od, s, TAPIR_FX_C(3));
     ev = fma_(ev, s, 1.0); od = fma_(od, s, 1.0);
-    ep = fma_(od, r, ev) * pow2i(ki);
-    em = fma_(od, -r, ev) * pow2i(-ki);
+    ep = scale_pow2(fma_(od, r, ev), ki);
+    em = scale_pow2(fma_(od, -r, ev), -ki);
 }
 
 // e^x for any x: +inf above the overflow threshold, gradual underflow to 0 below, NaN -> NaN
