@@ -262,24 +262,45 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             dist.barrier()
 
-    # ---- small-result gather over NCCL (N > 1): the library keeps every per-locus vector in ONE device block,
-    #      so a step's gather is a single NCCL call on that block (no packing kernels)
+    # ---- small-result gather (N > 1).  The library keeps every per-locus vector of a batch in ONE device block.
+    #  "push" (default): rank 0 owns a buffer with one slot per rank, exported through CUDA IPC; every rank's
+    #      tapir_cuda_compute ends with a device-to-device copy of its block into its slot over NVLink, on the
+    #      same stream as finalize -- no collective launch inside a step.
+    #  "nccl": one dist.gather of the block per step (fallback if IPC peer memory is unavailable, or --gather nccl)
     gather = None
+    gather_mode = "none"
     if dist is not None:
-        class _Dev:
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        eng.upload(offsets, rates, T, times, epochs, want_profile=True)
+        _, slot_bytes, sections = eng.device_small_block()
+        gather_mode = args.gather
+        if gather_mode == "push":
+            try:
+                obj = [eng.gather_create(slot_bytes, world) if rank == 0 else None]
+                dist.broadcast_object_list(obj, src=0)
+                eng.gather_attach(None if rank == 0 else obj[0], slot_bytes, rank)
+                ok = torch.tensor([1], device="cuda")
+            except Exception as err:                      # noqa: BLE001 - any failure means: use NCCL
+                sys.stderr.write("rank %d: push gather unavailable (%s); falling back to NCCL\n" % (rank, err))
+                ok = torch.tensor([0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                eng.gather_detach()
+                gather_mode = "nccl"
+        if gather_mode == "nccl":
+            class _Dev:
+                def __init__(self, ptr, n):
+                    self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
 
-        state = {}
+            state = {}
 
-        def gather():
-            ptr, nbytes, _ = eng.device_small_block()
-            if state.get("ptr") != (ptr, nbytes):
-                state["ptr"] = (ptr, nbytes)
-                state["src"] = torch.as_tensor(_Dev(ptr, nbytes // 8), device="cuda")
-                state["dst"] = [torch.empty_like(state["src"]) for _ in range(world)] if rank == 0 else None
-            dist.gather(state["src"], state["dst"], dst=0)
-            return state["dst"]
+            def gather():
+                ptr, nbytes, _ = eng.device_small_block()
+                if state.get("ptr") != (ptr, nbytes):
+                    state["ptr"] = (ptr, nbytes)
+                    state["src"] = torch.as_tensor(_Dev(ptr, nbytes // 8), device="cuda")
+                    state["dst"] = [torch.empty_like(state["src"]) for _ in range(world)] if rank == 0 else None
+                dist.gather(state["src"], state["dst"], dst=0)
+                return state["dst"]
 
     # ---- device-resident timing ----
     eng.upload(offsets, rates, T, times, epochs, want_profile=True)
@@ -314,6 +335,23 @@ def run_ours(args, rank, world, local_rank):
             gather_ms += e0.elapsed_time(e1)
     barrier()
     step_ms = (dev_ms + gather_ms) / args.steps
+    gather_check = None
+    if dist is not None:
+        # every rank's integral checksum, to compare with what arrived at rank 0
+        mine = eng.download()
+        sums = [None] * world
+        dist.all_gather_object(sums, float(mine.integral.sum()))
+        if rank == 0:
+            E = len(epochs)
+            if gather_mode == "push":
+                raw = eng.gather_read(slot_bytes * world)
+                blocks = [raw[r * slot_bytes:(r + 1) * slot_bytes] for r in range(world)]
+            else:
+                blocks = [d.cpu().numpy().view(np.uint8) for d in gather()]
+            got = [float(b[sections["integral"]:sections["integral"] + L * E * 8].view(np.float64).sum()) for b in blocks]
+            gather_check = "ok" if np.allclose(got, sums, rtol=1e-12) else "MISMATCH %r vs %r" % (got, sums)
+        elif gather_mode == "nccl":
+            gather()
 
     # ---- end to end through the public call: pinned host in, pinned host out ----
     out = eng.run(offsets, rates, T, times, epochs, want_profile=True, pinned_results=True)   # allocates + warms
@@ -324,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         eng.run(offsets, rates, T, times, epochs, want_profile=True, out=out)
-        if gather:
+        if gather_mode == "nccl":
             # the step's results are on the host already (tapir_cuda_run); the per-locus vectors go through NCCL
             packed = torch.from_numpy(sharded.pack_small(out)).cuda()
             dst = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
@@ -371,7 +409,9 @@ def run_ours(args, rank, world, local_rank):
                    "loci_per_gpu": L, "grid": T, "epochs": epochs, "times": times,
                    "cache": "L2 flushed (256 MB memset) before every timed step",
                    "timing": "CUDA events on the launching stream per step, max over ranks",
-                   "parallelism": "locus-sharded x%d, NCCL gather of per-locus vectors" % world if world > 1 else "single GPU"},
+                   "parallelism": ("locus-sharded x%d, per-locus vectors gathered to rank 0 by %s" % (
+                       world, "NVLink peer-memory push fused after finalize (CUDA IPC)" if gather_mode == "push"
+                       else "one NCCL gather per step")) if world > 1 else "single GPU"},
         "loci_per_s": total_loci / (step_ms * 1e-3),
         "kernel_ms": {"profile": prof_ms / args.steps, "quad": quad_ms / args.steps, "finalize": fin_ms / args.steps,
                       "serialised_step": serial_ms / args.steps, "gather": gather_ms / args.steps,
@@ -393,7 +433,7 @@ def run_ours(args, rank, world, local_rank):
                 "loci_per_s": total_loci / e2e_s, "timing": "host wall clock around tapir_cuda_run, pinned buffers",
                 "d2h_alone_ms": d2h_s * 1e3, "d2h_gbs": d2h_gbs,
                 "note": "chunked over two lanes (copies overlap kernels); bounded below by the D2H copy of the profile"},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "gather": {"mode": gather_mode, "check": gather_check},
         "clocks": clocks,
         "checksum": checksum,
     }
@@ -410,6 +450,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="push", choices=["push", "nccl"], help="N > 1: how per-locus vectors reach rank 0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -116,6 +116,18 @@ int tapir_cuda_device_results(tapir_cuda_ctx *ctx, tapir_results *device_ptrs);
  * pi_times, integral, abserr, max_pi, argmax_t, mean_rate, n_finite, n_multi_panel, argmax_epoch. */
 int tapir_cuda_device_small_block(tapir_cuda_ctx *ctx, void **block, size_t *bytes, size_t section_offset[9]);
 
+/* --- multi-GPU gather without a collective launch: every rank pushes its small block over NVLink into one
+ * buffer that lives on the owner's GPU (CUDA IPC peer memory), on the same stream right after finalize ---
+ * owner (rank 0): tapir_cuda_gather_create allocates n_slots * slot_bytes and returns a 64-byte IPC handle to
+ * pass to the other processes; every rank (the owner with handle == NULL) then calls tapir_cuda_gather_attach
+ * with its slot; from then on each tapir_cuda_compute ends with the push.  tapir_cuda_gather_read copies the
+ * whole buffer to the owner's host after the ranks have synchronised (e.g. a barrier). */
+#define TAPIR_IPC_HANDLE_BYTES 64
+int tapir_cuda_gather_create(tapir_cuda_ctx *ctx, size_t slot_bytes, int n_slots, void *handle_out);
+int tapir_cuda_gather_attach(tapir_cuda_ctx *ctx, const void *handle, size_t slot_bytes, int slot);
+int tapir_cuda_gather_read(tapir_cuda_ctx *ctx, void *host_dst, size_t bytes);
+int tapir_cuda_gather_detach(tapir_cuda_ctx *ctx);
+
 /* serial != 0: run the profile and the epoch-integral kernels back to back on one stream instead of
  * concurrently on two (per-kernel tapir_timing fields are only exact in this mode; also set by
  * TAPIR_CUDA_SERIAL_KERNELS=1 in the environment at context creation) */

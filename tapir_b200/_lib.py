@@ -69,6 +69,10 @@ SYMBOLS = {
     "tapir_cuda_device_results": (ctypes.c_int, [_vp, ctypes.POINTER(Results)]),
     "tapir_cuda_device_small_block": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_size_t),
                                                      ctypes.POINTER(ctypes.c_size_t * 9)]),
+    "tapir_cuda_gather_create": (ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.c_int, _vp]),
+    "tapir_cuda_gather_attach": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int]),
+    "tapir_cuda_gather_read": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "tapir_cuda_gather_detach": (ctypes.c_int, [_vp]),
     "tapir_cuda_set_serial_kernels": (ctypes.c_int, [_vp, ctypes.c_int]),
     "tapir_cuda_transfer_bytes": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "tapir_cuda_pi_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),

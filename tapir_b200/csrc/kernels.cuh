@@ -648,6 +648,28 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalArgs fa)
 }
 
 // ------------------------------------------------------------------------------------------
+// multi-GPU gather: copy the 9 sections of a batch's small-result block into this rank's slot of the owner's
+// buffer.  `dst` is peer memory (CUDA IPC mapping of a buffer on another GPU): the stores travel over NVLink.
+// A chunk of a larger batch lands at its row offset inside the full batch's layout.
+// ------------------------------------------------------------------------------------------
+struct PushArgs {
+    const uint32_t* src;
+    uint32_t* dst;
+    uint32_t src_off[9], dst_off[9], words[9];  // all in 4-byte words
+};
+
+__global__ void __launch_bounds__(256) push_small_kernel(const PushArgs pa)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const uint32_t* s = pa.src + pa.src_off[i];
+        uint32_t* d = pa.dst + pa.dst_off[i];
+        for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < pa.words[i]; w += stride) d[w] = s[w];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // API-parity element-wise kernels (tapir.compute.get_townsend_pi / get_integral_over_times)
 // ------------------------------------------------------------------------------------------
 // out[t*S + s] = ((16 r^2) t) exp(-((4 r) t)) in the reference's evaluation order (compute.py:48).

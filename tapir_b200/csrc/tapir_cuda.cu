@@ -133,6 +133,15 @@ struct tapir_cuda_ctx {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     DevBuf d_scratch_a, d_scratch_b, d_scratch_c, d_flush, d_counter;
     uint64_t bytes_h2d = 0, bytes_d2h = 0;
+    // gather target (see tapir_cuda_gather_*): a buffer on the owner's GPU, local or mapped through CUDA IPC
+    DevBuf d_gather;                  // owner only
+    void* gather_mapped = nullptr;    // non-owner: base pointer returned by cudaIpcOpenMemHandle
+    char* gather_slot_ptr = nullptr;  // where this rank's small block goes
+    size_t gather_slot_bytes = 0, gather_total_bytes = 0;
+    // layout of the batch being gathered when it is processed in chunks (tapir_cuda_run): section offsets of the
+    // FULL batch and the first row of the chunk in flight; 0/unused for the staged single-batch path
+    bool gather_chunked = false;
+    size_t gather_full_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -381,7 +390,8 @@ int tapir_cuda_destroy(tapir_cuda_ctx* ctx)
         if (ln.stream) cudaStreamDestroy(ln.stream);
         if (ln.stream_q) cudaStreamDestroy(ln.stream_q);
     }
-    DevBuf* bufs[] = {&ctx->d_scratch_a, &ctx->d_scratch_b, &ctx->d_scratch_c, &ctx->d_flush, &ctx->d_counter};
+    if (ctx->gather_mapped) cudaIpcCloseMemHandle(ctx->gather_mapped);
+    DevBuf* bufs[] = {&ctx->d_scratch_a, &ctx->d_scratch_b, &ctx->d_scratch_c, &ctx->d_flush, &ctx->d_counter, &ctx->d_gather};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
@@ -669,6 +679,29 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
         CU(ctx, cudaEventRecord(ln.ev[1], st));
         CU(ctx, cudaEventRecord(ln.ev[2], st));
     }
+    if (ctx->gather_slot_ptr && plan.L > 0) {
+        // NVLink push: the batch's small block goes into this rank's slot of the owner's buffer (peer memory),
+        // by stores issued from this GPU on the same stream as finalize -- no collective launch
+        const size_t K = size_t(plan.T > 0 ? plan.K : 0), E = size_t(plan.E);
+        const size_t row_bytes[9] = {K * 8, E * 8, E * 8, 8, 8, 8, 8, 8, 4};
+        PushArgs pa;
+        pa.src = ln.d_small.as<uint32_t>();
+        pa.dst = reinterpret_cast<uint32_t*>(ctx->gather_slot_ptr);
+        size_t end = 0;
+        for (int i = 0; i < 9; ++i) {
+            const size_t dst_off = ctx->gather_chunked ? ctx->gather_full_off[i] + size_t(ln.pending_row0) * row_bytes[i]
+                                                       : plan.small_off[i];
+            pa.src_off[i] = uint32_t(plan.small_off[i] / 4);
+            pa.dst_off[i] = uint32_t(dst_off / 4);
+            pa.words[i] = uint32_t(size_t(plan.L) * row_bytes[i] / 4);
+            end = std::max(end, dst_off + size_t(plan.L) * row_bytes[i]);
+        }
+        if (end > ctx->gather_slot_bytes)
+            return fail(ctx, TAPIR_E_STATE, "gather slot of %zu bytes is smaller than the batch's %zu", ctx->gather_slot_bytes, end);
+        push_small_kernel<<<unsigned(std::min<int64_t>(ctx->sm_count, (plan.L * 16 + 255) / 256 + 1)), 256, 0, st>>>(pa);
+        CU(ctx, cudaGetLastError());
+        ++launches;
+    }
     CU(ctx, cudaEventRecord(ln.ev[3], st));
     if (sync || timing) CU(ctx, cudaStreamSynchronize(st));
     if (timing) {
@@ -759,6 +792,75 @@ int tapir_cuda_device_small_block(tapir_cuda_ctx* ctx, void** block, size_t* byt
     return TAPIR_OK;
 }
 
+int tapir_cuda_gather_detach(tapir_cuda_ctx* ctx)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    for (Lane& ln : ctx->lanes)
+        if (ln.stream) cudaStreamSynchronize(ln.stream);
+    if (ctx->gather_mapped) cudaIpcCloseMemHandle(ctx->gather_mapped);
+    ctx->gather_mapped = nullptr;
+    ctx->gather_slot_ptr = nullptr;
+    ctx->gather_slot_bytes = ctx->gather_total_bytes = 0;
+    ctx->d_gather.release();
+    cudaGetLastError();
+    return TAPIR_OK;
+}
+
+int tapir_cuda_gather_create(tapir_cuda_ctx* ctx, size_t slot_bytes, int n_slots, void* handle_out)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!handle_out || slot_bytes == 0 || n_slots < 1) return fail(ctx, TAPIR_E_INVALID, "bad gather geometry");
+    static_assert(sizeof(cudaIpcMemHandle_t) == TAPIR_IPC_HANDLE_BYTES, "IPC handle size");
+    tapir_cuda_gather_detach(ctx);
+    ctx->d_gather.release();
+    CU(ctx, ctx->d_gather.ensure(slot_bytes * size_t(n_slots)));
+    CU(ctx, cudaMemset(ctx->d_gather.p, 0, slot_bytes * size_t(n_slots)));
+    cudaIpcMemHandle_t h;
+    CU(ctx, cudaIpcGetMemHandle(&h, ctx->d_gather.p));
+    memcpy(handle_out, &h, sizeof h);
+    ctx->gather_total_bytes = slot_bytes * size_t(n_slots);
+    return TAPIR_OK;
+}
+
+int tapir_cuda_gather_attach(tapir_cuda_ctx* ctx, const void* handle, size_t slot_bytes, int slot)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (slot < 0 || slot_bytes == 0) return fail(ctx, TAPIR_E_INVALID, "bad gather slot");
+    char* base = nullptr;
+    if (!handle) {
+        if (!ctx->d_gather.p) return fail(ctx, TAPIR_E_STATE, "tapir_cuda_gather_attach(NULL) on a context that owns no gather buffer");
+        if (slot_bytes * size_t(slot + 1) > ctx->gather_total_bytes) return fail(ctx, TAPIR_E_INVALID, "slot outside the gather buffer");
+        base = ctx->d_gather.as<char>();
+    } else {
+        if (ctx->gather_mapped) cudaIpcCloseMemHandle(ctx->gather_mapped);
+        ctx->gather_mapped = nullptr;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof h);
+        void* p = nullptr;
+        CU(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->gather_mapped = p;
+        base = static_cast<char*>(p);
+    }
+    ctx->gather_slot_ptr = base + slot_bytes * size_t(slot);
+    ctx->gather_slot_bytes = slot_bytes;
+    return TAPIR_OK;
+}
+
+int tapir_cuda_gather_read(tapir_cuda_ctx* ctx, void* host_dst, size_t bytes)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!ctx->d_gather.p) return fail(ctx, TAPIR_E_STATE, "this context owns no gather buffer");
+    if (!host_dst || bytes > ctx->gather_total_bytes) return fail(ctx, TAPIR_E_INVALID, "bad destination");
+    ctx->bytes_d2h += bytes;
+    CU(ctx, cudaMemcpyAsync(host_dst, ctx->d_gather.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return TAPIR_OK;
+}
+
 int tapir_cuda_set_serial_kernels(tapir_cuda_ctx* ctx, int serial)
 {
     if (!ctx) return fail(nullptr, TAPIR_E_INVALID, "null context");
@@ -813,6 +915,16 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
     int64_t n_chunks = int64_t(bytes / double(12 << 20));
     n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, 16));
     if (L < 64 * n_chunks) n_chunks = 1;  // few (possibly huge) loci: one pass, split over sites instead
+    if (ctx->gather_slot_ptr) {  // where each chunk's rows go inside the full batch's small-block layout
+        const size_t Ls = size_t(L), Ks = size_t(p->n_times), Es = size_t(p->n_epochs);  // as lane_upload lays it out
+        const size_t sizes[9] = {Ls * Ks * 8, Ls * Es * 8, Ls * Es * 8, Ls * 8, Ls * 8, Ls * 8, Ls * 8, Ls * 8, Ls * 4};
+        size_t o = 0;
+        for (int i = 0; i < 9; ++i) {
+            ctx->gather_full_off[i] = o;
+            o += (sizes[i] + 255) & ~size_t(255);
+        }
+        ctx->gather_chunked = true;
+    }
     int64_t l0 = 0;
     for (int64_t k = 0; k < n_chunks; ++k) {
         // chunk boundaries at equal shares of the sites
@@ -826,6 +938,7 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
         Lane& ln = ctx->lanes[k % kLanes];
         if (k >= kLanes && (rc = lane_finish(ctx, ln)) != TAPIR_OK) break;  // its previous chunk (and its staging) is done
         if ((rc = lane_upload(ctx, ln, p, l0, l1, false)) != TAPIR_OK) break;
+        ln.pending_row0 = l0;
         if ((rc = lane_compute(ctx, ln, nullptr, false)) != TAPIR_OK) break;
         if ((rc = lane_download(ctx, ln, host_out, l0, false)) != TAPIR_OK) break;
         l0 = l1;
@@ -834,6 +947,7 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
         const int rc2 = lane_finish(ctx, ln);
         if (rc == TAPIR_OK) rc = rc2;
     }
+    ctx->gather_chunked = false;
     if (n_chunks > 1) ctx->lanes[0].plan.valid = false;  // the resident data is one chunk, not the batch
     return rc;
 }

@@ -195,6 +195,26 @@ class Engine:
                                                       ctypes.byref(offs)), self._ctx)
         return ptr.value, nbytes.value, dict(zip(self.SMALL_SECTIONS, list(offs)))
 
+    # ---- NVLink push gather (CUDA IPC peer memory on the owner's GPU) ----
+    def gather_create(self, slot_bytes: int, n_slots: int) -> bytes:
+        """Owner (rank 0): allocate the gather buffer, return the 64-byte IPC handle for the other ranks."""
+        handle = ctypes.create_string_buffer(64)
+        check(self._lib.tapir_cuda_gather_create(self._ctx, slot_bytes, n_slots, handle), self._ctx)
+        return handle.raw
+
+    def gather_attach(self, handle, slot_bytes: int, slot: int):
+        """Every rank (owner: handle=None): from now on compute() ends by pushing the small block into `slot`."""
+        buf = ctypes.create_string_buffer(handle, 64) if handle is not None else None
+        check(self._lib.tapir_cuda_gather_attach(self._ctx, buf, slot_bytes, slot), self._ctx)
+
+    def gather_read(self, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        check(self._lib.tapir_cuda_gather_read(self._ctx, out.ctypes.data, nbytes), self._ctx)
+        return out
+
+    def gather_detach(self):
+        check(self._lib.tapir_cuda_gather_detach(self._ctx), self._ctx)
+
     # ---- element-wise parity API ----
     def pi_matrix(self, time, rates):
         time = np.ascontiguousarray(np.asarray(time, dtype=np.float64).reshape(-1))

@@ -290,3 +290,38 @@ def test_device_small_block_holds_every_small_vector(eng):
         got = raw[sec[name]:sec[name] + want.nbytes].view(want.dtype).reshape(want.shape)
         assert np.array_equal(got, want, equal_nan=True), name
     assert L == 50
+
+
+def test_push_gather_owner_slot(eng):
+    """NVLink push gather, owner side (the peer side needs a second process and is checked by bench.py --gpus 2):
+    compute() ends by storing the small block into the attached slot; a chunked run() lands every chunk at its
+    row offset of the full batch's layout."""
+    from tapir_b200 import synthetic
+    off, rates, T = synthetic.build("cfg2", scale=0.02)
+    eng.upload(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+    _, slot, sec = eng.device_small_block()
+    try:
+        eng.gather_create(slot, 3)
+        eng.gather_attach(None, slot, 2)
+        eng.compute()
+        res = eng.download()
+        raw = eng.gather_read(3 * slot)
+        assert not raw[:2 * slot].any()                                   # other slots untouched
+        for name in eng.SMALL_SECTIONS:
+            want = np.ascontiguousarray(getattr(res, name))
+            got = raw[2 * slot + sec[name]:2 * slot + sec[name] + want.nbytes].view(want.dtype).reshape(want.shape)
+            assert np.array_equal(got, want, equal_nan=True), name
+        # chunked path: a batch large enough to be cut into several chunks
+        off, rates, T = synthetic.build("cfg3", scale=0.03)
+        eng.upload(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+        _, slot2, sec2 = eng.device_small_block()
+        eng.gather_create(slot2, 1)
+        eng.gather_attach(None, slot2, 0)
+        res = eng.run(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+        raw = eng.gather_read(slot2)
+        for name in eng.SMALL_SECTIONS:
+            want = np.ascontiguousarray(getattr(res, name))
+            got = raw[sec2[name]:sec2[name] + want.nbytes].view(want.dtype).reshape(want.shape)
+            assert np.array_equal(got, want, equal_nan=True), name
+    finally:
+        eng.gather_detach()
