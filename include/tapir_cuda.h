@@ -44,7 +44,6 @@ extern "C" {
 
 /* tapir_problem.flags */
 #define TAPIR_WANT_PROFILE 1u /* copy pi_net[L*T] back to the host (it is always computed) */
-#define TAPIR_FP32_PROFILE 2u /* profile terms in FP32 with FP64 block accumulation (<=1e-5 mode) */
 
 #define TAPIR_MAX_EPOCHS 64
 #define TAPIR_MAX_TIMES 4096
@@ -115,6 +114,13 @@ int tapir_cuda_device_results(tapir_cuda_ctx *ctx, tapir_results *device_ptrs);
  * driver gathers): *block / *bytes describe it, section_offset[i] is the byte offset of, in order,
  * pi_times, integral, abserr, max_pi, argmax_t, mean_rate, n_finite, n_multi_panel, argmax_epoch. */
 int tapir_cuda_device_small_block(tapir_cuda_ctx *ctx, void **block, size_t *bytes, size_t section_offset[9]);
+
+/* --- ranking queries on the resident, computed batch (results stay on the device until asked for) ---
+ * top_locus / top_pi [E][n_top]: per epoch the n_top (<= 1024) loci with the largest summed integral, descending,
+ * ties to the lower locus index -- the "ORDER BY pi DESC limit N" of bin/tapir_compare.py:93-101; rows are padded
+ * with locus -1 / NaN when the batch has fewer loci.  epoch_count[E]: number of loci whose max-PI epoch is e
+ * (README.rst:178-185; a tie counts for the first epoch).  Any output pointer may be NULL. */
+int tapir_cuda_rank(tapir_cuda_ctx *ctx, int32_t n_top, int64_t *top_locus, double *top_pi, int64_t *epoch_count);
 
 /* --- multi-GPU gather without a collective launch: every rank pushes its small block over NVLink into one
  * buffer that lives on the owner's GPU (CUDA IPC peer memory), on the same stream right after finalize ---

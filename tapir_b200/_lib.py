@@ -8,7 +8,6 @@ LIB_PATH = os.path.join(_HERE, "libtapir_cuda.so")
 TAPIR_OK = 0
 TAPIR_E_INVALID, TAPIR_E_CUDA, TAPIR_E_NOMEM, TAPIR_E_STATE = -1, -2, -3, -4
 WANT_PROFILE = 1
-FP32_PROFILE = 2
 MAX_EPOCHS = 64
 MAX_TIMES = 4096
 
@@ -69,6 +68,7 @@ SYMBOLS = {
     "tapir_cuda_device_results": (ctypes.c_int, [_vp, ctypes.POINTER(Results)]),
     "tapir_cuda_device_small_block": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_size_t),
                                                      ctypes.POINTER(ctypes.c_size_t * 9)]),
+    "tapir_cuda_rank": (ctypes.c_int, [_vp, ctypes.c_int32, _vp, _vp, _vp]),
     "tapir_cuda_gather_create": (ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.c_int, _vp]),
     "tapir_cuda_gather_attach": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int]),
     "tapir_cuda_gather_read": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),

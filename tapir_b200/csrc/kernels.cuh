@@ -648,6 +648,127 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalArgs fa)
 }
 
 // ------------------------------------------------------------------------------------------
+// ranking queries on the resident results (tapir_compare.py:93-101 "ORDER BY pi DESC limit N" per interval;
+// README.rst:178-185 count of loci per max-PI epoch).  One CTA per epoch: 8-bit radix select of the N-th
+// largest integral, index-ordered compaction of the winners, bitonic sort of the <= 1024 candidates.
+// Integer atomics only, so the result is deterministic; ties go to the lower locus index.
+// ------------------------------------------------------------------------------------------
+constexpr int kRankThreads = 1024;
+constexpr int kRankMaxTop = 1024;
+
+__device__ __forceinline__ unsigned long long rank_key(double v)
+{
+    // order-preserving map of a double to an unsigned integer (larger value -> larger key)
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(kRankThreads) rank_kernel(const double* __restrict__ integral, int64_t L, int32_t E,
+                                                            int32_t n_top, int64_t* __restrict__ top_locus,
+                                                            double* __restrict__ top_pi)
+{
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_need, s_count, s_warp[kRankThreads / 32];
+    __shared__ unsigned long long ckey[kRankMaxTop];
+    __shared__ int64_t cidx[kRankMaxTop];
+    const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t want = L < n_top ? L : n_top;
+    // ---- radix select: key of the want-th largest element ----
+    if (tid == 0) { s_prefix = 0; s_need = (unsigned int)want; }
+    __syncthreads();
+    for (int shift = 56; shift >= 0 && want > 0; shift -= 8) {
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+        for (int64_t l = tid; l < L; l += kRankThreads) {
+            const unsigned long long k = rank_key(integral[l * E + e]);
+            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int need = s_need;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (hist[b] >= need) break;
+                need -= hist[b];
+            }
+            s_prefix = prefix | ((unsigned long long)b << shift);
+            s_need = need;  // how many elements equal to the final key are still wanted
+        }
+        __syncthreads();
+    }
+    const unsigned long long tau = s_prefix;
+    const unsigned int need_equal = s_need;
+    // ---- index-ordered compaction: everything above tau, then the first need_equal elements equal to tau ----
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 2 && want > 0; ++pass) {
+        const unsigned int limit = pass == 0 ? (unsigned int)want : (unsigned int)want;
+        unsigned int taken_equal = 0;
+        for (int64_t base = 0; base < L; base += kRankThreads) {
+            const int64_t l = base + tid;
+            unsigned long long k = 0;
+            bool hit = false;
+            if (l < L) {
+                k = rank_key(integral[l * E + e]);
+                hit = pass == 0 ? (k > tau) : (k == tau);
+            }
+            const unsigned int ballot = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_warp[warp] = __popc(ballot);
+            __syncthreads();
+            unsigned int before = 0, total = 0;
+            for (int w = 0; w < kRankThreads / 32; ++w) {
+                if (w < warp) before += s_warp[w];
+                total += s_warp[w];
+            }
+            const unsigned int start = s_count;
+            const unsigned int pos = start + before + __popc(ballot & ((1u << lane) - 1u));
+            const unsigned int cap = pass == 0 ? limit : start + (need_equal - taken_equal);
+            if (hit && pos < cap && pos < (unsigned int)kRankMaxTop) { ckey[pos] = k; cidx[pos] = l; }
+            __syncthreads();
+            if (tid == 0) s_count = min(start + total, cap);
+            if (pass == 1) taken_equal = min(taken_equal + total, need_equal);
+            __syncthreads();
+            if (pass == 1 && taken_equal >= need_equal) break;
+        }
+    }
+    const unsigned int n = s_count;
+    // ---- bitonic sort of the candidates: key descending, index ascending ----
+    for (int i = tid; i < kRankMaxTop; i += kRankThreads)
+        if (i >= (int)n) { ckey[i] = 0; cidx[i] = 0x7fffffffffffffffLL; }
+    __syncthreads();
+    for (int size = 2; size <= kRankMaxTop; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int i = tid, j = i ^ stride;
+            if (j > i) {
+                const bool desc = (i & size) == 0;
+                const bool i_first = ckey[i] > ckey[j] || (ckey[i] == ckey[j] && cidx[i] < cidx[j]);
+                if (i_first != desc) {
+                    const unsigned long long tk = ckey[i]; ckey[i] = ckey[j]; ckey[j] = tk;
+                    const int64_t ti = cidx[i]; cidx[i] = cidx[j]; cidx[j] = ti;
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < n_top; i += kRankThreads) {
+        const bool ok = i < (int)n;
+        top_locus[int64_t(e) * n_top + i] = ok ? cidx[i] : -1;
+        top_pi[int64_t(e) * n_top + i] = ok ? integral[cidx[i] * E + e] : __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
+__global__ void epoch_count_kernel(const int32_t* __restrict__ argmax_epoch, int64_t L, int32_t E,
+                                   unsigned long long* __restrict__ count)
+{
+    for (int64_t l = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; l < L; l += int64_t(gridDim.x) * blockDim.x) {
+        const int32_t e = argmax_epoch[l];
+        if (e >= 0 && e < E) atomicAdd(count + e, 1ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // multi-GPU gather: copy the 9 sections of a batch's small-result block into this rank's slot of the owner's
 // buffer.  `dst` is peer memory (CUDA IPC mapping of a buffer on another GPU): the stores travel over NVLink.
 // A chunk of a larger batch lands at its row offset inside the full batch's layout.

@@ -792,6 +792,42 @@ int tapir_cuda_device_small_block(tapir_cuda_ctx* ctx, void** block, size_t* byt
     return TAPIR_OK;
 }
 
+int tapir_cuda_rank(tapir_cuda_ctx* ctx, int32_t n_top, int64_t* top_locus, double* top_pi, int64_t* epoch_count)
+{
+    int rc = bind(ctx);
+    if (rc) return rc;
+    Lane& ln = ctx->lanes[0];
+    const Plan& plan = ln.plan;
+    if (!plan.valid) return fail(ctx, TAPIR_E_STATE, "tapir_cuda_rank needs a resident, computed batch (upload + compute)");
+    if (n_top < 0 || n_top > kRankMaxTop) return fail(ctx, TAPIR_E_INVALID, "n_top must be in [0, %d]", kRankMaxTop);
+    const int E = plan.E;
+    if (E == 0) return TAPIR_OK;
+    cudaStream_t st = ln.stream;
+    const size_t b_idx = size_t(E) * n_top * 8, b_cnt = size_t(E) * 8;
+    CU(ctx, ctx->d_scratch_a.ensure(b_idx + 8));
+    CU(ctx, ctx->d_scratch_b.ensure(b_idx + 8));
+    CU(ctx, ctx->d_scratch_c.ensure(b_cnt + 8));
+    if (n_top > 0 && (top_locus || top_pi)) {
+        rank_kernel<<<unsigned(E), kRankThreads, 0, st>>>(ln.d_integral.as<double>(), plan.L, E, n_top,
+                                                          ctx->d_scratch_a.as<int64_t>(), ctx->d_scratch_b.as<double>());
+        CU(ctx, cudaGetLastError());
+        if (top_locus) CU(ctx, cudaMemcpyAsync(top_locus, ctx->d_scratch_a.p, b_idx, cudaMemcpyDeviceToHost, st));
+        if (top_pi) CU(ctx, cudaMemcpyAsync(top_pi, ctx->d_scratch_b.p, b_idx, cudaMemcpyDeviceToHost, st));
+    }
+    if (epoch_count) {
+        CU(ctx, cudaMemsetAsync(ctx->d_scratch_c.p, 0, b_cnt, st));
+        if (plan.L > 0) {
+            const int64_t blocks = std::min<int64_t>((plan.L + 255) / 256, int64_t(ctx->sm_count) * 8);
+            epoch_count_kernel<<<unsigned(blocks), 256, 0, st>>>(ln.d_argmax_epoch.as<int32_t>(), plan.L, E,
+                                                                 ctx->d_scratch_c.as<unsigned long long>());
+            CU(ctx, cudaGetLastError());
+        }
+        CU(ctx, cudaMemcpyAsync(epoch_count, ctx->d_scratch_c.p, b_cnt, cudaMemcpyDeviceToHost, st));
+    }
+    CU(ctx, cudaStreamSynchronize(st));
+    return TAPIR_OK;
+}
+
 int tapir_cuda_gather_detach(tapir_cuda_ctx* ctx)
 {
     int rc = bind(ctx);

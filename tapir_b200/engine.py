@@ -195,6 +195,20 @@ class Engine:
                                                       ctypes.byref(offs)), self._ctx)
         return ptr.value, nbytes.value, dict(zip(self.SMALL_SECTIONS, list(offs)))
 
+    # ---- ranking queries on the resident results ----
+    def rank(self, n_top: int):
+        """(top_locus[E,n_top], top_pi[E,n_top], epoch_count[E]) of the batch last uploaded and computed."""
+        if self._resident is None:
+            raise _lib.TapirCudaError(_lib.TAPIR_E_STATE, "rank before upload")
+        E = self._resident[3]
+        top_locus = np.full((E, n_top), -1, dtype=np.int64)
+        top_pi = np.full((E, n_top), np.nan)
+        count = np.zeros(E, dtype=np.int64)
+        check(self._lib.tapir_cuda_rank(self._ctx, n_top, top_locus.ctypes.data if top_locus.size else None,
+                                        top_pi.ctypes.data if top_pi.size else None,
+                                        count.ctypes.data if E else None), self._ctx)
+        return top_locus, top_pi, count
+
     # ---- NVLink push gather (CUDA IPC peer memory on the owner's GPU) ----
     def gather_create(self, slot_bytes: int, n_slots: int) -> bytes:
         """Owner (rank 0): allocate the gather buffer, return the 64-byte IPC handle for the other ranks."""

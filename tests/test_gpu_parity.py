@@ -325,3 +325,40 @@ def test_push_gather_owner_slot(eng):
             assert np.array_equal(got, want, equal_nan=True), name
     finally:
         eng.gather_detach()
+
+
+def test_rank_queries(eng):
+    """Top-N loci per interval (bin/tapir_compare.py:93-101) and loci per max-PI epoch (README.rst:178-185),
+    computed on the device from the resident results."""
+    from tapir_b200 import synthetic
+    from tapir_b200.engine import pack_csr
+    rng = np.random.default_rng(21)
+    loci = [synthetic.uce_rates(rng, int(n), 200) for n in rng.integers(1, 60, size=3000)]
+    for l in range(0, 3000, 7):
+        loci[l] = np.zeros(5)                                 # many exact ties at 0
+    loci[11] = loci[10].copy()                                # an exact tie at a large value
+    off, rates = pack_csr(loci, pinned=False)
+    epochs = [[32, 42], [88, 98], [95, 105], [164, 174], [0, 5]]
+    eng.upload(off, rates, 200, [3], epochs)
+    eng.compute()
+    res = eng.download()
+    L = len(loci)
+    for n_top in (1, 10, 1000, 1024):
+        top_locus, top_pi, count = eng.rank(n_top)
+        assert np.array_equal(count, np.bincount(res.argmax_epoch, minlength=len(epochs)))
+        for e in range(len(epochs)):
+            order = np.lexsort((np.arange(L), -res.integral[:, e]))[:n_top]
+            assert np.array_equal(top_locus[e], order), (n_top, e)
+            assert np.array_equal(top_pi[e], res.integral[order, e])
+    # fewer loci than requested: padded with -1 / NaN
+    eng.upload(off[:4], rates[:off[3]], 200, [3], epochs)
+    eng.compute()
+    res = eng.download()
+    top_locus, top_pi, count = eng.rank(8)
+    assert count.sum() == 3
+    for e in range(len(epochs)):
+        order = np.lexsort((np.arange(3), -res.integral[:, e]))
+        assert list(top_locus[e][:3]) == list(order) and np.all(top_locus[e][3:] == -1) and np.isnan(top_pi[e][3:]).all()
+    from tapir_b200._lib import TapirCudaError
+    with pytest.raises(TapirCudaError):
+        eng.rank(5000)
