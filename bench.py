@@ -232,7 +232,7 @@ def workload_name(w):
 def run_ours(args, rank, world, local_rank):
     from tapir_b200 import synthetic
     from tapir_b200 import sharded
-    from tapir_b200.engine import Engine, pinned_empty
+    from tapir_b200.engine import Engine, bind_host_thread_near, pinned_empty
 
     times, epochs = synthetic.TIMES, synthetic.EPOCHS
     # every rank owns one shard of the global batch (same shape, different seed)
@@ -242,6 +242,13 @@ def run_ours(args, rank, world, local_rank):
     off_np, rates_np, T = synthetic.build("_shard")
     L, nnz = off_np.size - 1, rates_np.size
     evals_rank = nnz * T
+    # sites that contribute: a zero rate (invariant site) or a culled (NaN/Inf) site adds exactly 0 everywhere; the
+    # kernels drop them after the load.  `value` counts every site*timepoint (BASELINE.json's metric); the roofline
+    # counts only the FMAs that are algorithmically required, i.e. those of the active sites.
+    with np.errstate(over="ignore", invalid="ignore"):
+        a_np = 16.0 * rates_np * rates_np
+    n_active = int(np.count_nonzero(np.isfinite(a_np) & (a_np != 0.0)))
+    evals_active = n_active * T
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -254,6 +261,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    numa_bound = bind_host_thread_near(local_rank) if world > 1 else False   # after the CPU pool (N = 1 keeps all cores)
     eng = Engine(local_rank)
     offsets = pinned_empty(off_np.shape, np.int64); offsets[:] = off_np
     rates = pinned_empty(rates_np.shape, np.float64); rates[:] = rates_np
@@ -400,7 +408,7 @@ def run_ours(args, rank, world, local_rank):
     total_loci = L * world
     peaks, peak_src = measured_peaks()
     prof_s = prof_ms / args.steps * 1e-3
-    achieved_tf = 2.0 * evals_rank / prof_s / 1e12        # one FP64 FMA per (site, timepoint): DESIGN.md
+    achieved_tf = 2.0 * evals_active / prof_s / 1e12      # one FP64 FMA per (active site, timepoint): DESIGN.md
     line = {
         "metric": METRIC, "value": total_evals / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -423,7 +431,10 @@ def run_ours(args, rank, world, local_rank):
             "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": profile_traffic(args.workload),
             "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has HBM and bf16 entries only; "
                            "tools/microbench/fp64_pipes.cu: DMMA 37.0, DFMA 36.6 TFLOP/s, one shared pipe)",
-            "algorithmic": "2 flop (1 FP64 FMA) per site*timepoint eval, %d evals per launch" % evals_rank,
+            "algorithmic": "2 flop (1 FP64 FMA) per site*timepoint eval of a site with a non-zero finite rate: "
+                           "%d of the launch's %d evals (zero-rate and culled sites add exactly 0 and are dropped after "
+                           "the load)" % (evals_active, evals_rank),
+            "active_site_fraction": n_active / max(nnz, 1),
             "quad_kernel": {"ms": quad_ms / args.steps, "site_epochs_per_s": nnz * len(epochs) / (quad_ms / args.steps * 1e-3)},
             "hbm": {"achieved_gbs": 8.0 * nnz / prof_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src,
                     "note": "rate stream, 8 B per site per time tile"},
@@ -431,7 +442,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": total_evals / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": (h1 - h0) // args.steps, "d2h_bytes_per_step": (d1 - d0) // args.steps,
                 "loci_per_s": total_loci / e2e_s, "timing": "host wall clock around tapir_cuda_run, pinned buffers",
-                "d2h_alone_ms": d2h_s * 1e3, "d2h_gbs": d2h_gbs,
+                "d2h_alone_ms": d2h_s * 1e3, "d2h_gbs": d2h_gbs, "host_thread_bound_to_gpu_numa_node": numa_bound,
                 "note": "chunked over two lanes (copies overlap kernels); bounded below by the D2H copy of the profile"},
         "gpu_launches": launches, "gather": {"mode": gather_mode, "check": gather_check},
         "clocks": clocks,

@@ -40,7 +40,7 @@ struct QuadItem {      // up to kQuadBlock consecutive sites of one locus
     int32_t locus;
 };
 
-constexpr int kQuadBlock = 256;
+constexpr int kQuadBlock = 256;  // sites per quad item (one warp takes an item)
 constexpr int kEpochsPerLaunch = 4;
 constexpr int kProfWarps = 4;  // warps per CTA of the profile kernel (warps are autonomous)
 constexpr int kB = 32;         // lo extent of a time tile
@@ -77,7 +77,7 @@ struct ProfCfg {
     static constexpr int H = 8 * RH;            // hi extent = RH n-tiles of the 8x8x4 FP64 MMA
     static constexpr int TT = kB * H;           // times per tile
     static constexpr int WStride = (RH == 1) ? 12 : H + 2;
-    static constexpr int WarpDoubles = 32 * (kUStride + WStride);
+    static constexpr int WarpDoubles = 32 * (kUStride + WStride) + 64;  // U, W tables + the active-rate queue
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
     // resident 4-warp CTAs per SM the register budget is sized for (shared memory allows 3 / 2 at RH = 4 / 8)
     static constexpr int MinBlocks = RH >= 8 ? 2 : (RH == 4 ? 3 : 4);
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
     const int fk = lane & 3, fg = lane >> 2;  // MMA fragment coordinates of this lane
     double* Us = smem + size_t(warp) * Cfg::WarpDoubles;
     double* Ws = Us + 32 * US;
+    double* Qs = Ws + 32 * WS;
     double* myU = Us + lane * US;  // generation phase: lane == site
     double* myW = Ws + lane * WS;
     // fragment sources: site row fk (+4 per k-step); lo chunk = 4 entries, hi chunk = RH entries
@@ -147,20 +148,37 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
 #pragma unroll
             for (int j = 0; j < RH; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+        // Sites with a zero rate (invariant sites: HyPhy prints 0.0000) and culled sites (NaN/Inf) add exactly 0
+        // to every grid point.  They are dropped right after the load: the active rates of the item are
+        // compacted, in order, through a 64-entry per-warp queue and the tables are built 32 active sites at
+        // a time, so the contraction only ever sees sites that contribute.
         const double* rp = args.rates + item.site_begin;
-        double lam_next = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
-        for (int base = 0; base < item.n_sites; base += 32) {
-            const int cnt = min(32, item.n_sites - base);
-            const double lam = lam_next;
-            {
-                const int nb = base + 32 + lane;
-                lam_next = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+        int qh = 0, qn = 0;  // queue head / tail (running counts)
+        double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
+        for (int base = 0;; base += 32) {
+            const bool more = base < item.n_sites;
+            if (more) {
+                const double lam_new = lam_in;
+                {
+                    const int nb = base + 32 + lane;
+                    lam_in = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                }
+                const double a_new = 16.0 * (lam_new * lam_new);
+                const bool act = (fabs(a_new) <= DBL_MAX) && (a_new != 0.0);  // lanes past the item hold 0
+                const unsigned ballot = __ballot_sync(0xffffffffu, act);
+                if (act) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                qn += __popc(ballot);
+                __syncwarp();
             }
+            while (qn - qh >= 32 || (!more && qn > qh)) {
+            const int cnt = min(32, qn - qh);
+            const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
+            qh += cnt;
             // ---- generation: this lane's site -> U[0..31], W[0..H-1] (power tables) ----
-            // rows of lanes >= cnt and of culled sites are U = 0, W = 1: they add exactly 0
+            // rows of lanes >= cnt are U = 0, W = 1: they add exactly 0
             {
                 double a = 16.0 * (lam * lam);
-                const bool ok = (fabs(a) <= DBL_MAX) && (lane < cnt);  // NaN/Inf rate (or 16 r^2 overflow): culled
+                const bool ok = lane < cnt;  // queue entries are finite and non-zero; idle lanes build a zero row
                 const double c = ok ? 4.0 * lam : 0.0;
                 a = ok ? a : 0.0;
                 const double q = exp_full(-c);
@@ -235,6 +253,8 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 }
             }
             __syncwarp();
+            }  // groups of 32 active sites
+            if (!more) break;
         }
 
         // ---- epilogue: this lane holds 4 consecutive lo for each of its 2*RH hi ----
@@ -320,6 +340,7 @@ struct QuadArgs {
     double* qpart;       // [n_items][2*e_total + 4]: integral[e], abserr[e] ..., rate_sum, n_notnan, n_finite, n_multi
     FixEntry* fix;       // [n_items * kEpochsPerLaunch] worst case
     uint32_t* fix_count; // entries appended by this launch (zeroed before it)
+    uint32_t* queue;     // work-queue head of this launch (zeroed before it)
     int32_t n_items;
 };
 
@@ -335,8 +356,13 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
 {
     const double fc = eb.center[e];
     double fv1[10], fv2[10];
-    double resk = c_wgk[10] * fc;
-    double resg = 0.0;
+    // Kronrod and Gauss sums over the node pairs.  dqk21 adds the 21 terms into one accumulator; here each sum
+    // is split over independent partial accumulators (Gauss nodes / Kronrod-only nodes, two halves each) that are
+    // combined at the end: same terms, a different association of the additions (differences of a few 1e-16
+    // relative, below the noise of resk - resg that the reference itself carries), and a dependent chain of
+    // 3 FMAs instead of 21.
+    double rk0 = c_wgk[10] * fc, rk1 = 0.0, rk2 = 0.0, rk3 = 0.0;
+    double rg0 = 0.0, rg1 = 0.0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int jt = 2 * j + 1;
@@ -344,8 +370,8 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
         const double f2 = eb.tp[e][jt] * D[jt];
         fv1[jt] = f1; fv2[jt] = f2;
         const double fsum = f1 + f2;
-        resg += c_wg[j] * fsum;
-        resk += c_wgk[jt] * fsum;
+        if (j & 1) { rg1 += c_wg[j] * fsum; rk1 += c_wgk[jt] * fsum; }
+        else       { rg0 += c_wg[j] * fsum; rk0 += c_wgk[jt] * fsum; }
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -353,12 +379,22 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
         const double f1 = eb.tm[e][jt] * R[jt];
         const double f2 = eb.tp[e][jt] * D[jt];
         fv1[jt] = f1; fv2[jt] = f2;
-        resk += c_wgk[jt] * (f1 + f2);
+        if (j & 1) rk3 += c_wgk[jt] * (f1 + f2);
+        else       rk2 += c_wgk[jt] * (f1 + f2);
     }
+    const double resk = (rk0 + rk1) + (rk2 + rk3);
+    const double resg = rg0 + rg1;
     const double reskh = resk * 0.5;
-    double rasc = c_wgk[10] * fabs(fc - reskh);
+    double ra0 = c_wgk[10] * fabs(fc - reskh), ra1 = 0.0, ra2 = 0.0, ra3 = 0.0;
 #pragma unroll
-    for (int j = 0; j < 10; ++j) rasc += c_wgk[j] * (fabs(fv1[j] - reskh) + fabs(fv2[j] - reskh));
+    for (int j = 0; j < 10; ++j) {
+        const double t = c_wgk[j] * (fabs(fv1[j] - reskh) + fabs(fv2[j] - reskh));
+        if ((j & 3) == 0) ra0 += t;
+        else if ((j & 3) == 1) ra1 += t;
+        else if ((j & 3) == 2) ra2 += t;
+        else ra3 += t;
+    }
+    const double rasc = (ra0 + ra1) + (ra2 + ra3);
     result = resk * scale;
     resabs = result;
     resasc = rasc * scale;
@@ -378,123 +414,156 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
     }
 }
 
-// First GK21 panel of every (site, epoch) of the batch, one thread per site of a 256-site item.  A site
-// whose panel is what QAGS returns (the overwhelmingly common case) is summed here; the
-// others contribute 0 and are handed to quad_fix_kernel through the FixEntry list.
-// Persistent blocks: the next item's rates are fetched while the current item is integrated, and the
-// per-item sums are formed column-wise in shared memory in a fixed order.
-constexpr int kQuadCols = 2 * kEpochsPerLaunch + 3;  // integral/abserr per epoch, rate sum, #not-NaN, #finite
+// First GK21 panel of every (site, epoch) of the batch.  A site whose panel is what QAGS returns (the
+// overwhelmingly common case) is summed here; the others contribute 0 and are handed to
+// quad_fix_kernel through the FixEntry list.
+//
+// Warps are autonomous (no block barrier): a warp takes one item (<= 256 consecutive sites of one locus) from
+// a work queue, streams its rates 32 at a time, and packs the sites that need arithmetic -- finite, 16 r^2 != 0;
+// a zero-rate site integrates to exactly (0, 0) and QAGS accepts that as is -- through a 64-entry queue in
+// shared memory, so every pass over the GK21 code runs with 32 useful lanes.  Each lane adds its sites' values
+// into its own shared-memory accumulators (site order), and one shuffle tree per column closes the item: the
+// summation order depends on the item's content only, so results are bit-reproducible.
+//
+// NE = eb.n (0..kEpochsPerLaunch) is a template parameter so that the per-site computation is one straight-line
+// block the scheduler can interleave (the NE exponentials of the common factors in particular).
+constexpr int kQuadWarps = 4;  // warps per CTA
 
-// NE = eb.n (1..kEpochsPerLaunch) is a template parameter so that the whole per-site computation is one
-// straight-line block the scheduler can interleave (the NE exponentials of the common factors in particular).
 template <int NE>
-__global__ void __launch_bounds__(kQuadBlock, 2) quad_kernel(const QuadArgs args, const EpochBatch eb)
+__global__ void __launch_bounds__(kQuadWarps * 32, 4) quad_kernel(const QuadArgs args, const EpochBatch eb)
 {
-    __shared__ double cols[kQuadCols][kQuadBlock];
-    __shared__ uint32_t flagged[kEpochsPerLaunch][kQuadBlock / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int stride = gridDim.x;
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    int it = blockIdx.x;
-    if (it >= args.n_items) return;
-    QuadItem item = args.items[it];
-    QuadItem item_next = item;
-    if (it + stride < args.n_items) item_next = args.items[it + stride];
-    double lam = tid < item.count ? __ldg(args.rates + item.site_begin + tid) : qnan;
+    constexpr int NA = NE > 0 ? 2 * NE : 1;
+    __shared__ double s_q[kQuadWarps][64];                 // queue of active rates
+    __shared__ uint16_t s_src[kQuadWarps][64];             // their position inside the item
+    __shared__ double s_acc[kQuadWarps][NA][32];           // per-lane sums: integral / abserr per epoch
+    __shared__ uint32_t s_flag[kQuadWarps][kEpochsPerLaunch][kQuadBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* q = s_q[warp];
+    uint16_t* qsrc = s_src[warp];
     const int row = 2 * eb.e_total + 4;
 
-    for (; it < args.n_items; it += stride) {
-        // ---- prefetch: rates of the next item, descriptor of the one after ----
-        double lam_next = qnan;
-        QuadItem item_after = item_next;
-        if (it + stride < args.n_items) {
-            if (tid < item_next.count) lam_next = __ldg(args.rates + item_next.site_begin + tid);
-            if (it + 2 * stride < args.n_items) item_after = args.items[it + 2 * stride];
+    for (;;) {
+        int it = 0;
+        if (lane == 0) it = int(atomicAdd(args.queue, 1u));
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= args.n_items) break;
+        const QuadItem item = args.items[it];
+        const double* rp = args.rates + item.site_begin;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) s_acc[warp][k][lane] = 0.0;
+        if (lane < kQuadBlock / 32) {
+#pragma unroll
+            for (int e = 0; e < kEpochsPerLaunch; ++e) s_flag[warp][e][lane] = 0;
         }
-
-        const bool active = tid < item.count;
-        const bool notnan = active && (lam == lam);
-        const bool fin = active && (fabs(lam) <= DBL_MAX);
-        const double a = 16.0 * (lam * lam);
-        const double c = 4.0 * lam;
-        // fast path: all exponent arguments stay well inside the normal range and every node value is >= 0
-        const bool fast = fin && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
-        const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps the arithmetic of idle lanes finite
-        // common factors a e^{-c centre} h of all epochs first: independent chains
-        double scale[NE > 0 ? NE : 1];
-        if constexpr (NE > 0) {
-            double xs[NE];
-#pragma unroll
-            for (int e = 0; e < NE; ++e) xs[e] = -(cs * eb.center[e]);  // |c * centre| <= 600 on this path
-            exp_bounded_n<NE>(xs, scale);
-#pragma unroll
-            for (int e = 0; e < NE; ++e) scale[e] = (as * scale[e]) * eb.half[e];
-        }
-        double D[10], R[10];
-        uint32_t redo_bits = 0;
-#pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            if (eb.new_half[e]) {
-                const double y = cs * eb.half[e];
-#pragma unroll
-                for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
+        double rs = 0.0, nn = 0.0, nf = 0.0;  // rate sum, #not-NaN, #finite of this lane's sites
+        int qh = 0, qn = 0;
+        double lam_in = (lane < item.count) ? __ldg(rp + lane) : __longlong_as_double(0x7ff8000000000000LL);
+        __syncwarp();
+        for (int base = 0;; base += 32) {
+            const bool more = base < item.count;
+            if (more) {
+                const double lam = lam_in;
+                {
+                    const int nb = base + 32 + lane;
+                    lam_in = (nb < item.count) ? __ldg(rp + nb) : __longlong_as_double(0x7ff8000000000000LL);
+                }
+                const bool notnan = lam == lam;  // lanes past the item hold NaN
+                const bool fin = fabs(lam) <= DBL_MAX;
+                rs += notnan ? lam : 0.0;
+                nn += notnan ? 1.0 : 0.0;
+                nf += fin ? 1.0 : 0.0;
+                const bool act = fin && (16.0 * (lam * lam) != 0.0);
+                const unsigned ballot = __ballot_sync(0xffffffffu, act);
+                if (act) {
+                    const int pos = (qn + __popc(ballot & ((1u << lane) - 1u))) & 63;
+                    q[pos] = lam;
+                    qsrc[pos] = uint16_t(base + lane);
+                }
+                qn += __popc(ballot);
+                __syncwarp();
             }
-            double result, abserr, resabs, resasc;
-            gk21_shared_exp(eb, e, scale[e], D, R, result, abserr, resabs, resasc);
-            const bool keep = fast && qags_first_panel_final(result, abserr, resabs, resasc);
-            cols[2 * e][tid] = keep ? result : 0.0;
-            cols[2 * e + 1][tid] = keep ? abserr : 0.0;
-            redo_bits |= (fin && !keep) ? (1u << e) : 0u;
-        }
+            if constexpr (NE > 0) {
+                while (qn - qh >= 32 || (!more && qn > qh)) {
+                    const int cnt = min(32, qn - qh);
+                    const bool on = lane < cnt;
+                    const double lam2 = on ? q[(qh + lane) & 63] : 0.0;
+                    const uint32_t src = on ? qsrc[(qh + lane) & 63] : 0u;
+                    qh += cnt;
+                    const double a = 16.0 * (lam2 * lam2);
+                    const double c = 4.0 * lam2;
+                    // fast path: all exponent arguments stay well inside the normal range, every node value >= 0
+                    const bool fast = on && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
+                    const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps idle lanes' arithmetic finite
+                    // common factors a e^{-c centre} h of all epochs first: independent chains
+                    double scale[NA];
+                    {
+                        double xs[NE > 0 ? NE : 1];
 #pragma unroll
-        for (int e = 0; e < NE; ++e) {
-            const uint32_t ballot = __ballot_sync(0xffffffffu, (redo_bits >> e) & 1u);
-            if (lane == 0) flagged[e][warp] = ballot;
-        }
-        if (eb.first) {
-            cols[2 * kEpochsPerLaunch + 0][tid] = notnan ? lam : 0.0;
-            cols[2 * kEpochsPerLaunch + 1][tid] = notnan ? 1.0 : 0.0;
-            cols[2 * kEpochsPerLaunch + 2][tid] = fin ? 1.0 : 0.0;
-        }
-        __syncthreads();
-        // ---- column sums: warp w owns columns w, w + 8, w + 16; fixed order ----
-        double* out = args.qpart + size_t(it) * row;
+                        for (int e = 0; e < NE; ++e) xs[e] = -(cs * eb.center[e]);  // |c * centre| <= 600 here
+                        double ex[NE > 0 ? NE : 1];
+                        exp_bounded_n<(NE > 0 ? NE : 1)>(xs, ex);
 #pragma unroll
-        for (int rep = 0; rep < (kQuadCols + 7) / 8; ++rep) {
-            const int col = warp + 8 * rep;
-            const bool is_stat = col >= 2 * kEpochsPerLaunch;
-            const bool wanted = col < kQuadCols && (is_stat ? eb.first != 0 : col < 2 * NE);
-            if (wanted) {  // warp-uniform
-                double v = 0.0;
+                        for (int e = 0; e < NE; ++e) scale[e] = (as * ex[e]) * eb.half[e];
+                    }
+                    double D[10], R[10];
 #pragma unroll
-                for (int k = 0; k < kQuadBlock / 32; ++k) v += cols[col][lane + 32 * k];
+                    for (int e = 0; e < NE; ++e) {
+                        if (eb.new_half[e]) {
+                            const double y = cs * eb.half[e];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-                if (lane == 0) {
-                    if (is_stat) out[2 * eb.e_total + (col - 2 * kEpochsPerLaunch)] = v;
-                    else out[2 * eb.col[col >> 1] + (col & 1)] = v;
+                            for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
+                        }
+                        double result, abserr, resabs, resasc;
+                        gk21_shared_exp(eb, e, scale[e], D, R, result, abserr, resabs, resasc);
+                        const bool keep = fast && qags_first_panel_final(result, abserr, resabs, resasc);
+                        s_acc[warp][2 * e][lane] += keep ? result : 0.0;
+                        s_acc[warp][2 * e + 1][lane] += keep ? abserr : 0.0;
+                        if (on && !keep)  // rare: hand the site (by its position in the item) to quad_fix_kernel
+                            atomicOr(&s_flag[warp][e][src >> 5], 1u << (src & 31));
+                    }
+                    __syncwarp();
                 }
             }
+            if (!more) break;
         }
-        if (tid < NE) {
-            const int e = tid;
+        // ---- close the item: one shuffle tree per column, fixed order ----
+        double* out = args.qpart + size_t(it) * row;
+#pragma unroll
+        for (int k = 0; k < 2 * NE; ++k) {
+            double v = s_acc[warp][k][lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) out[2 * eb.col[k >> 1] + (k & 1)] = v;
+        }
+        if (eb.first) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                rs += __shfl_down_sync(0xffffffffu, rs, off);
+                nn += __shfl_down_sync(0xffffffffu, nn, off);
+                nf += __shfl_down_sync(0xffffffffu, nf, off);
+            }
+            if (lane == 0) {
+                out[2 * eb.e_total + 0] = rs;
+                out[2 * eb.e_total + 1] = nn;
+                out[2 * eb.e_total + 2] = nf;
+                out[2 * eb.e_total + 3] = 0.0;  // multi-panel count, accumulated by quad_fix_kernel
+            }
+        }
+        __syncwarp();
+        if (lane < NE) {
+            const int e = lane;
             uint32_t any = 0;
 #pragma unroll
-            for (int w = 0; w < kQuadBlock / 32; ++w) any |= flagged[e][w];
+            for (int w = 0; w < kQuadBlock / 32; ++w) any |= s_flag[warp][e][w];
             if (any) {
                 FixEntry* fe = args.fix + atomicAdd(args.fix_count, 1u);
                 fe->item = it;
                 fe->slot = e;
 #pragma unroll
-                for (int w = 0; w < kQuadBlock / 32; ++w) fe->mask[w] = flagged[e][w];
+                for (int w = 0; w < kQuadBlock / 32; ++w) fe->mask[w] = s_flag[warp][e][w];
             }
-        } else if (tid == 32 && eb.first) {
-            out[2 * eb.e_total + 3] = 0.0;  // multi-panel count, accumulated by quad_fix_kernel
         }
-        __syncthreads();
-        item = item_next;
-        item_next = item_after;
-        lam = lam_next;
+        __syncwarp();
     }
 }
 

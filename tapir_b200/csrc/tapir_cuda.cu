@@ -623,15 +623,18 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
             qa.n_items = int32_t(plan.n_quad_items);
             int k = 0;
             for (const EpochBatch& eb : plan.batches) {
-                // one counter per batch (d_counter[1..]); slot 0 is the profile kernel's work queue head
-                qa.fix_count = ln.d_counter.as<uint32_t>() + 1 + k++;
-                const unsigned qgrid = unsigned(std::min<int64_t>(plan.n_quad_items, int64_t(ctx->sm_count) * 2));
+                // two counters per batch (d_counter[1..]); slot 0 is the profile kernel's work queue head
+                qa.fix_count = ln.d_counter.as<uint32_t>() + 1 + 2 * k;
+                qa.queue = ln.d_counter.as<uint32_t>() + 2 + 2 * k;
+                ++k;
+                const int64_t want = (plan.n_quad_items + kQuadWarps - 1) / kQuadWarps;
+                const unsigned qgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(ctx->sm_count) * 4)));
                 switch (eb.n) {
-                    case 0: quad_kernel<0><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;  // rate statistics only
-                    case 1: quad_kernel<1><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;
-                    case 2: quad_kernel<2><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;
-                    case 3: quad_kernel<3><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;
-                    default: quad_kernel<4><<<qgrid, kQuadBlock, 0, sq>>>(qa, eb); break;
+                    case 0: quad_kernel<0><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;  // rate statistics only
+                    case 1: quad_kernel<1><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    case 2: quad_kernel<2><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    case 3: quad_kernel<3><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    default: quad_kernel<4><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
                 }
                 CU(ctx, cudaGetLastError());
                 quad_fix_kernel<<<unsigned(ctx->sm_count * 4), 128, 0, sq>>>(qa, eb);

@@ -278,6 +278,21 @@ class Engine:
         check(self._lib.tapir_cuda_flush_l2(self._ctx), self._ctx)
 
 
+def bind_host_thread_near(device: int) -> bool:
+    """Pin the calling thread to the CPUs NVML reports as closest to `device` (so that pinned buffers allocated
+    afterwards are first-touched on the GPU's NUMA node).  Best effort: False when NVML is unavailable."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[device]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else device
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return True
+    except Exception:
+        return False
+
+
 def device_count() -> int:
     n = ctypes.c_int()
     lib = _lib.load()
