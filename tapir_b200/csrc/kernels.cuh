@@ -171,88 +171,88 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 __syncwarp();
             }
             while (qn - qh >= 32 || (!more && qn > qh)) {
-            const int cnt = min(32, qn - qh);
-            const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
-            qh += cnt;
-            // ---- generation: this lane's site -> U[0..31], W[0..H-1] (power tables) ----
-            // rows of lanes >= cnt are U = 0, W = 1: they add exactly 0
-            {
-                double a = 16.0 * (lam * lam);
-                const bool ok = lane < cnt;  // queue entries are finite and non-zero; idle lanes build a zero row
-                const double c = ok ? 4.0 * lam : 0.0;
-                a = ok ? a : 0.0;
-                const double q = exp_full(-c);
-                const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
-                const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
-                const double qB = q16 * q16;  // q^32
-                double xa = u0, xb = u0 * q16;
+                const int cnt = min(32, qn - qh);
+                const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
+                qh += cnt;
+                // ---- generation: this lane's site -> U[0..31], W[0..H-1] (power tables) ----
+                // rows of lanes >= cnt are U = 0, W = 1: they add exactly 0
+                {
+                    double a = 16.0 * (lam * lam);
+                    const bool ok = lane < cnt;  // queue entries are finite and non-zero; idle lanes build a zero row
+                    const double c = ok ? 4.0 * lam : 0.0;
+                    a = ok ? a : 0.0;
+                    const double q = exp_full(-c);
+                    const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
+                    const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
+                    const double qB = q16 * q16;  // q^32
+                    double xa = u0, xb = u0 * q16;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    st_shared_v2(myU + 2 * k, xa, xa * q);
-                    st_shared_v2(myU + 16 + 2 * k, xb, xb * q);
-                    xa *= q2;
-                    xb *= q2;
-                }
-                if constexpr (RH >= 2) {
-                    const double qB2 = qB * qB;
-                    double qBh = qB2;  // -> qB^(H/2)
-#pragma unroll
-                    for (int k = 2; k < H / 2; k *= 2) qBh *= qBh;
-                    double wa = 1.0, wb = qBh;
-#pragma unroll
-                    for (int k = 0; k < H / 4; ++k) {
-                        st_shared_v2(myW + 2 * k, wa, wa * qB);
-                        st_shared_v2(myW + H / 2 + 2 * k, wb, wb * qB);
-                        wa *= qB2;
-                        wb *= qB2;
+                    for (int k = 0; k < 8; ++k) {
+                        st_shared_v2(myU + 2 * k, xa, xa * q);
+                        st_shared_v2(myU + 16 + 2 * k, xb, xb * q);
+                        xa *= q2;
+                        xb *= q2;
                     }
-                } else {
-                    const double qB2 = qB * qB;
-                    double wa = 1.0;
+                    if constexpr (RH >= 2) {
+                        const double qB2 = qB * qB;
+                        double qBh = qB2;  // -> qB^(H/2)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        st_shared_v2(myW + 2 * k, wa, wa * qB);
-                        wa *= qB2;
-                    }
-                }
-            }
-            __syncwarp();
-            // ---- contraction over the chunk's sites: acc(lo,hi) += sum_s U[s][lo] * W[s][hi] ----
-            // 4 sites per k-step; fragments of step s+1 are fetched while the MMAs of step s issue
-            {
-                auto fetch = [&](double (&a)[4], double (&b)[RH], int step) {
-                    const double* up = fragU + step * (4 * US);
-                    const double* wp = fragW + step * (4 * WS);
-                    const double2 u01 = *reinterpret_cast<const double2*>(up);
-                    const double2 u23 = *reinterpret_cast<const double2*>(up + 2);
-                    a[0] = u01.x; a[1] = u01.y; a[2] = u23.x; a[3] = u23.y;
-                    if constexpr (RH == 1) {
-                        b[0] = wp[0];
+                        for (int k = 2; k < H / 2; k *= 2) qBh *= qBh;
+                        double wa = 1.0, wb = qBh;
+#pragma unroll
+                        for (int k = 0; k < H / 4; ++k) {
+                            st_shared_v2(myW + 2 * k, wa, wa * qB);
+                            st_shared_v2(myW + H / 2 + 2 * k, wb, wb * qB);
+                            wa *= qB2;
+                            wb *= qB2;
+                        }
                     } else {
+                        const double qB2 = qB * qB;
+                        double wa = 1.0;
 #pragma unroll
-                        for (int r = 0; r < RH / 2; ++r) {
-                            const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
-                            b[2 * r] = v.x; b[2 * r + 1] = v.y;
+                        for (int k = 0; k < 4; ++k) {
+                            st_shared_v2(myW + 2 * k, wa, wa * qB);
+                            wa *= qB2;
                         }
                     }
-                };
-                auto mma_step = [&](const double (&a)[4], const double (&b)[RH]) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < RH; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-                };
-                const int nk = (cnt + 3) >> 2;  // 1..8 k-steps; rows past cnt are zero, so odd counts round up
-                double a0[4], b0[RH], a1[4], b1[RH];
-                fetch(a0, b0, 0);
-                for (int s = 0; s < nk; s += 2) {
-                    fetch(a1, b1, s + 1);
-                    mma_step(a0, b0);
-                    fetch(a0, b0, min(s + 2, 7));
-                    mma_step(a1, b1);
                 }
-            }
-            __syncwarp();
+                __syncwarp();
+                // ---- contraction over the chunk's sites: acc(lo,hi) += sum_s U[s][lo] * W[s][hi] ----
+                // 4 sites per k-step; fragments of step s+1 are fetched while the MMAs of step s issue
+                {
+                    auto fetch = [&](double (&a)[4], double (&b)[RH], int step) {
+                        const double* up = fragU + step * (4 * US);
+                        const double* wp = fragW + step * (4 * WS);
+                        const double2 u01 = *reinterpret_cast<const double2*>(up);
+                        const double2 u23 = *reinterpret_cast<const double2*>(up + 2);
+                        a[0] = u01.x; a[1] = u01.y; a[2] = u23.x; a[3] = u23.y;
+                        if constexpr (RH == 1) {
+                            b[0] = wp[0];
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < RH / 2; ++r) {
+                                const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
+                                b[2 * r] = v.x; b[2 * r + 1] = v.y;
+                            }
+                        }
+                    };
+                    auto mma_step = [&](const double (&a)[4], const double (&b)[RH]) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < RH; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    };
+                    const int nk = (cnt + 3) >> 2;  // 1..8 k-steps; rows past cnt are zero, so odd counts round up
+                    double a0[4], b0[RH], a1[4], b1[RH];
+                    fetch(a0, b0, 0);
+                    for (int s = 0; s < nk; s += 2) {
+                        fetch(a1, b1, s + 1);
+                        mma_step(a0, b0);
+                        fetch(a0, b0, min(s + 2, 7));
+                        mma_step(a1, b1);
+                    }
+                }
+                __syncwarp();
             }  // groups of 32 active sites
             if (!more) break;
         }

@@ -98,7 +98,7 @@ struct Plan {
 }  // namespace
 
 // One in-flight batch (or chunk of a batch): its own streams, device buffers and pinned staging, so that
-// two lanes can overlap H2D, kernels and D2H of consecutive chunks.
+// the lanes can overlap H2D, kernels and D2H of consecutive chunks.
 struct Lane {
     cudaStream_t stream = nullptr;    // copies, profile, finalize
     cudaStream_t stream_q = nullptr;  // epoch-integral kernels, concurrent with the profile kernel
@@ -121,7 +121,7 @@ struct Lane {
     DevBuf* all_bufs[10] = {&d_rates, &d_work, &d_counter, &d_ws, &d_tile_max, &d_tile_arg, &d_qpart, &d_fix, &d_pi_net, &d_small};
 };
 
-constexpr int kLanes = 2;
+constexpr int kLanes = 3;
 
 struct tapir_cuda_ctx {
     int device = 0;
@@ -583,7 +583,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
     const bool fork = !ctx->serial_kernels && plan.L > 0 && plan.n_quad_items > 0 && plan.n_prof_items > 0 && plan.T > 0;
     cudaStream_t sq = fork ? ln.stream_q : st;
     int launches = 0;
-    CU(ctx, cudaEventRecord(ln.ev[0], st));
+    if (timing) CU(ctx, cudaEventRecord(ln.ev[0], st));
     if (plan.L > 0) {
         CU(ctx, cudaMemsetAsync(ln.d_counter.p, 0, 256, st));
         if (fork) {
@@ -613,7 +613,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
             CU(ctx, e);
             ++launches;
         }
-        CU(ctx, cudaEventRecord(ln.ev[1], st));
+        if (timing) CU(ctx, cudaEventRecord(ln.ev[1], st));
         if (plan.n_quad_items > 0) {
             QuadArgs qa;
             qa.rates = ln.d_rates.as<double>();
@@ -646,7 +646,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
             CU(ctx, cudaEventRecord(ln.ev_join, sq));
             CU(ctx, cudaStreamWaitEvent(st, ln.ev_join, 0));
         }
-        CU(ctx, cudaEventRecord(ln.ev[2], st));
+        if (timing) CU(ctx, cudaEventRecord(ln.ev[2], st));
         {
             FinalArgs fa;
             fa.n_loci = plan.L;
@@ -679,8 +679,8 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
             ++launches;
         }
     } else {
-        CU(ctx, cudaEventRecord(ln.ev[1], st));
-        CU(ctx, cudaEventRecord(ln.ev[2], st));
+        if (timing) CU(ctx, cudaEventRecord(ln.ev[1], st));
+        if (timing) CU(ctx, cudaEventRecord(ln.ev[2], st));
     }
     if (ctx->gather_slot_ptr && plan.L > 0) {
         // NVLink push: the batch's small block goes into this rank's slot of the owner's buffer (peer memory),
@@ -705,7 +705,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
         CU(ctx, cudaGetLastError());
         ++launches;
     }
-    CU(ctx, cudaEventRecord(ln.ev[3], st));
+    if (timing) CU(ctx, cudaEventRecord(ln.ev[3], st));
     if (sync || timing) CU(ctx, cudaStreamSynchronize(st));
     if (timing) {
         memset(timing, 0, sizeof *timing);
@@ -938,7 +938,7 @@ int tapir_cuda_download(tapir_cuda_ctx* ctx, const tapir_results* out)
     return lane_download(ctx, ctx->lanes[0], out, 0, true);
 }
 
-// Whole path with host buffers.  Large batches are cut into chunks of loci that alternate between the two
+// Whole path with host buffers.  Large batches are cut into chunks of loci that rotate over the
 // lanes, so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k (PCIe is
 // full duplex; a step of this path moves ~3x more bytes out than in).
 int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_results* host_out)
@@ -951,7 +951,7 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
     const int64_t L = p->n_loci;
     const int64_t nnz = L ? p->offsets[L] : 0;
     const double bytes = double(nnz) * 8.0 + ((p->flags & TAPIR_WANT_PROFILE) ? double(L) * double(p->n_grid) * 8.0 : 0.0);
-    int64_t n_chunks = int64_t(bytes / double(12 << 20));
+    int64_t n_chunks = int64_t(bytes / double(8 << 20));
     n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, 16));
     if (L < 64 * n_chunks) n_chunks = 1;  // few (possibly huge) loci: one pass, split over sites instead
     if (ctx->gather_slot_ptr) {  // where each chunk's rows go inside the full batch's small-block layout
