@@ -494,27 +494,21 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 4) quad_kernel(const QuadArgs
                     // fast path: all exponent arguments stay well inside the normal range, every node value >= 0
                     const bool fast = on && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
                     const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps idle lanes' arithmetic finite
-                    // common factors a e^{-c centre} h of all epochs first: independent chains
-                    double scale[NA];
-                    {
-                        double xs[NE > 0 ? NE : 1];
-#pragma unroll
-                        for (int e = 0; e < NE; ++e) xs[e] = -(cs * eb.center[e]);  // |c * centre| <= 600 here
-                        double ex[NE > 0 ? NE : 1];
-                        exp_bounded_n<(NE > 0 ? NE : 1)>(xs, ex);
-#pragma unroll
-                        for (int e = 0; e < NE; ++e) scale[e] = (as * ex[e]) * eb.half[e];
-                    }
                     double D[10], R[10];
-#pragma unroll
+                    // one copy of the GK21 code, looped over the epochs: the fully unrolled form (4 x ~350
+                    // instructions) thrashed the instruction cache once the warps ran out of step (18 % of the
+                    // stall samples were instruction fetches)
+#pragma unroll 1
                     for (int e = 0; e < NE; ++e) {
                         if (eb.new_half[e]) {
                             const double y = cs * eb.half[e];
 #pragma unroll
                             for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
                         }
+                        // common factor a e^{-c centre} h; |c * centre| <= 600 on this path
+                        const double scale = (as * exp_bounded(-(cs * eb.center[e]))) * eb.half[e];
                         double result, abserr, resabs, resasc;
-                        gk21_shared_exp(eb, e, scale[e], D, R, result, abserr, resabs, resasc);
+                        gk21_shared_exp(eb, e, scale, D, R, result, abserr, resabs, resasc);
                         const bool keep = fast && qags_first_panel_final(result, abserr, resabs, resasc);
                         s_acc[warp][2 * e][lane] += keep ? result : 0.0;
                         s_acc[warp][2 * e + 1][lane] += keep ? abserr : 0.0;
