@@ -442,6 +442,10 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     plan.flags = p->flags;
     plan.nnz = plan.L ? off[plan.L] - base : 0;
     plan.rh = choose_rh(std::max<int64_t>(plan.T, 1));
+    if (const char* env = getenv("TAPIR_CUDA_RH")) {  // tuning override: 1, 2, 4 or 8
+        const int v = atoi(env);
+        if (v == 1 || v == 2 || v == 4 || v == 8) plan.rh = v;
+    }
     plan.TT = 32 * 8 * plan.rh;
     plan.n_tiles = int32_t(std::max<int64_t>(1, (plan.T + plan.TT - 1) / plan.TT));
     fill_batches(plan, p->epoch_ab);
