@@ -152,6 +152,15 @@ int tapir_cuda_nansum_rows(tapir_cuda_ctx *ctx, const double *matrix, int64_t n_
 int tapir_cuda_site_integrals(tapir_cuda_ctx *ctx, double a, double b, const double *rates, int64_t n,
                               double *integral, double *abserr, int32_t *panels);
 
+/* --- batched rate ingest (host only, no device needed): parse_site_rates' read half (compute.py:30-39) for
+ * n_files HyPhy site-rate JSON files on n_threads threads into one CSR pack.  offsets[n_files + 1] is always
+ * filled and *needed = total number of sites; rates (each divided by `correction`) is filled only when
+ * capacity >= *needed, so a caller may first call with capacity 0 to size a (pinned) buffer.  Files are not
+ * modified.  Returns TAPIR_E_INVALID on an unreadable or malformed file (tapir_ingest_last_error()). */
+int tapir_ingest_rates(const char *const *paths, int64_t n_files, int n_threads, double correction, int64_t *offsets,
+                       double *rates, int64_t capacity, int64_t *needed);
+const char *tapir_ingest_last_error(void);
+
 /* --- measurement helpers used by bench.py --- */
 /* sustained FP64 FMA rate of this device, TFLOP/s (2 flop per DFMA), dependent-chain-free register kernel */
 int tapir_cuda_fp64_peak(tapir_cuda_ctx *ctx, double *tflops, float *ms);

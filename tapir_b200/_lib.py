@@ -78,6 +78,9 @@ SYMBOLS = {
     "tapir_cuda_pi_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "tapir_cuda_nansum_rows": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "tapir_cuda_site_integrals": (ctypes.c_int, [_vp, _dbl, _dbl, _vp, _i64, _vp, _vp, _vp]),
+    "tapir_ingest_rates": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), _i64, ctypes.c_int, _dbl, _vp, _vp, _i64,
+                                          ctypes.POINTER(_i64)]),
+    "tapir_ingest_last_error": (ctypes.c_char_p, []),
     "tapir_cuda_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(_dbl), ctypes.POINTER(ctypes.c_float)]),
     "tapir_cuda_flush_l2": (ctypes.c_int, [_vp]),
 }

@@ -44,6 +44,10 @@ def get_args(argv=None):
         with the alignment file name in the 1st column, the start of the
         interval (0-offset) in the 2nd column, and the end of the interval in
         the 3rd column.""")
+    # extension (not in the reference): read the rate files with the library's multi-threaded C++ reader and
+    # leave them untouched, instead of json.load + rewrite-with-corrected_rates per file (compute.py:30-43)
+    parser.add_argument('--no-rate-rewrite', default=False, action='store_true',
+                        help="With --site-rates: do not rewrite the *.rates files with corrected rates (fast batched ingest)")
     return parser.parse_args(argv)
 
 
@@ -96,10 +100,28 @@ def worker(params):
     return compute.compute_loci([rates], time_vector, times, epochs, names=[alignment], keep_matrix=True)[0]
 
 
-def run_batch(params, threads=1):
-    """All loci of a run: host-side ingest (optionally threaded), then ONE device pass."""
+def run_batch(params, threads=1, native_ingest=False):
+    """All loci of a run: host-side ingest (optionally threaded), then ONE device pass.
+
+    native_ingest (only for --site-rates parameters): the rate files are parsed by tapir_ingest_rates on
+    `threads` C++ threads straight into one CSR pack and are not rewritten."""
     if not params:
         return []
+    if native_ingest and all(p[3] is None for p in params):
+        from . import ingest
+        sys.stdout.write("." * len(params))
+        sys.stdout.flush()
+        offsets, rates = ingest.read_rate_files([p[4] for p in params], correction=params[0][5], threads=threads, pinned=False)
+        subsets = params[0][10]
+        vectors = []
+        for l, p in enumerate(params):
+            v = rates[offsets[l]:offsets[l + 1]]
+            name = os.path.basename(p[6])
+            if name in subsets:
+                v = v[subsets[name][0]:subsets[name][1]]
+            vectors.append(v)
+        time_vector, times, epochs = params[0][0], params[0][7], params[0][8]
+        return compute.compute_loci(vectors, time_vector, times, epochs, names=[p[6] for p in params])
     if threads > 1:
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=threads) as pool:
@@ -140,7 +162,7 @@ def main(argv=None):
             params.append([time_vector, args.hyphy, template, None, rate_file, correction, rate_file,
                            args.times, args.intervals, args.threshold, subset_pi])
     threads = max(1, (os.cpu_count() or 2) - 1) if args.multiprocessing else 1
-    pis = run_batch(params, threads=threads)
+    pis = run_batch(params, threads=threads, native_ingest=args.site_rates and args.no_rate_rewrite)
     db_name = os.path.join(args.output, 'phylogenetic-informativeness.sqlite')
     sys.stdout.write("\nStoring results in {0}...".format(db_name))
     sys.stdout.flush()

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_symbols():
     text = open(os.path.join(ROOT, "include", "tapir_cuda.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(tapir_cuda_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(tapir_(?:cuda|ingest)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_header_symbol():

@@ -123,3 +123,32 @@ def test_cli_site_rates_end_to_end(golden, tmp_path, capsys):
     from tapir_b200 import db
     assert db.max_pi_epochs(conn) == {"164-174": 3}
     conn.close()
+
+
+def test_cli_native_ingest_matches_default_path(golden, tmp_path):
+    """--no-rate-rewrite (extension): C++ batched ingest, files untouched, same database; subset map honoured."""
+    from tapir_b200 import driver
+    dbs = []
+    for tag, extra in (("a", []), ("b", ["--no-rate-rewrite", "--multiprocessing"])):
+        indir, outdir = tmp_path / ("in" + tag), tmp_path / ("out" + tag)
+        indir.mkdir()
+        outdir.mkdir()
+        for name in ("uce-1", "uce-2"):
+            shutil.copyfile(os.path.join(DATA, "test-uniform-draw-weights.rates.json"), indir / (name + ".rates"))
+        smap = tmp_path / ("map" + tag + ".tsv")
+        smap.write_text("uce-2.rates\t10\t60\n")
+        before = open(indir / "uce-1.rates").read()
+        assert driver.main([str(indir), os.path.join(DATA, "Euteleost.tree"), "--output", str(outdir),
+                            "--intervals=32-42,88-98", "--times=37,93", "--site-rates", "--subset-pi-map-file", str(smap)]
+                           + extra) == 0
+        assert (open(indir / "uce-1.rates").read() == before) == bool(extra)      # rewritten only on the default path
+        conn = sqlite3.connect(str(outdir / "phylogenetic-informativeness.sqlite"))
+        rows = {}
+        for locus, in conn.execute("SELECT locus FROM loci"):
+            key = conn.execute("SELECT id FROM loci WHERE locus=?", (locus,)).fetchone()[0]
+            rows[locus] = (conn.execute("SELECT time, pi FROM net WHERE id=? ORDER BY time", (key,)).fetchall(),
+                           conn.execute("SELECT interval, pi, error FROM interval WHERE id=? ORDER BY interval", (key,)).fetchall())
+        conn.close()
+        dbs.append(rows)
+    assert dbs[0] == dbs[1]                                         # bit-identical results either way
+    assert dbs[0]["uce-1"] != dbs[0]["uce-2"]                       # the subset slice changed locus 2
