@@ -154,14 +154,18 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
         // a time, so the contraction only ever sees sites that contribute.
         const double* rp = args.rates + item.site_begin;
         int qh = 0, qn = 0;  // queue head / tail (running counts)
+        // rates are fetched two rounds ahead: a round that completes no group of 32 active sites consumes its
+        // load immediately, so a distance of one would expose the DRAM latency every other round
         double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
+        double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
         for (int base = 0;; base += 32) {
             const bool more = base < item.n_sites;
             if (more) {
                 const double lam_new = lam_in;
+                lam_in = lam_in2;
                 {
-                    const int nb = base + 32 + lane;
-                    lam_in = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                    const int nb = base + 64 + lane;
+                    lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
                 }
                 const double a_new = 16.0 * (lam_new * lam_new);
                 const bool act = (fabs(a_new) <= DBL_MAX) && (a_new != 0.0);  // lanes past the item hold 0
@@ -457,15 +461,18 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 4) quad_kernel(const QuadArgs
         }
         double rs = 0.0, nn = 0.0, nf = 0.0;  // rate sum, #not-NaN, #finite of this lane's sites
         int qh = 0, qn = 0;
-        double lam_in = (lane < item.count) ? __ldg(rp + lane) : __longlong_as_double(0x7ff8000000000000LL);
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        double lam_in = (lane < item.count) ? __ldg(rp + lane) : qnan;        // fetched two rounds ahead, as in
+        double lam_in2 = (32 + lane < item.count) ? __ldg(rp + 32 + lane) : qnan;  // profile_kernel
         __syncwarp();
         for (int base = 0;; base += 32) {
             const bool more = base < item.count;
             if (more) {
                 const double lam = lam_in;
+                lam_in = lam_in2;
                 {
-                    const int nb = base + 32 + lane;
-                    lam_in = (nb < item.count) ? __ldg(rp + nb) : __longlong_as_double(0x7ff8000000000000LL);
+                    const int nb = base + 64 + lane;
+                    lam_in2 = (nb < item.count) ? __ldg(rp + nb) : qnan;
                 }
                 const bool notnan = lam == lam;  // lanes past the item hold NaN
                 const bool fin = fabs(lam) <= DBL_MAX;
