@@ -434,7 +434,7 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
 constexpr int kQuadWarps = 4;  // warps per CTA
 
 template <int NE>
-__global__ void __launch_bounds__(kQuadWarps * 32, 4) quad_kernel(const QuadArgs args, const EpochBatch eb)
+__global__ void __launch_bounds__(kQuadWarps * 32, 3) quad_kernel(const QuadArgs args, const EpochBatch eb)
 {
     constexpr int NA = NE > 0 ? 2 * NE : 1;
     __shared__ double s_q[kQuadWarps][64];                 // queue of active rates

@@ -632,7 +632,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
                 qa.queue = ln.d_counter.as<uint32_t>() + 2 + 2 * k;
                 ++k;
                 const int64_t want = (plan.n_quad_items + kQuadWarps - 1) / kQuadWarps;
-                const unsigned qgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(ctx->sm_count) * 4)));
+                const unsigned qgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(ctx->sm_count) * 3)));
                 switch (eb.n) {
                     case 0: quad_kernel<0><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;  // rate statistics only
                     case 1: quad_kernel<1><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
