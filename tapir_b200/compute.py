@@ -170,14 +170,15 @@ def cull_uninformative_rates(rates, inform):
     return rates * inform
 
 
-def compute_loci(rate_vectors, time_vector, times, epochs, names=None, keep_matrix=False, engine=None):
+def compute_loci(rate_vectors, time_vector, times, epochs, names=None, keep_matrix=False, engine=None, devices=None):
     """The body of worker() (bin/tapir_compute.py:104-123) for MANY loci in one device pass.
 
     rate_vectors: sequence of 1-D rate arrays (NaN = culled site), already corrected/subset.
     Returns a list of 7-tuples (name, rates, mean_rate, pi, pi_net, pi_times, pi_epochs) in input order,
     exactly what insert_pi_data (tapir/db.py:44-61) consumes; `pi` (the (T,S) matrix the reference
-    pickles back to the parent) is None unless keep_matrix is set."""
-    eng = engine or get_engine()
+    pickles back to the parent) is None unless keep_matrix is set.  `devices`: list of CUDA device indices to
+    spread the loci over (one host thread and one context per device); default: the process-wide engine."""
+    eng = engine or (get_engine() if not (devices and len(devices) > 1) else None)
     n = len(rate_vectors)
     names = list(names) if names is not None else [None] * n
     time_vector = numpy.asarray(time_vector)
@@ -193,8 +194,14 @@ def compute_loci(rate_vectors, time_vector, times, epochs, names=None, keep_matr
             raise ValueError("locus {0!r} has no finite site rate".format(name))
     if times:
         numpy.empty(T)[list(times)]                     # numpy's IndexError for an out-of-range time (compute.py:78)
-    offsets, rates = _engine_mod.pack_csr(vectors, pinned=True)
-    res = eng.run(offsets, rates, T, list(times), [[s[0], s[1]] for s in epochs], want_profile=True)
+    span_list = [[s[0], s[1]] for s in epochs]
+    if devices is not None and len(devices) > 1:
+        from . import sharded
+        offsets, rates = _engine_mod.pack_csr(vectors, pinned=False)
+        res = sharded.run_threaded(offsets, rates, T, list(times), span_list, devices)
+    else:
+        offsets, rates = _engine_mod.pack_csr(vectors, pinned=True)
+        res = eng.run(offsets, rates, T, list(times), span_list, want_profile=True)
     labels = ["{0}-{1}".format(s[0], s[1]) for s in epochs]
     out = []
     tcol = time_vector.reshape(-1, 1)

@@ -3,7 +3,8 @@ the per-locus numpy/scipy body replaced by ONE device pass over all loci.
 
 The command line, the glob rules, the output directory rule, the Tree_*.newick side file, the rewritten
 *.rates JSON and the sqlite database are the reference's.  ``--multiprocessing`` is accepted and means
-"parse the rate files with a thread pool"; the arithmetic always runs on the GPU.
+"parse the rate files on all host cores and spread the loci over every visible GPU" (one host thread and one
+context per device); without it one GPU is used.  The arithmetic always runs on the GPU.
 """
 import argparse
 import os
@@ -13,6 +14,7 @@ from subprocess import PIPE, Popen
 import numpy
 
 from . import base, compute, db
+from .engine import device_count
 
 
 def get_args(argv=None):
@@ -100,7 +102,7 @@ def worker(params):
     return compute.compute_loci([rates], time_vector, times, epochs, names=[alignment], keep_matrix=True)[0]
 
 
-def run_batch(params, threads=1, native_ingest=False):
+def run_batch(params, threads=1, native_ingest=False, devices=None):
     """All loci of a run: host-side ingest (optionally threaded), then ONE device pass.
 
     native_ingest (only for --site-rates parameters): the rate files are parsed by tapir_ingest_rates on
@@ -121,7 +123,7 @@ def run_batch(params, threads=1, native_ingest=False):
                 v = v[subsets[name][0]:subsets[name][1]]
             vectors.append(v)
         time_vector, times, epochs = params[0][0], params[0][7], params[0][8]
-        return compute.compute_loci(vectors, time_vector, times, epochs, names=[p[6] for p in params])
+        return compute.compute_loci(vectors, time_vector, times, epochs, names=[p[6] for p in params], devices=devices)
     if threads > 1:
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=threads) as pool:
@@ -129,7 +131,8 @@ def run_batch(params, threads=1, native_ingest=False):
     else:
         loaded = [load_rates(p) for p in params]
     time_vector, times, epochs = params[0][0], params[0][7], params[0][8]
-    return compute.compute_loci([r for _, r in loaded], time_vector, times, epochs, names=[a for a, _ in loaded])
+    return compute.compute_loci([r for _, r in loaded], time_vector, times, epochs, names=[a for a, _ in loaded],
+                                devices=devices)
 
 
 def get_hyphy_conf():
@@ -161,8 +164,10 @@ def main(argv=None):
         for rate_file in base.get_files(args.alignments, '*.rates'):
             params.append([time_vector, args.hyphy, template, None, rate_file, correction, rate_file,
                            args.times, args.intervals, args.threshold, subset_pi])
+    # --multiprocessing: all host cores for the ingest (as the reference's Pool) and every visible GPU for the math
     threads = max(1, (os.cpu_count() or 2) - 1) if args.multiprocessing else 1
-    pis = run_batch(params, threads=threads, native_ingest=args.site_rates and args.no_rate_rewrite)
+    devices = list(range(max(1, device_count()))) if args.multiprocessing else None
+    pis = run_batch(params, threads=threads, native_ingest=args.site_rates and args.no_rate_rewrite, devices=devices)
     db_name = os.path.join(args.output, 'phylogenetic-informativeness.sqlite')
     sys.stdout.write("\nStoring results in {0}...".format(db_name))
     sys.stdout.flush()

@@ -85,3 +85,52 @@ def run_sharded(compute_fn, offsets, rates, n_grid, times, epochs, group=None, g
         if pi_net is not None:
             pi_net[idx] = prof[r][:idx.size]
     return unpack_small(merged, K, E, pi_net)
+
+
+def run_threaded(offsets, rates, n_grid, times, epochs, devices, want_profile=True):
+    """Single-process form for the command line: one host thread and one Engine per device (ctypes releases
+    the GIL during the call), loci partitioned as in run_sharded, results merged in the original order.
+    No collective: every device copies its own results to the host."""
+    import threading
+
+    from .engine import Engine
+
+    offsets = np.asarray(offsets, dtype=np.int64)
+    L = offsets.size - 1
+    devices = list(devices)
+    if len(devices) <= 1 or L < 2 * len(devices):
+        eng = Engine(devices[0] if devices else 0)
+        try:
+            return eng.run(offsets, rates, n_grid, times, epochs, want_profile=want_profile)
+        finally:
+            eng.close()
+    parts = partition_loci(offsets[1:] - offsets[:-1], len(devices))
+    results, errors = [None] * len(devices), [None] * len(devices)
+
+    def work(k):
+        try:
+            eng = Engine(devices[k])
+            try:
+                off_p, rates_p = shard_csr(offsets, rates, parts[k])
+                results[k] = eng.run(off_p, rates_p, n_grid, times, epochs, want_profile=want_profile)
+            finally:
+                eng.close()
+        except Exception as err:          # noqa: BLE001 - re-raised in the caller's thread
+            errors[k] = err
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for err in errors:
+        if err is not None:
+            raise err
+    K, E = len(times), len(epochs)
+    merged = np.empty((L, K + 2 * E + 6), dtype=np.float64)
+    pi_net = np.empty((L, int(n_grid)), dtype=np.float64) if want_profile else None
+    for k, idx in enumerate(parts):
+        merged[idx] = pack_small(results[k])
+        if pi_net is not None:
+            pi_net[idx] = results[k].pi_net
+    return unpack_small(merged, K, E, pi_net)

@@ -152,3 +152,20 @@ def test_cli_native_ingest_matches_default_path(golden, tmp_path):
         dbs.append(rows)
     assert dbs[0] == dbs[1]                                         # bit-identical results either way
     assert dbs[0]["uce-1"] != dbs[0]["uce-2"]                       # the subset slice changed locus 2
+
+
+def test_threaded_multi_device_equals_single(golden):
+    """--multiprocessing spreads loci over all visible GPUs (a thread and a context per device); with one GPU the
+    two 'devices' are the same card, which still exercises partition, per-device contexts and the merge."""
+    from tapir_b200 import compute, engine, synthetic
+    rng = np.random.default_rng(5)
+    loci = [synthetic.uce_rates(rng, int(n), 300, nan_frac=0.03) for n in rng.integers(20, 400, size=57)]
+    tv = compute.get_time(0, 300)
+    times, epochs = [5, 250], [[32, 42], [88, 98], [164, 174]]
+    one = compute.compute_loci(loci, tv, times, epochs, names=list(map(str, range(57))))
+    n_dev = engine.device_count()
+    many = compute.compute_loci(loci, tv, times, epochs, names=list(map(str, range(57))),
+                                devices=[0, 1 % n_dev, 0])
+    for a, b in zip(one, many):
+        assert a[0] == b[0] and np.array_equal(a[4], b[4]) and a[5] == b[5] and a[6] == b[6]
+        np.testing.assert_allclose(a[2], b[2], rtol=0, atol=0, equal_nan=True)
