@@ -211,6 +211,10 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, profile_kernel<RH>, kProfWarps * 32, Cfg::SmemBytes);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (const char* env = getenv("TAPIR_PROF_CTAS_PER_SM")) {  // tuning override (co-residency experiments)
+        const int v = atoi(env);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     int64_t grid = int64_t(ctx->sm_count) * per_sm;
     const int64_t need = (n_items + kProfWarps - 1) / kProfWarps;
     if (grid > need) grid = need;
@@ -632,7 +636,12 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
                 qa.queue = ln.d_counter.as<uint32_t>() + 2 + 2 * k;
                 ++k;
                 const int64_t want = (plan.n_quad_items + kQuadWarps - 1) / kQuadWarps;
-                const unsigned qgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(ctx->sm_count) * 3)));
+                int q_per_sm = 3;
+                if (const char* env = getenv("TAPIR_QUAD_CTAS_PER_SM")) {  // tuning override
+                    const int v = atoi(env);
+                    if (v >= 1 && v <= 3) q_per_sm = v;
+                }
+                const unsigned qgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(ctx->sm_count) * q_per_sm)));
                 switch (eb.n) {
                     case 0: quad_kernel<0><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;  // rate statistics only
                     case 1: quad_kernel<1><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
