@@ -712,6 +712,8 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
             pa.words[i] = uint32_t(size_t(plan.L) * row_bytes[i] / 4);
             end = std::max(end, dst_off + size_t(plan.L) * row_bytes[i]);
         }
+        if (size_t(plan.L) * std::max(K, E) * 2 > size_t(UINT32_MAX))
+            return fail(ctx, TAPIR_E_INVALID, "batch too large for the gather push: split it into several calls");
         if (end > ctx->gather_slot_bytes)
             return fail(ctx, TAPIR_E_STATE, "gather slot of %zu bytes is smaller than the batch's %zu", ctx->gather_slot_bytes, end);
         push_small_kernel<<<unsigned(std::min<int64_t>(ctx->sm_count, (plan.L * 16 + 255) / 256 + 1)), 256, 0, st>>>(pa);

@@ -405,3 +405,30 @@ def test_randomised_batches_vs_oracle(eng, seed):
         else:
             with np.errstate(invalid="ignore"):
                 np.testing.assert_allclose(res.mean_rate[l], ok.sum() / ok.size, rtol=1e-12)
+
+
+def test_properties_cfg3_ragged_large(eng):
+    """BASELINE config 3 at a fifth of its size (10,000 ragged loci, 200-5,000 sites, 4,096-point grid, two time
+    tiles per locus, chunked pipeline): spot checks against numpy / the oracle and size-independent properties."""
+    from oracle import capi
+    from tapir_b200 import synthetic
+    off, rates, T = synthetic.build("cfg3", scale=0.2)
+    res = eng.run(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+    L = off.size - 1
+    assert res.pi_net.shape == (L, T) and np.all(np.isfinite(res.pi_net)) and np.all(res.pi_net[:, 0] == 0.0)
+    assert np.array_equal(res.argmax_t, np.argmax(res.pi_net, axis=1))
+    assert np.array_equal(res.max_pi, np.max(res.pi_net, axis=1))
+    assert np.array_equal(res.argmax_epoch, np.argmax(res.integral, axis=1))
+    assert np.array_equal(res.pi_times, res.pi_net[:, synthetic.TIMES])
+    sizes = off[1:] - off[:-1]
+    t = np.arange(T)[:, None]
+    for l in (0, int(np.argmax(sizes)), int(np.argmin(sizes)), L // 2, L - 1):
+        lam = rates[off[l]:off[l + 1]]
+        assert rel(res.pi_net[l], np.sum(16 * lam**2 * t * np.exp(-4 * lam * t), axis=1)) < RTOL
+        si, se, _ = capi.epochs(lam, synthetic.EPOCHS)
+        assert rel(res.integral[l], si) < RTOL
+        np.testing.assert_allclose(res.abserr[l], se, rtol=ERR_RTOL, atol=1e-300)
+    # a checksum of checksums: the sum over loci of the integrals equals the integral of all sites as one locus
+    one = eng.run(np.array([0, rates.size], dtype=np.int64), rates, T, synthetic.TIMES, synthetic.EPOCHS, want_profile=False)
+    assert rel(one.integral[0], res.integral.sum(axis=0)) < 1e-11
+    assert one.n_finite[0] == res.n_finite.sum()
