@@ -150,7 +150,7 @@ class ClockSampler:
         load = [x for x in self.sm if x >= 0.6 * hi]    # "under load": within 60 % of the busiest clock seen
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": self.smax,
                 "reasons": sorted(k for k, bit in self.REASONS.items() if self.mask & bit),
-                "samples": len(self.sm), "source": "NVML, %.0f ms period, sampled over the timed loops" % (self.period * 1e3)}
+                "samples": len(self.sm), "source": "NVML, %.0f ms period, sampled over the attribution, timed and end-to-end loops" % (self.period * 1e3)}
 
 
 def profile_traffic(workload):
@@ -312,6 +312,11 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident timing ----
     eng.upload(offsets, rates, T, times, epochs, want_profile=True)
+    # clocks and throttle reasons are sampled (NVML, 1 ms period) from here to the end of the end-to-end loop: the
+    # attribution pass, the timed steps and the e2e steps all run the same kernels under load
+    sampler = ClockSampler(local_rank, period_s=0.001)
+    if rank == 0:
+        sampler.start()
     # (1) attribution pass: kernels serialised on one stream so that per-kernel CUDA-event times are exact
     eng.set_serial_kernels(True)
     for _ in range(max(args.warmup, 3)):
@@ -327,9 +332,6 @@ def run_ours(args, rank, world, local_rank):
         eng.compute()
         if gather:
             gather()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     dev_ms, gather_ms, launches = 0.0, 0.0, 0
     for _ in range(args.steps):
@@ -436,6 +438,11 @@ def run_ours(args, rank, world, local_rank):
                            "the load)" % (evals_active, evals_rank),
             "active_site_fraction": n_active / max(nnz, 1),
             "quad_kernel": {"ms": quad_ms / args.steps, "site_epochs_per_s": nnz * len(epochs) / (quad_ms / args.steps * 1e-3)},
+            # the same evals/s against the ceiling of the reference's formulation, one FP64 exp per
+            # (site, timepoint): ~17 pipe operations for a branch-free exp + 3 for a*t*e, on the same measured pipe
+            "naive_one_exp_per_eval": {"ops_per_eval": 20, "ceiling_evals_per_s": peak_tf * 1e12 / 2.0 / 20.0,
+                                       "value_over_ceiling": (evals_rank / (step_ms * 1e-3)) / (peak_tf * 1e12 / 2.0 / 20.0)
+                                       if peak_tf else None},
             "hbm": {"achieved_gbs": 8.0 * nnz / prof_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src,
                     "note": "rate stream, 8 B per site per time tile"},
         },
