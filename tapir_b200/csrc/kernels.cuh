@@ -2,8 +2,14 @@
 //
 //   profile_kernel<RH>   pi_net[l,t] = t * sum_i a_i q_i^t           (compute.py:46-48 + nansum,
 //                        with a_i = 16 r_i^2, q_i = exp(-4 r_i)        bin/tapir_compute.py:119)
-//   quad_kernel          per-site GK21 / QAGS over every epoch       (compute.py:50-52, 81-94)
+//   quad_kernel<NE>      first GK21 panel of every (site, epoch)     (compute.py:50-52, 81-94)
+//   quad_fix_kernel      full QAGS for the sites QAGS would bisect   (scipy.integrate.quad = QUADPACK dqagse)
 //   finalize_kernel      per-locus reductions, --times picks, maxima (compute.py:76-79, README.rst:178-185)
+//   rank_kernel, epoch_count_kernel   top-N loci per interval, loci per max-PI epoch
+//                                     (bin/tapir_compare.py:93-101, README.rst:178-185)
+//   push_small_kernel    multi-GPU: small result block -> rank 0's buffer over NVLink (peer stores)
+//   pi_matrix_kernel, site_integrals_kernel, nansum_rows_kernel   element-wise parity with tapir.compute
+//   fp64_peak_kernel     measurement: FP64 FMA peak of the device
 //
 // The profile is evaluated as a blocked Vandermonde product instead of one exp per
 // (site, time): with t = T0 + hi*32 + lo,
