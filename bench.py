@@ -229,6 +229,55 @@ def workload_name(w):
         w, c["n_loci"], c["mean_sites"], c["smin"], c["smax"], c["T"])
 
 
+def host_side_rates(rates_np, off_np, T, times, epochs, out, n_files=512, n_db=256):
+    """JSON ingest and the sqlite sink are outside the timed region and reported separately.
+    Bounded samples: n_files rate files of this workload's shape parsed by the library's C++ reader (and by
+    json.load for comparison); n_db loci of this step's results written with the bulk sqlite writer."""
+    import json as _json
+    import shutil
+    import tempfile
+    from tapir_b200 import compute, db, ingest
+    from tapir_b200.engine import BatchResult
+    d = tempfile.mkdtemp(prefix="tapir_bench_")
+    try:
+        n_files = min(n_files, off_np.size - 1)
+        paths = []
+        for l in range(n_files):
+            lam = rates_np[off_np[l]:off_np[l + 1]]
+            doc = {"sites": {"rates": [{"site": k + 1, "subst": 0.0, "rate": float(v), "ll": 0.0} for k, v in enumerate(lam)]}}
+            p = os.path.join(d, "locus-%d.rates" % l)
+            with open(p, "w") as fh:
+                _json.dump(doc, fh)
+            paths.append(p)
+        t0 = time.perf_counter()
+        off_i, r_i = ingest.read_rate_files(paths, correction=1, pinned=False)
+        t_native = time.perf_counter() - t0
+        ok = bool(np.array_equal(r_i, rates_np[:off_np[n_files]], equal_nan=True))
+        n_py = min(64, n_files)
+        t0 = time.perf_counter()
+        for p in paths[:n_py]:
+            compute.parse_site_rates(p, 1, test=True)
+        t_py = (time.perf_counter() - t0) * n_files / n_py
+        n_db = min(n_db, out.integral.shape[0])
+        sub = BatchResult(pi_net=np.array(out.pi_net[:n_db]), pi_times=np.array(out.pi_times[:n_db]),
+                          integral=np.array(out.integral[:n_db]), abserr=np.array(out.abserr[:n_db]), max_pi=None,
+                          argmax_t=None, argmax_epoch=None, mean_rate=None, n_finite=None, n_multi_panel=None)
+        conn, c = db.create_probe_db(os.path.join(d, "pi.sqlite"))
+        t0 = time.perf_counter()
+        db.insert_batch(conn, c, ["locus-%d.rates" % l for l in range(n_db)], sub, times, epochs)
+        conn.commit()
+        t_db = time.perf_counter() - t0
+        conn.close()
+        rows = n_db * (1 + T + len(times) + len(epochs))
+        return {"ingest_files": n_files, "ingest_native_files_per_s": n_files / t_native, "ingest_native_matches": ok,
+                "ingest_json_load_files_per_s": n_files / t_py, "sqlite_loci": n_db, "sqlite_rows_per_s": rows / t_db,
+                "sqlite_loci_per_s": n_db / t_db,
+                "note": "host side of the drop-in, outside the timed region: tapir_ingest_rates (C++ threads) vs json.load "
+                        "per file; bulk executemany writer with the reference's schema incl. the T-rows-per-locus net table"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_ours(args, rank, world, local_rank):
     from tapir_b200 import synthetic
     from tapir_b200 import sharded
@@ -457,6 +506,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if world == 1 and not args.no_host_side:
+        line["host_side"] = host_side_rates(rates_np, off_np, T, times, epochs, out)
     print(json.dumps(line))
 
 
@@ -468,6 +519,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-side", action="store_true", help="skip the (untimed) ingest / sqlite sample")
     ap.add_argument("--gather", default="push", choices=["push", "nccl"], help="N > 1: how per-locus vectors reach rank 0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
