@@ -104,6 +104,8 @@ struct Lane {
     cudaStream_t stream_q = nullptr;  // epoch-integral kernels, concurrent with the profile kernel
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;  // staged path: the captured launch sequence of the resident batch
+    int graph_launches = 0;
     Plan plan;
     // inputs: the rate stream, and ONE buffer holding every work list (a single H2D copy per batch)
     DevBuf d_rates, d_work, d_counter;
@@ -127,6 +129,7 @@ struct tapir_cuda_ctx {
     int device = 0;
     int sm_count = 148;
     int serial_kernels = 0;  // 1: profile and integral kernels on one stream (per-kernel timing is then exact)
+    int use_graphs = 1;      // staged path replays a captured CUDA graph (TAPIR_CUDA_GRAPHS=0 disables)
     std::string last_error;
     Lane lanes[kLanes];
     cudaStream_t stream = nullptr;  // == lanes[0].stream; used by the element-wise / measurement entry points
@@ -357,6 +360,8 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
     {
         const char* env = getenv("TAPIR_CUDA_SERIAL_KERNELS");
         ctx->serial_kernels = (env && env[0] == '1') ? 1 : 0;
+        env = getenv("TAPIR_CUDA_GRAPHS");
+        ctx->use_graphs = (env && env[0] == '0') ? 0 : 1;
     }
     e = cudaSuccess;
     for (Lane& ln : ctx->lanes) {
@@ -389,6 +394,7 @@ int tapir_cuda_destroy(tapir_cuda_ctx* ctx)
         ln.h_small.release();
         for (auto& ev : ln.ev)
             if (ev) cudaEventDestroy(ev);
+        if (ln.graph_exec) cudaGraphExecDestroy(ln.graph_exec);
         if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
         if (ln.ev_join) cudaEventDestroy(ln.ev_join);
         if (ln.stream) cudaStreamDestroy(ln.stream);
@@ -432,10 +438,18 @@ int tapir_cuda_host_free(void* ptr)
 
 namespace {
 
+void drop_graph(Lane& ln)
+{
+    if (ln.graph_exec) cudaGraphExecDestroy(ln.graph_exec);
+    ln.graph_exec = nullptr;
+    ln.graph_launches = 0;
+}
+
 // Build the work lists of loci [l0, l1) of an already validated problem on lane `ln` and start their H2D copies.
 int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l0, int64_t l1, bool sync)
 {
     ln.plan.valid = false;
+    drop_graph(ln);
     Plan& plan = ln.plan;
     const int64_t* off = &p->offsets[l0];       // off[0..L]; site indices are taken relative to off[0]
     const int64_t base = (l1 > l0) ? off[0] : 0;
@@ -581,17 +595,15 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     return TAPIR_OK;
 }
 
-// Launch the kernels of the lane's resident batch.  Unless ctx->serial_kernels is set, the epoch-integral
-// kernels run on the lane's second stream, concurrently with the profile kernel, and join before finalize.
-int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
+// Enqueue the kernels of the lane's resident batch on its stream(s).  Unless ctx->serial_kernels is set, the
+// epoch-integral kernels go to the lane's second stream, concurrently with the profile kernel, and join before
+// finalize.  Also what the CUDA graph of the staged path captures.
+int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launches)
 {
     Plan& plan = ln.plan;
-    if (!plan.valid) return fail(ctx, TAPIR_E_STATE, "tapir_cuda_compute called before a successful tapir_cuda_upload");
     cudaStream_t st = ln.stream;
     const bool fork = !ctx->serial_kernels && plan.L > 0 && plan.n_quad_items > 0 && plan.n_prof_items > 0 && plan.T > 0;
     cudaStream_t sq = fork ? ln.stream_q : st;
-    int launches = 0;
-    if (timing) CU(ctx, cudaEventRecord(ln.ev[0], st));
     if (plan.L > 0) {
         CU(ctx, cudaMemsetAsync(ln.d_counter.p, 0, 256, st));
         if (fork) {
@@ -621,7 +633,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
             CU(ctx, e);
             ++launches;
         }
-        if (timing) CU(ctx, cudaEventRecord(ln.ev[1], st));
+        if (inner_events) CU(ctx, cudaEventRecord(ln.ev[1], st));
         if (plan.n_quad_items > 0) {
             QuadArgs qa;
             qa.rates = ln.d_rates.as<double>();
@@ -659,7 +671,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
             CU(ctx, cudaEventRecord(ln.ev_join, sq));
             CU(ctx, cudaStreamWaitEvent(st, ln.ev_join, 0));
         }
-        if (timing) CU(ctx, cudaEventRecord(ln.ev[2], st));
+        if (inner_events) CU(ctx, cudaEventRecord(ln.ev[2], st));
         {
             FinalArgs fa;
             fa.n_loci = plan.L;
@@ -692,8 +704,8 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
             ++launches;
         }
     } else {
-        if (timing) CU(ctx, cudaEventRecord(ln.ev[1], st));
-        if (timing) CU(ctx, cudaEventRecord(ln.ev[2], st));
+        if (inner_events) CU(ctx, cudaEventRecord(ln.ev[1], st));
+        if (inner_events) CU(ctx, cudaEventRecord(ln.ev[2], st));
     }
     if (ctx->gather_slot_ptr && plan.L > 0) {
         // NVLink push: the batch's small block goes into this rank's slot of the owner's buffer (peer memory),
@@ -720,14 +732,54 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync)
         CU(ctx, cudaGetLastError());
         ++launches;
     }
+    return TAPIR_OK;
+}
+
+// Run the kernels of the lane's resident batch.  The staged path (tapir_cuda_compute) repeats the same launch
+// sequence on the same buffers for as long as the batch stays resident, so it is captured once into a CUDA graph
+// (memset, fork, profile || integrals + fix-up, join, finalize, gather push) and replayed with a single launch.
+int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync, bool graph_ok)
+{
+    Plan& plan = ln.plan;
+    if (!plan.valid) return fail(ctx, TAPIR_E_STATE, "tapir_cuda_compute called before a successful tapir_cuda_upload");
+    cudaStream_t st = ln.stream;
+    const bool use_graph = graph_ok && ctx->use_graphs && !ctx->serial_kernels && plan.L > 0;
+    int launches = 0;
+    if (timing) CU(ctx, cudaEventRecord(ln.ev[0], st));
+    if (use_graph) {
+        if (!ln.graph_exec) {
+            CU(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+            int n = 0;
+            const int rc = enqueue_kernels(ctx, ln, false, n);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc != TAPIR_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                return rc;
+            }
+            CU(ctx, e);
+            const cudaError_t ei = cudaGraphInstantiate(&ln.graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            CU(ctx, ei);
+            ln.graph_launches = n;
+        }
+        CU(ctx, cudaGraphLaunch(ln.graph_exec, st));
+        launches = ln.graph_launches;
+    } else {
+        const int rc = enqueue_kernels(ctx, ln, timing != nullptr, launches);
+        if (rc != TAPIR_OK) return rc;
+    }
     if (timing) CU(ctx, cudaEventRecord(ln.ev[3], st));
     if (sync || timing) CU(ctx, cudaStreamSynchronize(st));
     if (timing) {
         memset(timing, 0, sizeof *timing);
         CU(ctx, cudaEventElapsedTime(&timing->total_ms, ln.ev[0], ln.ev[3]));
-        CU(ctx, cudaEventElapsedTime(&timing->profile_ms, ln.ev[0], ln.ev[1]));
-        CU(ctx, cudaEventElapsedTime(&timing->quad_ms, ln.ev[1], ln.ev[2]));
-        CU(ctx, cudaEventElapsedTime(&timing->finalize_ms, ln.ev[2], ln.ev[3]));
+        if (!use_graph) {  // the per-kernel events are not part of the captured graph
+            CU(ctx, cudaEventElapsedTime(&timing->profile_ms, ln.ev[0], ln.ev[1]));
+            CU(ctx, cudaEventElapsedTime(&timing->quad_ms, ln.ev[1], ln.ev[2]));
+            CU(ctx, cudaEventElapsedTime(&timing->finalize_ms, ln.ev[2], ln.ev[3]));
+        }
         timing->launches = launches;
     }
     return TAPIR_OK;
@@ -855,6 +907,7 @@ int tapir_cuda_gather_detach(tapir_cuda_ctx* ctx)
     if (ctx->gather_mapped) cudaIpcCloseMemHandle(ctx->gather_mapped);
     ctx->gather_mapped = nullptr;
     ctx->gather_slot_ptr = nullptr;
+    for (Lane& ln : ctx->lanes) drop_graph(ln);
     ctx->gather_slot_bytes = ctx->gather_total_bytes = 0;
     ctx->d_gather.release();
     cudaGetLastError();
@@ -900,6 +953,7 @@ int tapir_cuda_gather_attach(tapir_cuda_ctx* ctx, const void* handle, size_t slo
     }
     ctx->gather_slot_ptr = base + slot_bytes * size_t(slot);
     ctx->gather_slot_bytes = slot_bytes;
+    for (Lane& ln : ctx->lanes) drop_graph(ln);  // the push kernel joins the captured sequence
     return TAPIR_OK;
 }
 
@@ -943,7 +997,7 @@ int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
 {
     int rc = bind(ctx);
     if (rc) return rc;
-    return lane_compute(ctx, ctx->lanes[0], timing, true);
+    return lane_compute(ctx, ctx->lanes[0], timing, true, true);
 }
 
 int tapir_cuda_download(tapir_cuda_ctx* ctx, const tapir_results* out)
@@ -993,7 +1047,7 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
         if (k >= kLanes && (rc = lane_finish(ctx, ln)) != TAPIR_OK) break;  // its previous chunk (and its staging) is done
         if ((rc = lane_upload(ctx, ln, p, l0, l1, false)) != TAPIR_OK) break;
         ln.pending_row0 = l0;
-        if ((rc = lane_compute(ctx, ln, nullptr, false)) != TAPIR_OK) break;
+        if ((rc = lane_compute(ctx, ln, nullptr, false, false)) != TAPIR_OK) break;
         if ((rc = lane_download(ctx, ln, host_out, l0, false)) != TAPIR_OK) break;
         l0 = l1;
     }
