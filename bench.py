@@ -472,6 +472,9 @@ def run_ours(args, rank, world, local_rank):
                        world, "NVLink peer-memory push fused after finalize (CUDA IPC)" if gather_mode == "push"
                        else "one NCCL gather per step")) if world > 1 else "single GPU"},
         "loci_per_s": total_loci / (step_ms * 1e-3),
+        # the same step counted over the sites that need arithmetic only (non-zero finite rate): `value` follows the
+        # metric's definition (every site*timepoint of the input), this one is what the FP64 pipe actually evaluates
+        "active_evals_per_s": evals_active * world / (step_ms * 1e-3),
         "kernel_ms": {"profile": prof_ms / args.steps, "quad": quad_ms / args.steps, "finalize": fin_ms / args.steps,
                       "serialised_step": serial_ms / args.steps, "gather": gather_ms / args.steps,
                       "note": "per-kernel times from a separate pass with the kernels serialised on one stream; "
