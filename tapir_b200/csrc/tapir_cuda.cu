@@ -104,6 +104,7 @@ struct Lane {
     cudaStream_t stream_q = nullptr;  // epoch-integral kernels, concurrent with the profile kernel
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;  // upload landed / kernels done / download landed
     cudaGraphExec_t graph_exec = nullptr;  // staged path: the captured launch sequence of the resident batch
     int graph_launches = 0;
     Plan plan;
@@ -133,6 +134,10 @@ struct tapir_cuda_ctx {
     std::string last_error;
     Lane lanes[kLanes];
     cudaStream_t stream = nullptr;  // == lanes[0].stream; used by the element-wise / measurement entry points
+    // every batch copy goes through ONE host-to-device and ONE device-to-host stream: copies of one direction are
+    // serial on the link anyway, and a lane stream that alternates directions was seen to queue its next upload
+    // behind other lanes' pending downloads (uploads then waited ~200 us for the download engine)
+    cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     DevBuf d_scratch_a, d_scratch_b, d_scratch_c, d_flush, d_counter;
     uint64_t bytes_h2d = 0, bytes_d2h = 0;
@@ -370,8 +375,13 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ln.ev[i]);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_out, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming);
     }
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking);
     ctx->stream = ctx->lanes[0].stream;
     if (e != cudaSuccess) {
         tapir_cuda_destroy(ctx);
@@ -397,9 +407,14 @@ int tapir_cuda_destroy(tapir_cuda_ctx* ctx)
         if (ln.graph_exec) cudaGraphExecDestroy(ln.graph_exec);
         if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
         if (ln.ev_join) cudaEventDestroy(ln.ev_join);
+        if (ln.ev_in) cudaEventDestroy(ln.ev_in);
+        if (ln.ev_out) cudaEventDestroy(ln.ev_out);
+        if (ln.ev_done) cudaEventDestroy(ln.ev_done);
         if (ln.stream) cudaStreamDestroy(ln.stream);
         if (ln.stream_q) cudaStreamDestroy(ln.stream_q);
     }
+    if (ctx->stream_h2d) { cudaStreamSynchronize(ctx->stream_h2d); cudaStreamDestroy(ctx->stream_h2d); }
+    if (ctx->stream_d2h) { cudaStreamSynchronize(ctx->stream_d2h); cudaStreamDestroy(ctx->stream_d2h); }
     if (ctx->gather_mapped) cudaIpcCloseMemHandle(ctx->gather_mapped);
     DevBuf* bufs[] = {&ctx->d_scratch_a, &ctx->d_scratch_b, &ctx->d_scratch_c, &ctx->d_flush, &ctx->d_counter, &ctx->d_gather};
     for (DevBuf* b : bufs) b->release();
@@ -586,10 +601,12 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
         for (int i = 0; i < 9; ++i) views[i]->p = r + plan.small_off[i];
     }
 
-    cudaStream_t st = ln.stream;
+    cudaStream_t st = ctx->stream_h2d;
     ctx->bytes_h2d += size_t(plan.nnz) * 8 + total;
     if (plan.nnz) CU(ctx, cudaMemcpyAsync(ln.d_rates.p, p->rates + base, size_t(plan.nnz) * 8, cudaMemcpyHostToDevice, st));
     CU(ctx, cudaMemcpyAsync(ln.d_work.p, hs, total, cudaMemcpyHostToDevice, st));
+    CU(ctx, cudaEventRecord(ln.ev_in, st));
+    CU(ctx, cudaStreamWaitEvent(ln.stream, ln.ev_in, 0));  // the lane's kernels start when its inputs have landed
     if (sync) CU(ctx, cudaStreamSynchronize(st));
     plan.valid = true;
     return TAPIR_OK;
@@ -790,6 +807,7 @@ int lane_finish(tapir_cuda_ctx* ctx, Lane& ln)
 {
     CU(ctx, cudaStreamSynchronize(ln.stream));
     if (!ln.pending) return TAPIR_OK;
+    CU(ctx, cudaEventSynchronize(ln.ev_out));  // this lane's downloads (recorded on the download stream)
     ln.pending = false;
     const Plan& plan = ln.plan;
     const tapir_results& out = ln.pending_out;
@@ -811,7 +829,9 @@ int lane_download(tapir_cuda_ctx* ctx, Lane& ln, const tapir_results* out, int64
     const Plan& plan = ln.plan;
     if (!plan.valid) return fail(ctx, TAPIR_E_STATE, "tapir_cuda_download called before upload/compute");
     if (!out) return fail(ctx, TAPIR_E_INVALID, "null results");
-    cudaStream_t st = ln.stream;
+    cudaStream_t st = ctx->stream_d2h;
+    CU(ctx, cudaEventRecord(ln.ev_done, ln.stream));  // after the lane's kernels
+    CU(ctx, cudaStreamWaitEvent(st, ln.ev_done, 0));
     const size_t L = size_t(plan.L);
     if ((plan.flags & TAPIR_WANT_PROFILE) && out->pi_net && L * size_t(plan.T)) {
         const size_t row = size_t(plan.T) * 8;
@@ -823,6 +843,7 @@ int lane_download(tapir_cuda_ctx* ctx, Lane& ln, const tapir_results* out, int64
         ctx->bytes_d2h += plan.small_bytes;
         CU(ctx, cudaMemcpyAsync(ln.h_small.p, ln.d_small.p, plan.small_bytes, cudaMemcpyDeviceToHost, st));
     }
+    CU(ctx, cudaEventRecord(ln.ev_out, st));
     ln.pending_out = *out;
     ln.pending_row0 = l0;
     ln.pending = true;
