@@ -285,14 +285,18 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
             const int64_t row = int64_t(item.locus) * args.T;
             double* out = args.pi_net + row;
             const bool vec_ok = ((row & 1) == 0);
-            double best = -1.0;  // pi_net >= 0 always; first max wins
-            int best_i = 0;      // offset within the tile
+            // Tile maximum: the values are >= 0, so their bit patterns order like the values and the comparisons
+            // run on the integer pipe instead of the FP64 pipe the other warps' MMAs are using.  A lane visits
+            // its offsets in increasing order (c outer, j inner: w_chunk(2 fk) < w_chunk(2 fk + 1)), so a strict
+            // comparison keeps the first maximum, as numpy.argmax does.
+            long long best_bits = -1;
+            int best_i = 0;  // offset within the tile
             const int64_t t_left = args.T - T0;
             const int t_end = int(t_left < int64_t(TT) ? t_left : int64_t(TT));  // valid offsets of this tile
 #pragma unroll
-            for (int j = 0; j < RH; ++j)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int j = 0; j < RH; ++j) {
                     const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
                     const int o = hi * 32 + lo0;
                     const double td = t0d + double(o);  // exact: integers far below 2^53
@@ -311,19 +315,22 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                             if (o + i < t_end) dst[i] = v[i];
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (o + i < t_end && (v[i] > best || (v[i] == best && o + i < best_i))) {
-                            best = v[i];
+                    for (int i = 0; i < 4; ++i) {
+                        const long long bits = __double_as_longlong(v[i]);
+                        if (o + i < t_end && bits > best_bits) {
+                            best_bits = bits;
                             best_i = o + i;
                         }
+                    }
                 }
             int64_t best_t = T0 + best_i;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const long long ob = __shfl_xor_sync(0xffffffffu, best_bits, off);
                 const int64_t ot = __shfl_xor_sync(0xffffffffu, best_t, off);
-                if (ob > best || (ob == best && ot < best_t)) { best = ob; best_t = ot; }
+                if (ob > best_bits || (ob == best_bits && ot < best_t)) { best_bits = ob; best_t = ot; }
             }
+            const double best = __longlong_as_double(best_bits);
             if (lane == 0) {
                 const int64_t k = int64_t(item.locus) * args.n_tiles + item.tile;
                 args.tile_max[k] = best;
