@@ -14,6 +14,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "kernels.cuh"
 
@@ -105,6 +106,8 @@ struct Lane {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;  // upload landed / kernels done / download landed
+    cudaEvent_t ev_dstart = nullptr;   // trace only: the download stream has reached this lane's copies
+    double host_us[4] = {0, 0, 0, 0};  // trace only: host clock when upload / compute / download were enqueued
     cudaGraphExec_t graph_exec = nullptr;  // staged path: the captured launch sequence of the resident batch
     int graph_launches = 0;
     Plan plan;
@@ -124,13 +127,17 @@ struct Lane {
     DevBuf* all_bufs[10] = {&d_rates, &d_work, &d_counter, &d_ws, &d_tile_max, &d_tile_arg, &d_qpart, &d_fix, &d_pi_net, &d_small};
 };
 
-constexpr int kLanes = 3;
+constexpr int kLanes = 8;  // upper bound; ctx->n_lanes of them rotate (TAPIR_CUDA_LANES)
 
 struct tapir_cuda_ctx {
     int device = 0;
     int sm_count = 148;
     int serial_kernels = 0;  // 1: profile and integral kernels on one stream (per-kernel timing is then exact)
     int use_graphs = 1;      // staged path replays a captured CUDA graph (TAPIR_CUDA_GRAPHS=0 disables)
+    int n_lanes = 6;         // lanes the chunks of tapir_cuda_run rotate over
+    int ramp = 1;            // tapir_cuda_run starts with two short chunks so the first download begins early
+    int prof_ws = 0;         // profile kernel variant: TAPIR_PROF_WS=1 = warp-specialised (measured slower: DESIGN 3.1)
+    int trace = 0;           // TAPIR_CUDA_TRACE=1: tapir_cuda_run prints the timeline of its chunks to stderr
     std::string last_error;
     Lane lanes[kLanes];
     cudaStream_t stream = nullptr;  // == lanes[0].stream; used by the element-wise / measurement entry points
@@ -176,6 +183,11 @@ int fail(tapir_cuda_ctx* ctx, int code, const char* fmt, ...)
         }                                                                                                  \
     } while (0)
 
+double now_us()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int bind(tapir_cuda_ctx* ctx)
 {
     if (!ctx) return fail(nullptr, TAPIR_E_INVALID, "null context");
@@ -206,8 +218,22 @@ int choose_rh(int64_t T)
 template <int RH>
 cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, int64_t n_items)
 {
-    using Cfg = ProfCfg<RH>;
     static bool configured[64] = {false};
+    if (ctx->prof_ws) {
+        // warp-specialised variant: one CTA per SM, four consumer warps fed by eight producer warps
+        using Cfg = WsCfg<RH>;
+        if (!configured[ctx->device & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(profile_ws_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 int(Cfg::SmemBytes));
+            if (e != cudaSuccess) return e;
+            configured[ctx->device & 63] = true;
+        }
+        int64_t grid = std::min<int64_t>(ctx->sm_count, (n_items + kWsLanes - 1) / kWsLanes);
+        if (grid < 1) grid = 1;
+        profile_ws_kernel<RH><<<unsigned(grid), Cfg::Threads, Cfg::SmemBytes, ln.stream>>>(pa);
+        return cudaGetLastError();
+    }
+    using Cfg = ProfCfg<RH>;
     if (!configured[ctx->device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(profile_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              int(Cfg::SmemBytes));
@@ -367,6 +393,10 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         ctx->serial_kernels = (env && env[0] == '1') ? 1 : 0;
         env = getenv("TAPIR_CUDA_GRAPHS");
         ctx->use_graphs = (env && env[0] == '0') ? 0 : 1;
+        if ((env = getenv("TAPIR_CUDA_LANES"))) ctx->n_lanes = std::max(1, std::min(kLanes, atoi(env)));
+        if ((env = getenv("TAPIR_CUDA_RAMP"))) ctx->ramp = atoi(env) != 0;
+        if ((env = getenv("TAPIR_CUDA_TRACE"))) ctx->trace = atoi(env) != 0;
+        if ((env = getenv("TAPIR_PROF_WS"))) ctx->prof_ws = atoi(env) != 0;
     }
     e = cudaSuccess;
     for (Lane& ln : ctx->lanes) {
@@ -375,9 +405,11 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ln.ev[i]);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_join, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_out, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming);
+        const unsigned evf = ctx->trace ? cudaEventDefault : cudaEventDisableTiming;
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_in, evf);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_out, evf);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_done, evf);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ln.ev_dstart, evf);
     }
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking);
@@ -410,6 +442,7 @@ int tapir_cuda_destroy(tapir_cuda_ctx* ctx)
         if (ln.ev_in) cudaEventDestroy(ln.ev_in);
         if (ln.ev_out) cudaEventDestroy(ln.ev_out);
         if (ln.ev_done) cudaEventDestroy(ln.ev_done);
+        if (ln.ev_dstart) cudaEventDestroy(ln.ev_dstart);
         if (ln.stream) cudaStreamDestroy(ln.stream);
         if (ln.stream_q) cudaStreamDestroy(ln.stream_q);
     }
@@ -640,6 +673,8 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
             pa.T = plan.T;
             pa.n_items = int32_t(plan.n_prof_items);
             pa.n_tiles = plan.n_tiles;
+            pa.debug = 0;
+            if (const char* env = getenv("TAPIR_PROF_DEBUG")) pa.debug = atoi(env);
             cudaError_t e = cudaSuccess;
             switch (plan.rh) {
                 case 1: e = launch_profile<1>(ctx, ln, pa, plan.n_prof_items); break;
@@ -832,6 +867,7 @@ int lane_download(tapir_cuda_ctx* ctx, Lane& ln, const tapir_results* out, int64
     cudaStream_t st = ctx->stream_d2h;
     CU(ctx, cudaEventRecord(ln.ev_done, ln.stream));  // after the lane's kernels
     CU(ctx, cudaStreamWaitEvent(st, ln.ev_done, 0));
+    if (ctx->trace) CU(ctx, cudaEventRecord(ln.ev_dstart, st));
     const size_t L = size_t(plan.L);
     if ((plan.flags & TAPIR_WANT_PROFILE) && out->pi_net && L * size_t(plan.T)) {
         const size_t row = size_t(plan.T) * 8;
@@ -1041,7 +1077,12 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
     const int64_t L = p->n_loci;
     const int64_t nnz = L ? p->offsets[L] : 0;
     const double bytes = double(nnz) * 8.0 + ((p->flags & TAPIR_WANT_PROFILE) ? double(L) * double(p->n_grid) * 8.0 : 0.0);
-    int64_t n_chunks = int64_t(bytes / double(8 << 20));
+    double chunk_bytes = double(8 << 20);
+    if (const char* env = getenv("TAPIR_CUDA_CHUNK_MB")) {  // tuning override
+        const double v = atof(env);
+        if (v > 0.0) chunk_bytes = v * double(1 << 20);
+    }
+    int64_t n_chunks = int64_t(bytes / chunk_bytes);
     n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, 16));
     if (L < 64 * n_chunks) n_chunks = 1;  // few (possibly huge) loci: one pass, split over sites instead
     if (ctx->gather_slot_ptr) {  // where each chunk's rows go inside the full batch's small-block layout
@@ -1054,27 +1095,63 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
         }
         ctx->gather_chunked = true;
     }
+    // Chunk boundaries at cumulative shares of the sites.  Nothing flows back to the host before the first chunk
+    // has been uploaded and computed, so the run opens with a quarter- and a half-size chunk.
+    std::vector<int64_t> cut;  // site count at which chunk k ends
+    {
+        const int64_t per = nnz / n_chunks;
+        int64_t done = 0;
+        if (ctx->ramp && n_chunks >= 4 && L >= 256 * n_chunks) {
+            cut.push_back(done += per / 4);
+            cut.push_back(done += per / 2);
+        }
+        while (nnz - done > per + per / 2) cut.push_back(done += per);
+        cut.push_back(nnz);
+    }
+    n_chunks = int64_t(cut.size());
+    const int n_lanes = ctx->n_lanes;
+    const double t_host0 = now_us();
+    if (ctx->trace) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream_h2d));
     int64_t l0 = 0;
-    for (int64_t k = 0; k < n_chunks; ++k) {
-        // chunk boundaries at equal shares of the sites
+    for (int64_t k = 0; k < n_chunks && l0 < L; ++k) {
         int64_t l1 = L;
         if (k + 1 < n_chunks) {
-            const int64_t want = nnz / n_chunks * (k + 1);
-            l1 = std::lower_bound(p->offsets + l0, p->offsets + L, want) - p->offsets;
+            l1 = std::lower_bound(p->offsets + l0, p->offsets + L, cut[k]) - p->offsets;
             l1 = std::max(l1, l0 + 1);
-            l1 = std::min(l1, L - (n_chunks - 1 - k));
+            l1 = std::min(l1, L);
         }
-        Lane& ln = ctx->lanes[k % kLanes];
-        if (k >= kLanes && (rc = lane_finish(ctx, ln)) != TAPIR_OK) break;  // its previous chunk (and its staging) is done
+        Lane& ln = ctx->lanes[k % n_lanes];
+        if (k >= n_lanes && (rc = lane_finish(ctx, ln)) != TAPIR_OK) break;  // its previous chunk (and its staging) is done
+        if (ctx->trace) ln.host_us[0] = now_us() - t_host0;
         if ((rc = lane_upload(ctx, ln, p, l0, l1, false)) != TAPIR_OK) break;
         ln.pending_row0 = l0;
+        if (ctx->trace) ln.host_us[1] = now_us() - t_host0;
         if ((rc = lane_compute(ctx, ln, nullptr, false, false)) != TAPIR_OK) break;
+        if (ctx->trace) ln.host_us[2] = now_us() - t_host0;
         if ((rc = lane_download(ctx, ln, host_out, l0, false)) != TAPIR_OK) break;
+        if (ctx->trace) ln.host_us[3] = now_us() - t_host0;
         l0 = l1;
     }
     for (Lane& ln : ctx->lanes) {
         const int rc2 = lane_finish(ctx, ln);
         if (rc == TAPIR_OK) rc = rc2;
+    }
+    if (ctx->trace && rc == TAPIR_OK) {
+        // chunk k ran on lane k % n_lanes; with at least as many lanes as chunks every lane still holds its chunk's events
+        fprintf(stderr, "[tapir trace] %lld chunks on %d lanes, host done at %.0f us\n", (long long)n_chunks, n_lanes, now_us() - t_host0);
+        fprintf(stderr, "[tapir trace] chunk  loci   host: upload compute download enq'd |  device: H2D landed, kernels done, D2H start, D2H done (us)\n");
+        for (int64_t k = 0; k < std::min<int64_t>(n_chunks, n_lanes); ++k) {
+            Lane& ln = ctx->lanes[k];
+            float t[4] = {0, 0, 0, 0};
+            cudaEventElapsedTime(&t[0], ctx->ev[0], ln.ev_in);
+            cudaEventElapsedTime(&t[1], ctx->ev[0], ln.ev_done);
+            cudaEventElapsedTime(&t[2], ctx->ev[0], ln.ev_dstart);
+            cudaEventElapsedTime(&t[3], ctx->ev[0], ln.ev_out);
+            fprintf(stderr, "[tapir trace] %5lld %5lld   %6.0f %6.0f %6.0f %6.0f | %7.0f %7.0f %7.0f %7.0f\n", (long long)k,
+                    (long long)ln.plan.L, ln.host_us[0], ln.host_us[1], ln.host_us[2], ln.host_us[3], t[0] * 1e3, t[1] * 1e3,
+                    t[2] * 1e3, t[3] * 1e3);
+        }
+        cudaGetLastError();
     }
     ctx->gather_chunked = false;
     if (n_chunks > 1) ctx->lanes[0].plan.valid = false;  // the resident data is one chunk, not the batch
