@@ -76,7 +76,7 @@ struct ProfArgs {
     int64_t T;
     int32_t n_items;
     int32_t n_tiles;
-    int32_t debug;       // measurement only (TAPIR_PROF_DEBUG): 1 = consumers skip the DMMAs, 2 = producers skip the table build
+    long long* trace;    // measurement only (TAPIR_PROF_TRACE, profile_kernel<RH, true>): 32 words per warp
 };
 
 template <int RH>
@@ -121,7 +121,12 @@ __device__ __forceinline__ int w_chunk(int g)
 // ------------------------------------------------------------------------------------------
 // PI profile
 // ------------------------------------------------------------------------------------------
-template <int RH>
+// TRACE (measurement only, tools/prof_trace.py): lane 0 of every warp stamps clock64 into args.trace --
+// [0] SM id, [1] entry, [2] first item claimed, [3] first contraction, [4..11] end of item k, [12] exit, [13] items done,
+// [16 + 4 j + k], j = 0..3: groups 2..5 of the warp's second item, k = 0 group popped, 1 tables built, 2 contracted.
+// The production instantiation (TRACE = false) carries none of it: the kernel's schedule is sensitive to every
+// extra predicate (a run-time switch for the same stamps cost 8 %).
+template <int RH, bool TRACE = false>
 __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profile_kernel(const ProfArgs args)
 {
     using Cfg = ProfCfg<RH>;
@@ -138,6 +143,17 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
     // fragment sources: site row fk (+4 per k-step); lo chunk = 4 entries, hi chunk = RH entries
     const double* fragU = Us + fk * US + 4 * chunk_pair(fg);
     const double* fragW = Ws + fk * WS + RH * w_chunk<RH>(fg);
+    long long* tr = nullptr;
+    int n_done = 0, n_group = 0;
+    if constexpr (TRACE) {
+        tr = args.trace + (size_t(blockIdx.x) * kProfWarps + warp) * 32;
+        if (lane == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr[0] = smid;
+            tr[1] = clock64();
+        }
+    }
 
     for (;;) {
         uint32_t it = 0;
@@ -147,6 +163,10 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
         const ProfItem item = args.items[it];
         const int64_t T0 = int64_t(item.tile) * TT;
         const double t0d = double(T0);
+        if constexpr (TRACE) {
+            if (lane == 0 && n_done == 0) tr[2] = clock64() + (item.n_sites == -12345);
+            n_group = 0;
+        }
 
         // acc[mt][nt][c]: lo = 4*chunk_pair(fg) + mt, hi = RH*w_chunk(2*fk + c) + nt
         double acc[4][RH][2];
@@ -185,6 +205,13 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 const int cnt = min(32, qn - qh);
                 const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
                 qh += cnt;
+                int tg = -1;  // TRACE: which of the stamped groups this is
+                if constexpr (TRACE) {
+                    if (lane == 0 && n_done == 0 && n_group == 0) tr[3] = clock64() + (lam == -1.0);
+                    tg = (n_done == 1 && n_group >= 2 && n_group < 6) ? n_group - 2 : -1;
+                    ++n_group;
+                    if (tg >= 0 && lane == 0) tr[16 + 4 * tg] = clock64() + (lam == -1.0);
+                }
                 // ---- generation: this lane's site -> U[0..31], W[0..H-1] (power tables) ----
                 // rows of lanes >= cnt are U = 0, W = 1: they add exactly 0
                 {
@@ -228,6 +255,9 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                     }
                 }
                 __syncwarp();
+                if constexpr (TRACE) {
+                    if (tg >= 0 && lane == 0) tr[16 + 4 * tg + 1] = clock64();
+                }
                 // ---- contraction over the chunk's sites: acc(lo,hi) += sum_s U[s][lo] * W[s][hi] ----
                 // 4 sites per k-step; fragments of step s+1 are fetched while the MMAs of step s issue
                 {
@@ -264,6 +294,9 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                     }
                 }
                 __syncwarp();
+                if constexpr (TRACE) {
+                    if (tg >= 0 && lane == 0) tr[16 + 4 * tg + 2] = clock64() + (acc[0][0][0] == -1.0);
+                }
             }  // groups of 32 active sites
             if (!more) break;
         }
@@ -338,541 +371,14 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 args.tile_arg[k] = best_t;
             }
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// PI profile, warp-specialised
-// ------------------------------------------------------------------------------------------
-// profile_kernel's warps alternate between building the power tables (a chain of FP64 multiplies that is
-// granted one instruction per DMMA of the neighbouring warp) and contracting them; ncu's source page shows a
-// warp inside its DMMA stream only ~39 % of the time, so with three warps per SM sub-partition the FP64 pipe has
-// no DMMA stream to run for 0.61^3 = 23 % of the cycles.  Here the roles are split.  One CTA per SM holds four
-// "lanes", one per sub-partition: a CONSUMER warp that owns the accumulators and does nothing but DMMAs (plus the
-// epilogue of each item), fed through a ring of table buffers by two PRODUCER warps that claim the items, stream
-// and compact the rates and build the tables of alternate groups of 32 active sites.  Ring slots are handed over
-// with mbarriers (full / empty, CTA scope); the two producers of a lane agree on the claimed item through a
-// 64-thread named barrier.  The arithmetic, the order of the sites and therefore the results are those of
-// profile_kernel.
-constexpr int kWsLanes = 4;
-
-struct WsDesc {      // what the consumer needs to know about a ring slot
-    int32_t cnt;     // active sites in the slot's tables (0..32); < 0: no more work
-    int32_t last;    // last group of its item: run the epilogue
-    int32_t locus, tile, slot;
-    int32_t pad;
-};
-
-struct WsEpi {       // an item parked in a drained ring slot, waiting for its epilogue
-    int32_t locus, tile, slot, valid;
-};
-
-template <int NB>
-struct WsCtl {       // per lane, in shared memory
-    unsigned long long full[NB], empty[NB];
-    WsDesc desc[NB];
-    WsEpi epi[NB];
-    uint32_t item[4];  // items claimed by producer 0, for producer 1 (entry seq & 3)
-    uint32_t pub;      // number of entries published so far
-    uint32_t pad[3];
-};
-
-template <int RH>
-struct WsCfg {
-    static constexpr int WStride = ProfCfg<RH>::WStride;
-    static constexpr int BufDoubles = 32 * (kUStride + WStride);
-    static constexpr int NBuf = RH >= 8 ? 2 : 3;
-    // RH = 8 keeps 128 accumulator registers per consumer thread: one producer warp per lane (256 threads, 255
-    // registers) instead of two (384 threads, 168 registers); a group's 256 DMMAs leave it slots enough
-    static constexpr int NProd = RH >= 8 ? 1 : 2;
-    static constexpr int Threads = (1 + NProd) * kWsLanes * 32;
-    static constexpr int LaneDoubles = NBuf * BufDoubles + 2 * 64;  // ring + one active-rate queue per producer
-    static constexpr size_t SmemBytes = size_t(kWsLanes) * LaneDoubles * sizeof(double) + kWsLanes * sizeof(WsCtl<NBuf>);
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
-{
-    const uint32_t a = smem_u32(bar);
-    uint32_t done = 0;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(a), "r"(parity)
-                     : "memory");
-    } while (!done);
-}
-
-// finite, and 16 r^2 neither 0 nor Inf -- decided on the bit pattern: 16*(r*r) == 0 up to |r| = 0x1e56a09e667f3bcc
-// (1.57e-162) and is finite up to |r| = 0x5fcfffffffffffff (3.35e153); NaN and Inf compare above both
-__device__ __forceinline__ bool rate_is_active(double r)
-{
-    // on the two 32-bit halves, so that no part of the test is scheduled on the FP64 pipe
-    const uint32_t hi = uint32_t(__double2hiint(r)) & 0x7fffffffu, lo = uint32_t(__double2loint(r));
-    const bool above = hi > 0x1e56a09eu || (hi == 0x1e56a09eu && lo > 0x667f3bccu);
-    return above && hi <= 0x5fcfffffu;
-}
-
-// power tables of one group: lane = site; rows of lanes >= cnt are U = 0, W = 1 (they add exactly 0)
-template <int RH>
-__device__ __forceinline__ void prof_build_tables(double lam, bool ok, int64_t T0, double t0d, double* myU, double* myW)
-{
-    constexpr int H = 8 * RH;
-    double a = 16.0 * (lam * lam);
-    const double c = ok ? 4.0 * lam : 0.0;
-    a = ok ? a : 0.0;
-    const double q = exp_full(-c);
-    const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
-    const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
-    const double qB = q16 * q16;  // q^32
-    double xa = u0, xb = u0 * q16;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        st_shared_v2(myU + 2 * k, xa, xa * q);
-        st_shared_v2(myU + 16 + 2 * k, xb, xb * q);
-        xa *= q2;
-        xb *= q2;
-    }
-    if constexpr (RH >= 2) {
-        const double qB2 = qB * qB;
-        double qBh = qB2;  // -> qB^(H/2)
-#pragma unroll
-        for (int k = 2; k < H / 2; k *= 2) qBh *= qBh;
-        double wa = 1.0, wb = qBh;
-#pragma unroll
-        for (int k = 0; k < H / 4; ++k) {
-            st_shared_v2(myW + 2 * k, wa, wa * qB);
-            st_shared_v2(myW + H / 2 + 2 * k, wb, wb * qB);
-            wa *= qB2;
-            wb *= qB2;
-        }
-    } else {
-        const double qB2 = qB * qB;
-        double wa = 1.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            st_shared_v2(myW + 2 * k, wa, wa * qB);
-            wa *= qB2;
-        }
-    }
-}
-
-// acc(lo,hi) += sum_s U[s][lo] * W[s][hi] over nk k-steps of 4 sites
-template <int RH>
-__device__ __forceinline__ void prof_contract(double (&acc)[4][RH][2], const double* fragU, const double* fragW, int nk)
-{
-    constexpr int WS = ProfCfg<RH>::WStride, US = kUStride;
-    auto fetch = [&](double (&a)[4], double (&b)[RH], int step) {
-        const double* up = fragU + step * (4 * US);
-        const double* wp = fragW + step * (4 * WS);
-        const double2 u01 = *reinterpret_cast<const double2*>(up);
-        const double2 u23 = *reinterpret_cast<const double2*>(up + 2);
-        a[0] = u01.x; a[1] = u01.y; a[2] = u23.x; a[3] = u23.y;
-        if constexpr (RH == 1) {
-            b[0] = wp[0];
-        } else {
-#pragma unroll
-            for (int r = 0; r < RH / 2; ++r) {
-                const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
-                b[2 * r] = v.x; b[2 * r + 1] = v.y;
-            }
-        }
-    };
-    auto mma_step = [&](const double (&a)[4], const double (&b)[RH]) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < RH; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    };
-    double a0[4], b0[RH], a1[4], b1[RH];
-    fetch(a0, b0, 0);
-    for (int s = 0; s < nk; s += 2) {
-        fetch(a1, b1, s + 1);
-        mma_step(a0, b0);
-        fetch(a0, b0, min(s + 2, 7));
-        mma_step(a1, b1);
-    }
-}
-
-// one item's accumulators -> pi_net (times t) and the tile maximum, or the split workspace
-template <int RH>
-__device__ __forceinline__ void prof_epilogue(const ProfArgs& args, const double (&acc)[4][RH][2], int locus, int tile, int slot,
-                                              int lane)
-{
-    constexpr int TT = ProfCfg<RH>::TT;
-    const int fk = lane & 3, fg = lane >> 2;
-    const int64_t T0 = int64_t(tile) * TT;
-    const double t0d = double(T0);
-    const int lo0 = 4 * chunk_pair(fg);
-    if (slot >= 0) {
-        double* out = args.ws + size_t(slot) * TT;
-#pragma unroll
-        for (int j = 0; j < RH; ++j)
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
-                double* o = out + hi * 32 + lo0;
-                *reinterpret_cast<double2*>(o) = make_double2(acc[0][j][c], acc[1][j][c]);
-                *reinterpret_cast<double2*>(o + 2) = make_double2(acc[2][j][c], acc[3][j][c]);
-            }
-        return;
-    }
-    const int64_t row = int64_t(locus) * args.T;
-    double* out = args.pi_net + row;
-    const bool vec_ok = ((row & 1) == 0);
-    long long best_bits = -1;
-    int best_i = 0;
-    const int64_t t_left = args.T - T0;
-    const int t_end = int(t_left < int64_t(TT) ? t_left : int64_t(TT));
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int j = 0; j < RH; ++j) {
-            const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
-            const int o = hi * 32 + lo0;
-            const double td = t0d + double(o);
-            double v[4];
-            v[0] = acc[0][j][c] * td;
-            v[1] = acc[1][j][c] * (td + 1.0);
-            v[2] = acc[2][j][c] * (td + 2.0);
-            v[3] = acc[3][j][c] * (td + 3.0);
-            double* dst = out + T0 + o;
-            if (o + 3 < t_end && vec_ok) {
-                *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
-                *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (o + i < t_end) dst[i] = v[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long bits = __double_as_longlong(v[i]);
-                if (o + i < t_end && bits > best_bits) {
-                    best_bits = bits;
-                    best_i = o + i;
-                }
-            }
-        }
-    int64_t best_t = T0 + best_i;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const long long ob = __shfl_xor_sync(0xffffffffu, best_bits, off);
-        const int64_t ot = __shfl_xor_sync(0xffffffffu, best_t, off);
-        if (ob > best_bits || (ob == best_bits && ot < best_t)) { best_bits = ob; best_t = ot; }
-    }
-    if (lane == 0) {
-        const int64_t k = int64_t(locus) * args.n_tiles + tile;
-        args.tile_max[k] = __longlong_as_double(best_bits);
-        args.tile_arg[k] = best_t;
-    }
-}
-
-// Inverse of w_chunk: which fragment column group (2 fk + c) owns hi chunk x.
-template <int RH>
-__device__ __forceinline__ int w_chunk_inv(int x)
-{
-    if constexpr (RH == 4) return chunk_pair(x);  // swaps bits 0 and 1: its own inverse
-    else if constexpr (RH == 2) return ((x << 1) & 7) | (x >> 2);
-    else return x;
-}
-
-// The consumer parks an item's accumulators in the ring slot it has just drained, in time order (offset
-// o = 32 hi + lo), as 16-byte units whose two low index bits are XORed with the owning fragment row fk so that
-// both the fragment-ordered stores and the linear loads below are free of bank conflicts.
-template <int RH>
-__device__ __forceinline__ int ws_unit(int u)
-{
-    const int hi = u >> 4;
-    return u ^ ((w_chunk_inv<RH>(hi / RH) >> 1) & 3);
-}
-
-template <int RH>
-__device__ __forceinline__ void ws_park(double* buf, const double (&acc)[4][RH][2], int lane)
-{
-    const int fk = lane & 3, fg = lane >> 2;
-    const int w0 = 2 * chunk_pair(fg);
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int j = 0; j < RH; ++j) {
-            const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
-            const int u = hi * 16 + w0;
-            *reinterpret_cast<double2*>(buf + 2 * (u ^ fk)) = make_double2(acc[0][j][c], acc[1][j][c]);
-            *reinterpret_cast<double2*>(buf + 2 * ((u + 1) ^ fk)) = make_double2(acc[2][j][c], acc[3][j][c]);
-        }
-}
-
-// Epilogue of a parked item, run by a producer warp: pi_net = t * sum (rows written as 512-byte runs), the tile
-// maximum (first maximum, as numpy.argmax), or the raw sums of a split item into the workspace.
-template <int RH>
-__device__ __forceinline__ void ws_epilogue(const ProfArgs& args, const double* buf, int locus, int tile, int slot, int lane)
-{
-    constexpr int TT = ProfCfg<RH>::TT, NU = TT / 64;  // 16-byte units per lane
-    if (slot >= 0) {
-        double* out = args.ws + size_t(slot) * TT;
-#pragma unroll 4
-        for (int k = 0; k < NU; ++k) {
-            const int u = k * 32 + lane;
-            *reinterpret_cast<double2*>(out + 2 * u) = *reinterpret_cast<const double2*>(buf + 2 * ws_unit<RH>(u));
-        }
-        return;
-    }
-    const int64_t T0 = int64_t(tile) * TT;
-    const int64_t row = int64_t(locus) * args.T;
-    double* out = args.pi_net + row + T0;
-    const bool vec_ok = ((row & 1) == 0);
-    const int64_t t_left = args.T - T0;
-    const int t_end = int(t_left < int64_t(TT) ? t_left : int64_t(TT));
-    long long best_bits = -1;
-    int best_i = 0;
-    double td = double(T0) + double(2 * lane);  // exact: integers far below 2^53
-#pragma unroll 4
-    for (int k = 0; k < NU; ++k) {
-        const int u = k * 32 + lane, o = 2 * u;
-        const double2 s = *reinterpret_cast<const double2*>(buf + 2 * ws_unit<RH>(u));
-        const double v0 = s.x * td, v1 = s.y * (td + 1.0);
-        td += 64.0;
-        if (o + 1 < t_end && vec_ok) {
-            *reinterpret_cast<double2*>(out + o) = make_double2(v0, v1);
-        } else {
-            if (o < t_end) out[o] = v0;
-            if (o + 1 < t_end) out[o + 1] = v1;
-        }
-        // values are >= 0: their bit patterns order like the values; a lane sees its offsets in increasing order
-        const long long b0 = __double_as_longlong(v0), b1 = __double_as_longlong(v1);
-        if (o < t_end && b0 > best_bits) { best_bits = b0; best_i = o; }
-        if (o + 1 < t_end && b1 > best_bits) { best_bits = b1; best_i = o + 1; }
-    }
-    int64_t best_t = T0 + best_i;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const long long ob = __shfl_xor_sync(0xffffffffu, best_bits, off);
-        const int64_t ot = __shfl_xor_sync(0xffffffffu, best_t, off);
-        if (ob > best_bits || (ob == best_bits && ot < best_t)) { best_bits = ob; best_t = ot; }
-    }
-    if (lane == 0) {
-        const int64_t k = int64_t(locus) * args.n_tiles + tile;
-        args.tile_max[k] = __longlong_as_double(best_bits);
-        args.tile_arg[k] = best_t;
-    }
-}
-
-template <int RH>
-__global__ void __launch_bounds__(WsCfg<RH>::Threads, 1) profile_ws_kernel(const ProfArgs args)
-{
-    using Cfg = WsCfg<RH>;
-    constexpr int NB = Cfg::NBuf, WS = Cfg::WStride, US = kUStride, TT = ProfCfg<RH>::TT;
-    constexpr bool kPair = Cfg::NProd == 2;
-    extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int ln = warp & 3;     // lane group: warps ln, 4 + ln (and 8 + ln) share an SM sub-partition
-    const int role = warp >> 2;  // 0: consumer, 1 and 2: producers
-    double* ring = smem + size_t(ln) * Cfg::LaneDoubles;
-    WsCtl<NB>* ctl = reinterpret_cast<WsCtl<NB>*>(smem + size_t(kWsLanes) * Cfg::LaneDoubles) + ln;
-    if (role == 0 && lane == 0) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            mbar_init(&ctl->full[b], 32);
-            mbar_init(&ctl->empty[b], 32);
-            ctl->epi[b].valid = 0;
-        }
-        ctl->pub = 0;
-    }
-    __syncthreads();
-
-    if (role == 0) {
-        // ---------------- consumer: nothing but DMMAs ----------------
-        const int fk = lane & 3, fg = lane >> 2;
-        double acc[4][RH][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < RH; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        int b = 0;
-        uint32_t ph = 0;
-        for (;;) {
-            mbar_wait(&ctl->full[b], ph);
-            const WsDesc d = ctl->desc[b];
-            if (d.cnt < 0) break;
-            double* Us = ring + size_t(b) * Cfg::BufDoubles;
-            const double* Ws = Us + 32 * US;
-            const double* fragU = Us + fk * US + 4 * chunk_pair(fg);
-            const double* fragW = Ws + fk * WS + RH * w_chunk<RH>(fg);
-            const int nk = (d.cnt + 3) >> 2;
-            if (nk > 0 && !(args.debug & 1)) prof_contract<RH>(acc, fragU, fragW, nk);
-            if (d.last) {
-                // the item is complete: park its sums in this slot; the producer that takes the slot next finishes it
-                __syncwarp();  // every lane has fetched its last fragments
-                ws_park<RH>(Us, acc, lane);
-                if (lane == 0) {
-                    WsEpi e;
-                    e.locus = d.locus; e.tile = d.tile; e.slot = d.slot; e.valid = 1;
-                    ctl->epi[b] = e;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < RH; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-            }
-            mbar_arrive(&ctl->empty[b]);  // every lane releases its own accesses to the slot
-            if (++b == NB) { b = 0; ph ^= 1u; }
-        }
-        return;
-    }
-
-    // ---------------- producers: claim items, compact the active rates, build alternate groups ----------------
-    const int p = role - 1;
-    double* Qs = ring + size_t(NB) * Cfg::BufDoubles + p * 64;
-    int b = 0;            // ring slot of the next group (both producers count every group)
-    uint32_t ph = 1;      // parity to wait for on empty[b]: a fresh barrier passes parity 1
-    int mine = (p == 0);  // the next group is this producer's
-    uint32_t seq = 0;
-    const uint32_t n_items = uint32_t(args.n_items);
-    // take ring slot b: wait until the consumer has drained it, and finish the item it may have parked there
-    auto acquire = [&]() -> double* {
-        mbar_wait(&ctl->empty[b], ph);
-        double* buf = ring + size_t(b) * Cfg::BufDoubles;
-        const WsEpi e = ctl->epi[b];
-        if (e.valid) {
-            ws_epilogue<RH>(args, buf, e.locus, e.tile, e.slot, lane);
+        if constexpr (TRACE) {
             __syncwarp();
-            if (lane == 0) ctl->epi[b].valid = 0;
+            if (lane == 0 && n_done < 8) tr[4 + n_done] = clock64();
+            ++n_done;
         }
-        return buf;
-    };
-    auto advance = [&]() {
-        if constexpr (kPair) mine ^= 1;
-        if (++b == NB) { b = 0; ph ^= 1u; }
-    };
-    // hand one group to the consumer; lam of this lane's site as popped from the queue
-    auto emit = [&](double lam, int cnt, int last, const ProfItem& item) {
-        if (mine) {
-            double* Us = acquire();
-            const int64_t T0 = int64_t(item.tile) * TT;
-            if (cnt > 0 && !(args.debug & 2)) prof_build_tables<RH>(lam, lane < cnt, T0, double(T0), Us + lane * US, Us + 32 * US + lane * WS);
-            if (lane == 0) {
-                WsDesc d;
-                d.cnt = cnt; d.last = last; d.locus = item.locus; d.tile = item.tile; d.slot = item.slot; d.pad = 0;
-                ctl->desc[b] = d;
-            }
-            mbar_arrive(&ctl->full[b]);  // every lane publishes its own table rows
-        }
-        advance();
-    };
-    // Producer 0 claims the items; producer 1 learns them through a small ring in shared memory.  Producer 0 never
-    // waits for producer 1 here (the table ring keeps the two within a few groups of each other, so an entry is
-    // read long before it is reused).
-    auto share = [&](uint32_t claimed) -> uint32_t {
-        uint32_t it = claimed;
-        if constexpr (kPair) {
-            volatile uint32_t* pub = &ctl->pub;
-            volatile uint32_t* slot = &ctl->item[seq & 3];
-            if (p == 0) {
-                if (lane == 0) {
-                    *slot = claimed;
-                    __threadfence_block();
-                    *pub = seq + 1;
-                }
-            } else {
-                if (lane == 0) {
-                    while (int32_t(*pub - (seq + 1)) < 0) __nanosleep(20);
-                    __threadfence_block();
-                    it = *slot;
-                }
-            }
-        }
-        ++seq;
-        return __shfl_sync(0xffffffffu, it, 0);
-    };
-    constexpr int kAhead = 4;  // rounds of 32 rates in flight per producer
-    ProfItem item;
-    double lam_q[kAhead];
-    auto open_rates = [&](const ProfItem& src, double (&q)[kAhead]) {
-        const double* rp = args.rates + src.site_begin;
-#pragma unroll
-        for (int k = 0; k < kAhead; ++k) q[k] = (32 * k + lane < src.n_sites) ? __ldg(rp + 32 * k + lane) : 0.0;
-    };
-    uint32_t it = share((p == 0 && lane == 0) ? atomicAdd(args.counter, 1u) : 0u);
-    if (it < n_items) {
-        item = args.items[it];
-        open_rates(item, lam_q);
     }
-    while (it < n_items) {
-        const double* rp = args.rates + item.site_begin;
-        int qh = 0, qn = 0;
-        // The next item is prepared while this one is being produced, a step at a time so that no step waits for the
-        // one before it: claim it (round ra), pass it to the other producer (rb), fetch its descriptor (rc), and
-        // request its first rates once this item's are all in.  The consumer then never sees the item boundary.
-        const int n_rounds = (item.n_sites + 31) >> 5;
-        const int ra = n_rounds >> 2, rb = n_rounds >> 1, rc = (3 * n_rounds) >> 2;
-        uint32_t claimed = 0, it_next = n_items;
-        ProfItem next_item = item;
-        auto prep = [&](int r) {
-            if (r == ra && p == 0 && lane == 0) claimed = atomicAdd(args.counter, 1u);
-            if (r == rb) it_next = share(claimed);
-            if (r == rc && it_next < n_items) next_item = args.items[it_next];
-        };
-        for (int base = 0, r = 0; base < item.n_sites; base += 32, ++r) {
-            prep(r);
-            const double lam_new = lam_q[0];
-#pragma unroll
-            for (int k = 0; k + 1 < kAhead; ++k) lam_q[k] = lam_q[k + 1];
-            {
-                const int nb = base + 32 * kAhead + lane;
-                lam_q[kAhead - 1] = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
-            }
-            const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
-            const unsigned ballot = __ballot_sync(0xffffffffu, act);
-            if (act) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
-            qn += __popc(ballot);
-            __syncwarp();
-            // more than 32 queued: the first 32 are certainly not the item's last group
-            if (qn - qh > 32) {
-                const double lam = Qs[(qh + lane) & 63];
-                qh += 32;
-                __syncwarp();
-                emit(lam, 32, 0, item);
-            }
-        }
-        if (n_rounds == 0) prep(0);
-        if (it_next < n_items) open_rates(next_item, lam_q);
-        {
-            const int cnt = qn - qh;  // 0..32
-            const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
-            __syncwarp();
-            emit(lam, cnt, 1, item);
-        }
-        it = it_next;
-        item = next_item;
-    }
-    // no more items: one more turn around the ring finishes the parked items; its first slot carries the stop mark
-#pragma unroll 1
-    for (int v = 0; v < NB; ++v) {
-        if (mine) {
-            acquire();
-            if (v == 0) {
-                if (lane == 0) {
-                    WsDesc d;
-                    d.cnt = -1; d.last = 0; d.locus = 0; d.tile = 0; d.slot = -1; d.pad = 0;
-                    ctl->desc[b] = d;
-                }
-                mbar_arrive(&ctl->full[b]);
-            }
-        }
-        advance();
+    if constexpr (TRACE) {
+        if (lane == 0) { tr[12] = clock64(); tr[13] = n_done; }
     }
 }
 

@@ -136,7 +136,9 @@ struct tapir_cuda_ctx {
     int use_graphs = 1;      // staged path replays a captured CUDA graph (TAPIR_CUDA_GRAPHS=0 disables)
     int n_lanes = 6;         // lanes the chunks of tapir_cuda_run rotate over
     int ramp = 1;            // tapir_cuda_run starts with two short chunks so the first download begins early
-    int prof_ws = 0;         // profile kernel variant: TAPIR_PROF_WS=1 = warp-specialised (measured slower: DESIGN 3.1)
+    long long* prof_trace = nullptr;  // TAPIR_PROF_TRACE=<file>: per-warp time stamps of profile_kernel, dumped by tapir_cuda_compute
+    size_t prof_trace_words = 0;
+    std::string prof_trace_path;
     int trace = 0;           // TAPIR_CUDA_TRACE=1: tapir_cuda_run prints the timeline of its chunks to stderr
     std::string last_error;
     Lane lanes[kLanes];
@@ -219,20 +221,6 @@ template <int RH>
 cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, int64_t n_items)
 {
     static bool configured[64] = {false};
-    if (ctx->prof_ws) {
-        // warp-specialised variant: one CTA per SM, four consumer warps fed by eight producer warps
-        using Cfg = WsCfg<RH>;
-        if (!configured[ctx->device & 63]) {
-            cudaError_t e = cudaFuncSetAttribute(profile_ws_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 int(Cfg::SmemBytes));
-            if (e != cudaSuccess) return e;
-            configured[ctx->device & 63] = true;
-        }
-        int64_t grid = std::min<int64_t>(ctx->sm_count, (n_items + kWsLanes - 1) / kWsLanes);
-        if (grid < 1) grid = 1;
-        profile_ws_kernel<RH><<<unsigned(grid), Cfg::Threads, Cfg::SmemBytes, ln.stream>>>(pa);
-        return cudaGetLastError();
-    }
     using Cfg = ProfCfg<RH>;
     if (!configured[ctx->device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(profile_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -253,6 +241,16 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
     const int64_t need = (n_items + kProfWarps - 1) / kProfWarps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if (pa.trace) {  // measurement only
+        static bool trace_configured[64] = {false};
+        if (!trace_configured[ctx->device & 63]) {
+            e = cudaFuncSetAttribute(profile_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
+            if (e != cudaSuccess) return e;
+            trace_configured[ctx->device & 63] = true;
+        }
+        profile_kernel<RH, true><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
+        return cudaGetLastError();
+    }
     profile_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
     return cudaGetLastError();
 }
@@ -396,7 +394,13 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         if ((env = getenv("TAPIR_CUDA_LANES"))) ctx->n_lanes = std::max(1, std::min(kLanes, atoi(env)));
         if ((env = getenv("TAPIR_CUDA_RAMP"))) ctx->ramp = atoi(env) != 0;
         if ((env = getenv("TAPIR_CUDA_TRACE"))) ctx->trace = atoi(env) != 0;
-        if ((env = getenv("TAPIR_PROF_WS"))) ctx->prof_ws = atoi(env) != 0;
+        if ((env = getenv("TAPIR_PROF_TRACE")) && env[0]) {
+            ctx->prof_trace_path = env;
+            ctx->prof_trace_words = size_t(prop.multiProcessorCount) * 4 * kProfWarps * 32;
+            if (cudaMalloc(&ctx->prof_trace, ctx->prof_trace_words * 8) != cudaSuccess) ctx->prof_trace = nullptr;
+            else cudaMemset(ctx->prof_trace, 0, ctx->prof_trace_words * 8);
+            ctx->use_graphs = 0;
+        }
     }
     e = cudaSuccess;
     for (Lane& ln : ctx->lanes) {
@@ -673,8 +677,7 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
             pa.T = plan.T;
             pa.n_items = int32_t(plan.n_prof_items);
             pa.n_tiles = plan.n_tiles;
-            pa.debug = 0;
-            if (const char* env = getenv("TAPIR_PROF_DEBUG")) pa.debug = atoi(env);
+            pa.trace = ctx->prof_trace;
             cudaError_t e = cudaSuccess;
             switch (plan.rh) {
                 case 1: e = launch_profile<1>(ctx, ln, pa, plan.n_prof_items); break;
@@ -1054,7 +1057,16 @@ int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
 {
     int rc = bind(ctx);
     if (rc) return rc;
-    return lane_compute(ctx, ctx->lanes[0], timing, true, true);
+    rc = lane_compute(ctx, ctx->lanes[0], timing, true, true);
+    if (rc == TAPIR_OK && ctx->prof_trace) {  // measurement only: the stamps of this step's profile_kernel launch
+        std::vector<long long> h(ctx->prof_trace_words);
+        CU(ctx, cudaMemcpy(h.data(), ctx->prof_trace, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(ctx->prof_trace_path.c_str(), "wb")) {
+            fwrite(h.data(), 8, h.size(), f);
+            fclose(f);
+        }
+    }
+    return rc;
 }
 
 int tapir_cuda_download(tapir_cuda_ctx* ctx, const tapir_results* out)
