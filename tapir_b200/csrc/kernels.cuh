@@ -409,7 +409,12 @@ struct QuadArgs {
 // in the node values, and A0 >= 1e-270 on this path, so nothing under- or overflows differently).
 // Node values are >= 0 here, so dqk21's resabs sum equals resk's.
 // `scale` = a e^{-c centre} h (>= 0).
-__device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, double scale, const double (&D)[10],
+// Returns true when the whole warp took the short way out: for every live lane the rounding floor
+// 50 eps resabs is PROVED to be dqk21's error estimate (and dqagse accepts the panel) from a lower bound of resasc
+// -- two of its 21 non-negative terms -- so the other 19 are never formed; resasc is then not set.  The proof is
+// the existing floor test, which is monotone in resasc, plus resasc > floor (dqagse compares abserr with resasc);
+// whenever it holds the full computation yields the same abserr bit for bit.  `live`: the lane's result is used.
+__device__ __forceinline__ bool gk21_shared_exp(const EpochBatch& eb, int e, double scale, bool live, const double (&D)[10],
                                                 const double (&R)[10], double& result, double& abserr, double& resabs,
                                                 double& resasc)
 {
@@ -444,6 +449,25 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
     const double resk = (rk0 + rk1) + (rk2 + rk3);
     const double resg = rg0 + rg1;
     const double reskh = resk * 0.5;
+    result = resk * scale;
+    resabs = result;
+    // dqk21's error heuristic: err = resasc * min(1, (200 e0 / resasc)^1.5), then raised to the rounding
+    // floor 50 eps resabs.  Whether the floor wins is decided without the divide and the square root:
+    // resasc (n/resasc)^1.5 <= floor  <=>  n^3 <= floor^2 resasc, compared in units of resk (scaled by a
+    // power of two taken from resk's exponent so that neither side can overflow or underflow to a tie).
+    const double e0 = fabs(resk - resg);
+    const double unit = __hiloint2double((2046 - ((__double2hiint(resk) >> 20) & 0x7ff)) << 20, 0);  // ~ 1 / resk
+    const double n = (200.0 * e0) * unit, fl = ((kEpmach * 50.0) * resk) * unit;
+    const bool above_uflow = resabs > kUflow / (50.0 * kEpmach);
+    {
+        const double lb = (c_wgk[4] * (fabs(fv1[4] - reskh) + fabs(fv2[4] - reskh)) +
+                           c_wgk[5] * (fabs(fv1[5] - reskh) + fabs(fv2[5] - reskh))) * unit;  // <= resasc * unit
+        const bool proved = above_uflow && n < lb && (n * n) * n <= (fl * fl) * lb && lb > fl;
+        if (__all_sync(0xffffffffu, proved || !live)) {
+            abserr = (kEpmach * 50.0) * resabs;
+            return true;
+        }
+    }
     double ra0 = c_wgk[10] * fabs(fc - reskh), ra1 = 0.0, ra2 = 0.0, ra3 = 0.0;
 #pragma unroll
     for (int j = 0; j < 10; ++j) {
@@ -454,23 +478,16 @@ __device__ __forceinline__ void gk21_shared_exp(const EpochBatch& eb, int e, dou
         else ra3 += t;
     }
     const double rasc = (ra0 + ra1) + (ra2 + ra3);
-    result = resk * scale;
-    resabs = result;
     resasc = rasc * scale;
-    // dqk21's error heuristic: err = resasc * min(1, (200 e0 / resasc)^1.5), then raised to the rounding
-    // floor 50 eps resabs.  Whether the floor wins is decided without the divide and the square root:
-    // resasc (n/resasc)^1.5 <= floor  <=>  n^3 <= floor^2 resasc, compared in units of resk (scaled by a
-    // power of two taken from resk's exponent so that neither side can overflow or underflow to a tie).
-    const double e0 = fabs(resk - resg);
-    const double unit = __hiloint2double((2046 - ((__double2hiint(resk) >> 20) & 0x7ff)) << 20, 0);  // ~ 1 / resk
-    const double n = (200.0 * e0) * unit, ra = rasc * unit, fl = ((kEpmach * 50.0) * resk) * unit;
-    if (resabs > kUflow / (50.0 * kEpmach) && (ra == 0.0 || e0 == 0.0)) {
+    const double ra = rasc * unit;
+    if (above_uflow && (ra == 0.0 || e0 == 0.0)) {
         abserr = fmax((kEpmach * 50.0) * resabs, e0 * scale);
-    } else if (resabs > kUflow / (50.0 * kEpmach) && n < ra && (n * n) * n <= (fl * fl) * ra) {
+    } else if (above_uflow && n < ra && (n * n) * n <= (fl * fl) * ra) {
         abserr = (kEpmach * 50.0) * resabs;
     } else {
         abserr = gk_error(resk, resg, scale, resabs, resasc);
     }
+    return false;
 }
 
 // First GK21 panel of every (site, epoch) of the batch.  A site whose panel is what QAGS returns (the
@@ -569,9 +586,11 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 3) quad_kernel(const QuadArgs
                         }
                         // common factor a e^{-c centre} h; |c * centre| <= 600 on this path
                         const double scale = (as * exp_bounded(-(cs * eb.center[e]))) * eb.half[e];
-                        double result, abserr, resabs, resasc;
-                        gk21_shared_exp(eb, e, scale, D, R, result, abserr, resabs, resasc);
-                        const bool keep = fast && qags_first_panel_final(result, abserr, resabs, resasc);
+                        double result, abserr, resabs, resasc = 0.0;
+                        const bool by_floor = gk21_shared_exp(eb, e, scale, fast, D, R, result, abserr, resabs, resasc);
+                        // by_floor: abserr = 50 eps resabs <= 100 eps resabs and abserr != resasc, so dqagse's test
+                        // (round-off exit above errbnd, plain acceptance below) passes either way
+                        const bool keep = fast && (by_floor || qags_first_panel_final(result, abserr, resabs, resasc));
                         s_acc[warp][2 * e][lane] += keep ? result : 0.0;
                         s_acc[warp][2 * e + 1][lane] += keep ? abserr : 0.0;
                         if (on && !keep)  // rare: hand the site (by its position in the item) to quad_fix_kernel
