@@ -37,6 +37,20 @@ __device__ __constant__ double c_wg[5] = {
     0.219086362515982043995534934228163, 0.269266719309996355091226921569469,
     0.295524224714752870173815619188769};
 
+// Products of the rule's constants for the collapsed panel of quad_kernel (kernels.cuh, gk21_collapsed):
+// c_wx[j] = wgk[j] x[j]; c_dl[j] = wgk[j] - wg[(j-1)/2] on the Gauss nodes (odd j), wgk[j] elsewhere, so that
+// resk - resg = wgk[10] f(centre) + sum_j c_dl[j] (f1_j + f2_j); c_dlx[j] = c_dl[j] x[j].  Derived in 60-digit
+// decimal arithmetic from the doubles above and rounded once.
+__device__ __constant__ double c_wx[10] = {0.01164385095729883,  0.03170860682824855, 0.05093160739453187, 0.06491407372718101,
+                                           0.07271400573536937,  0.07431868233932587, 0.06949599071580352, 0.0583823543295484,
+                                           0.04203221728258857,  0.02199456158392464};
+__device__ __constant__ double c_dl[10] = {0.011694638867371874, -0.03411318200072341, 0.054755896574351995, -0.07441167433966063,
+                                           0.0931254545836976,   -0.1096992037136844,  0.12349197626206584,  -0.134557501998523,
+                                           0.14277593857706009,  -0.14778511981341438};
+__device__ __constant__ double c_dlx[10] = {0.01164385095729883,  -0.033223050658999005, 0.05093160739453187, -0.06437081352523115,
+                                            0.07271400573536937,  -0.07453068863786105,  0.06949599071580352, -0.05831660161169685,
+                                            0.04203221728258857,  -0.022001412023543238};
+
 // Host copies of the abscissae (the host precomputes centre -/+ h*x_j per epoch).
 static const double h_xgk[10] = {
     0.995657163025808080735527280689003, 0.973906528517171720077964012084452,

@@ -490,6 +490,61 @@ __device__ __forceinline__ bool gk21_shared_exp(const EpochBatch& eb, int e, dou
     return false;
 }
 
+// The same panel without forming the node values.  With the common factor taken out, the pair sum of node j is
+//   f1_j + f2_j = (centre - h x_j) R_j + (centre + h x_j) D_j = centre (R_j + D_j) - h x_j (R_j - D_j),
+// linear in the epoch's centre, so for all epochs of one half-length
+//   resk = centre Ak - Bk,   resk - resg = centre dA - dB,
+//   Ak = wgk_10 + sum wgk_j (R_j + D_j),  Bk = h sum wgk_j x_j (R_j - D_j),  dA, dB: the same with the weights
+//   c_dl (Kronrod minus Gauss), summed directly so that the cancellation happens once, in the site's tables.
+// An epoch then costs two FMAs plus the proof that the rounding floor is dqk21's error estimate (lower bound of
+// resasc from node pairs 4 and 5, which are formed as before).  Returns true when the proof holds for every live
+// lane of the warp; otherwise nothing is written and the caller runs gk21_shared_exp.  The integral differs from
+// the node-by-node sum by rounding only (a different association, ~1e-16 relative).
+struct PanelSums {
+    double Ak, Bk, dA, dB;
+    double D4, R4, D5, R5;  // the two node pairs the proof looks at
+};
+
+__device__ __forceinline__ void panel_sums(double h, const double (&D)[10], const double (&R)[10], PanelSums& ps)
+{
+    double ak0 = c_wgk[10], ak1 = 0.0, bk0 = 0.0, bk1 = 0.0, da0 = c_wgk[10], da1 = 0.0, db0 = 0.0, db1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const double sj = R[j] + D[j], dj = R[j] - D[j];
+        if (j & 1) {
+            ak1 = fma(c_wgk[j], sj, ak1); bk1 = fma(c_wx[j], dj, bk1);
+            da1 = fma(c_dl[j], sj, da1);  db1 = fma(c_dlx[j], dj, db1);
+        } else {
+            ak0 = fma(c_wgk[j], sj, ak0); bk0 = fma(c_wx[j], dj, bk0);
+            da0 = fma(c_dl[j], sj, da0);  db0 = fma(c_dlx[j], dj, db0);
+        }
+    }
+    ps.Ak = ak0 + ak1;
+    ps.Bk = (bk0 + bk1) * h;
+    ps.dA = da0 + da1;
+    ps.dB = (db0 + db1) * h;
+    ps.D4 = D[4]; ps.R4 = R[4]; ps.D5 = D[5]; ps.R5 = R[5];
+}
+
+__device__ __forceinline__ bool gk21_collapsed(const EpochBatch& eb, int e, double scale, bool live, const PanelSums& ps,
+                                               double& result, double& abserr)
+{
+    const double fc = eb.center[e];
+    const double resk = fma(fc, ps.Ak, -ps.Bk);
+    const double e0 = fabs(fma(fc, ps.dA, -ps.dB));
+    const double reskh = resk * 0.5;
+    const double unit = __hiloint2double((2046 - ((__double2hiint(resk) >> 20) & 0x7ff)) << 20, 0);  // ~ 1 / resk
+    const double n = (200.0 * e0) * unit, fl = ((kEpmach * 50.0) * resk) * unit;
+    const double f14 = eb.tm[e][4] * ps.R4, f24 = eb.tp[e][4] * ps.D4, f15 = eb.tm[e][5] * ps.R5, f25 = eb.tp[e][5] * ps.D5;
+    const double lb = (c_wgk[4] * (fabs(f14 - reskh) + fabs(f24 - reskh)) + c_wgk[5] * (fabs(f15 - reskh) + fabs(f25 - reskh))) * unit;
+    const double res = resk * scale;
+    const bool proved = res > kUflow / (50.0 * kEpmach) && n < lb && (n * n) * n <= (fl * fl) * lb && lb > fl;
+    if (!__all_sync(0xffffffffu, proved || !live)) return false;
+    result = res;
+    abserr = (kEpmach * 50.0) * res;
+    return true;
+}
+
 // First GK21 panel of every (site, epoch) of the batch.  A site whose panel is what QAGS returns (the
 // overwhelmingly common case) is summed here; the others contribute 0 and are handed to
 // quad_fix_kernel through the FixEntry list.
@@ -573,21 +628,32 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 3) quad_kernel(const QuadArgs
                     // fast path: all exponent arguments stay well inside the normal range, every node value >= 0
                     const bool fast = on && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
                     const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps idle lanes' arithmetic finite
-                    double D[10], R[10];
+                    PanelSums ps;
                     // one copy of the GK21 code, looped over the epochs: the fully unrolled form (4 x ~350
                     // instructions) thrashed the instruction cache once the warps ran out of step (18 % of the
                     // stall samples were instruction fetches)
 #pragma unroll 1
                     for (int e = 0; e < NE; ++e) {
                         if (eb.new_half[e]) {
+                            double D[10], R[10];
                             const double y = cs * eb.half[e];
 #pragma unroll
                             for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
+                            panel_sums(eb.half[e], D, R, ps);
                         }
                         // common factor a e^{-c centre} h; |c * centre| <= 600 on this path
                         const double scale = (as * exp_bounded(-(cs * eb.center[e]))) * eb.half[e];
                         double result, abserr, resabs, resasc = 0.0;
-                        const bool by_floor = gk21_shared_exp(eb, e, scale, fast, D, R, result, abserr, resabs, resasc);
+                        bool by_floor = gk21_collapsed(eb, e, scale, fast, ps, result, abserr);
+                        if (!by_floor) {
+                            // rare: some site's estimate is not the floor.  The node tables are rebuilt here (same
+                            // function, same argument, same values) instead of being kept alive across the epochs.
+                            double D[10], R[10];
+                            const double y = cs * eb.half[e];
+#pragma unroll
+                            for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);
+                            by_floor = gk21_shared_exp(eb, e, scale, fast, D, R, result, abserr, resabs, resasc);
+                        }
                         // by_floor: abserr = 50 eps resabs <= 100 eps resabs and abserr != resasc, so dqagse's test
                         // (round-off exit above errbnd, plain acceptance below) passes either way
                         const bool keep = fast && (by_floor || qags_first_panel_final(result, abserr, resabs, resasc));
