@@ -637,8 +637,15 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 3) quad_kernel(const QuadArgs
                         if (eb.new_half[e]) {
                             double D[10], R[10];
                             const double y = cs * eb.half[e];
+                            // slow sites (the bulk of UCE-like data): every y x_j is below ln(2)/2, where the range
+                            // reduction is the identity -- same bits without it (x_0 log2 e = 1.4364...)
+                            if (__all_sync(0xffffffffu, y * 1.4365 < 0.4999)) {
 #pragma unroll
-                            for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
+                                for (int j = 0; j < 10; ++j) exp_pm_small(y * c_xgk[j], D[j], R[j]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
+                            }
                             panel_sums(eb.half[e], D, R, ps);
                         }
                         // common factor a e^{-c centre} h; |c * centre| <= 600 on this path

@@ -3,6 +3,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <random>
 #include "../../tapir_b200/csrc/fastexp.cuh"
 
@@ -43,6 +44,16 @@ int main()
         if (!(g == w || ulp_err(g, expl((long double)s)) <= 1.0)) { ++bad; std::printf("special %g: got %g want %g\n", s, g, w); }
     }
     if (!std::isnan(tapir::exp_full(NAN))) ++bad;
+    // exp_pm_small is exp_pm_bounded without the (identity) range reduction: same bits wherever it is used
+    int small_diff = 0;
+    for (int i = 0; i <= 400000; ++i) {
+        const double z = 0.3465 * double(i) / 400000.0;  // z log2(e) < 0.4999
+        double a, b, c, d;
+        tapir::exp_pm_bounded(z, a, b);
+        tapir::exp_pm_small(z, c, d);
+        if (std::memcmp(&a, &c, 8) != 0 || std::memcmp(&b, &d, 8) != 0) ++small_diff;
+    }
+    std::printf("exp_pm_small_diff %d\n", small_diff);
     std::printf("exp_bounded %.3f\nexp_pm_minus %.3f\nexp_pm_plus %.3f\nexp_full %.3f\nspecials_bad %d\n", wb, wpm, wpp, wf, bad);
     return 0;
 }

@@ -16,3 +16,4 @@ def test_fastexp_accuracy(tmp_path):
     assert float(vals["exp_full"]) <= 1.1             # Estrin form
     assert float(vals["exp_pm_minus"]) <= 2.0 and float(vals["exp_pm_plus"]) <= 2.0   # even/odd split: 2 ulp
     assert int(vals["specials_bad"]) == 0
+    assert int(vals["exp_pm_small_diff"]) == 0        # the reduction-free pair: bit-identical below ln(2)/2
