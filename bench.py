@@ -240,7 +240,12 @@ def host_side_rates(rates_np, off_np, T, times, epochs, out, n_files=512, n_db=2
     from tapir_b200.engine import BatchResult
     d = tempfile.mkdtemp(prefix="tapir_bench_")
     try:
+        # bounded by content, not only by count: at most ~1M sites of rate files and ~1M sqlite rows (the genome-scale
+        # shape has 1e6 sites per locus and a 10,000-point grid; 512 such files would take minutes to write and parse)
         n_files = min(n_files, off_np.size - 1)
+        while n_files > 1 and off_np[n_files] > 1_000_000:
+            n_files //= 2
+        n_db = max(1, min(n_db, 1_000_000 // max(int(T), 1)))
         paths = []
         for l in range(n_files):
             lam = rates_np[off_np[l]:off_np[l + 1]]
@@ -502,7 +507,7 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": (h1 - h0) // args.steps, "d2h_bytes_per_step": (d1 - d0) // args.steps,
                 "loci_per_s": total_loci / e2e_s, "timing": "host wall clock around tapir_cuda_run, pinned buffers",
                 "d2h_alone_ms": d2h_s * 1e3, "d2h_gbs": d2h_gbs, "host_thread_bound_to_gpu_numa_node": numa_bound,
-                "note": "chunks of loci alternate between three lanes (H2D / kernels / D2H of consecutive chunks overlap); bounded below by the D2H copy of the profile"},
+                "note": "chunks of loci rotate over up to six lanes, two short chunks first (H2D / kernels / D2H of consecutive chunks overlap); bounded below by the D2H copy of the profile"},
         "gpu_launches": launches, "gather": {"mode": gather_mode, "check": gather_check},
         "clocks": clocks,
         "checksum": checksum,
