@@ -1,9 +1,16 @@
 #!/usr/bin/env python
 """Summarise an `ncu --page source --csv` dump: total stall samples by reason, and the hottest SASS lines.
-usage: ncu_stalls.py src.csv [top_n]"""
+usage: ncu_stalls.py src.csv [top_n [kernel-substring]]"""
 import csv, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+want = sys.argv[3] if len(sys.argv) > 3 else None   # kernel-name substring: only that kernel's first block
+# the dump holds one block per captured launch ("Kernel Name" row, header row, one row per SASS line)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+pick = next((i for i in starts if want is None or want in rows[i][1]), starts[0])
+end = next((i for i in starts if i > pick), len(rows))
+print("kernel:", rows[pick][1])
+rows = rows[pick:end]
 hdr = rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 stall_cols = [h for h in hdr if h.startswith('stall_') and '(Not Issued)' not in h]
