@@ -252,6 +252,41 @@ def test_bisection_heavy_loci_are_deterministic(eng):
         assert a.n_multi_panel[l] == int(nm.sum())
 
 
+def test_mixed_error_estimates_within_a_warp(eng):
+    """quad_kernel settles an epoch for a whole warp when dqk21's rounding floor is provably every site's error
+    estimate (collapsed panel) and redoes it node by node otherwise.  Wide epochs with moderately fast rates mix, inside
+    the same groups of 32 sites, floor-estimate sites, single-panel sites whose estimate is the 1.5-power heuristic,
+    and sites QAGS bisects -- all three must come out as QUADPACK has them."""
+    from oracle import capi
+    from tapir_b200.engine import pack_csr
+    rng = np.random.default_rng(23)
+    eps = np.finfo(float).eps
+    loci = [rng.uniform(0.02, 0.1, size=600), rng.uniform(0.001, 0.3, size=257), rng.uniform(0.1, 0.3, size=96)]
+    loci[1][::7] = 0.0
+    epochs = [[0, 40], [10, 110], [5, 45], [32, 42]]
+    # a locus whose [5, 45] column is nothing but single-panel sites with a heuristic (non-floor) estimate
+    cand = rng.uniform(0.1, 0.3, size=20000)
+    integ, err, last = capi.epoch_sites(cand, 5, 45)
+    pick = cand[(last == 1) & ~np.isclose(err, 50 * eps * np.abs(integ), rtol=1e-6)][:96]
+    assert pick.size >= 64
+    loci.append(pick)
+    off, rates = pack_csr(loci, pinned=False)
+    res = eng.run(off, rates, 128, [3], epochs, want_profile=False)
+    kinds = np.zeros(3, dtype=int)
+    for l, lam in enumerate(loci):
+        si, se, nm = capi.epochs(lam, epochs)
+        assert rel(res.integral[l], si) < RTOL
+        np.testing.assert_allclose(res.abserr[l], se, rtol=ERR_RTOL, atol=1e-300)
+        assert res.n_multi_panel[l] == int(nm.sum())
+        for (a, b) in epochs:
+            integ, err, last = capi.epoch_sites(lam[lam != 0.0], a, b)
+            floor = np.isclose(err, 50 * eps * np.abs(integ), rtol=1e-6)
+            kinds += [int(np.sum((last == 1) & floor)), int(np.sum((last == 1) & ~floor)), int(np.sum(last > 1))]
+    assert np.all(kinds > 20), kinds                     # the batch really holds all three kinds
+    again = eng.run(off, rates, 128, [3], epochs, want_profile=False)
+    assert np.array_equal(res.integral, again.integral) and np.array_equal(res.abserr, again.abserr)
+
+
 def test_chunked_run_equals_single_pass(eng):
     """tapir_cuda_run cuts a large batch into chunks that alternate between two lanes (copies overlap
     kernels); the result must be bit-identical to the unchunked staged path, ragged loci included."""
