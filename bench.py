@@ -507,7 +507,7 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": (h1 - h0) // args.steps, "d2h_bytes_per_step": (d1 - d0) // args.steps,
                 "loci_per_s": total_loci / e2e_s, "timing": "host wall clock around tapir_cuda_run, pinned buffers",
                 "d2h_alone_ms": d2h_s * 1e3, "d2h_gbs": d2h_gbs, "host_thread_bound_to_gpu_numa_node": numa_bound,
-                "note": "chunks of loci rotate over up to six lanes, two short chunks first (H2D / kernels / D2H of consecutive chunks overlap); bounded below by the D2H copy of the profile"},
+                "note": "chunks of loci (13 MB of traffic each, a quarter- and a half-size one first) rotate over up to eight lanes (H2D / kernels / D2H of consecutive chunks overlap); bounded below by the D2H copy of the profile"},
         "gpu_launches": launches, "gather": {"mode": gather_mode, "check": gather_check},
         "clocks": clocks,
         "checksum": checksum,

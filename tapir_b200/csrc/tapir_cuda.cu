@@ -134,8 +134,8 @@ struct tapir_cuda_ctx {
     int sm_count = 148;
     int serial_kernels = 0;  // 1: profile and integral kernels on one stream (per-kernel timing is then exact)
     int use_graphs = 1;      // staged path replays a captured CUDA graph (TAPIR_CUDA_GRAPHS=0 disables)
-    int n_lanes = 6;         // lanes the chunks of tapir_cuda_run rotate over
-    int ramp = 1;            // tapir_cuda_run starts with two short chunks so the first download begins early
+    int n_lanes = 8;         // lanes the chunks of tapir_cuda_run rotate over
+    int ramp = 4;            // tapir_cuda_run opens with chunks of 1/ramp, 2/ramp, ... of the regular size (<= 1: off)
     long long* prof_trace = nullptr;  // TAPIR_PROF_TRACE=<file>: per-warp time stamps of profile_kernel, dumped by tapir_cuda_compute
     size_t prof_trace_words = 0;
     std::string prof_trace_path;
@@ -392,7 +392,7 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         env = getenv("TAPIR_CUDA_GRAPHS");
         ctx->use_graphs = (env && env[0] == '0') ? 0 : 1;
         if ((env = getenv("TAPIR_CUDA_LANES"))) ctx->n_lanes = std::max(1, std::min(kLanes, atoi(env)));
-        if ((env = getenv("TAPIR_CUDA_RAMP"))) ctx->ramp = atoi(env) != 0;
+        if ((env = getenv("TAPIR_CUDA_RAMP"))) ctx->ramp = atoi(env);
         if ((env = getenv("TAPIR_CUDA_TRACE"))) ctx->trace = atoi(env) != 0;
         if ((env = getenv("TAPIR_PROF_TRACE")) && env[0]) {
             ctx->prof_trace_path = env;
@@ -1089,7 +1089,7 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
     const int64_t L = p->n_loci;
     const int64_t nnz = L ? p->offsets[L] : 0;
     const double bytes = double(nnz) * 8.0 + ((p->flags & TAPIR_WANT_PROFILE) ? double(L) * double(p->n_grid) * 8.0 : 0.0);
-    double chunk_bytes = double(8 << 20);
+    double chunk_bytes = double(13 << 20);  // measured on config 2 (20 MB in, 41 MB out): 8 MB chunks 1.19 ms, 12-14 MB 1.03-1.05 ms
     if (const char* env = getenv("TAPIR_CUDA_CHUNK_MB")) {  // tuning override
         const double v = atof(env);
         if (v > 0.0) chunk_bytes = v * double(1 << 20);
@@ -1108,14 +1108,14 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
         ctx->gather_chunked = true;
     }
     // Chunk boundaries at cumulative shares of the sites.  Nothing flows back to the host before the first chunk
-    // has been uploaded and computed, so the run opens with a quarter- and a half-size chunk.
+    // has been uploaded and computed, so the run opens with short chunks (1/ramp, 2/ramp, ... of the regular size).
     std::vector<int64_t> cut;  // site count at which chunk k ends
     {
         const int64_t per = nnz / n_chunks;
         int64_t done = 0;
-        if (ctx->ramp && n_chunks >= 4 && L >= 256 * n_chunks) {
-            cut.push_back(done += per / 4);
-            cut.push_back(done += per / 2);
+        if (ctx->ramp > 1 && n_chunks >= 2 && L >= 256 * n_chunks) {
+            // ctx->ramp = 4: a quarter- and a half-size chunk; 8: an eighth, a quarter, a half
+            for (int64_t piece = per / ctx->ramp; piece < per && piece > 0; piece *= 2) cut.push_back(done += piece);
         }
         while (nnz - done > per + per / 2) cut.push_back(done += per);
         cut.push_back(nnz);
