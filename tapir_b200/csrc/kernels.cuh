@@ -632,8 +632,12 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 3) quad_kernel(const QuadArgs
                     // one copy of the GK21 code, looped over the epochs: the fully unrolled form (4 x ~350
                     // instructions) thrashed the instruction cache once the warps ran out of step (18 % of the
                     // stall samples were instruction fetches)
+                    // (for NE <= 2 the trip count is read from the batch, eb.n == NE: with a compile-time count of 1 or 2
+                    // the compiler flattens the loop and the longer live ranges spill 140-190 bytes -- E = 2: 0.105 ->
+                    // 0.087 ms on config 2)
+                    const int ne = NE <= 2 ? eb.n : NE;
 #pragma unroll 1
-                    for (int e = 0; e < NE; ++e) {
+                    for (int e = 0; e < ne; ++e) {
                         if (eb.new_half[e]) {
                             double D[10], R[10];
                             const double y = cs * eb.half[e];
