@@ -47,7 +47,7 @@ struct QuadItem {      // up to kQuadBlock consecutive sites of one locus
 };
 
 constexpr int kQuadBlock = 256;  // sites per quad item (one warp takes an item)
-constexpr int kEpochsPerLaunch = 4;
+constexpr int kEpochsPerLaunch = 8;
 constexpr int kProfWarps = 4;  // warps per CTA of the profile kernel (warps are autonomous)
 constexpr int kB = 32;         // lo extent of a time tile
 constexpr int kUStride = kB + 2;

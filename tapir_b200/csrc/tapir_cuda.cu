@@ -714,7 +714,11 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
                     case 1: quad_kernel<1><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
                     case 2: quad_kernel<2><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
                     case 3: quad_kernel<3><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
-                    default: quad_kernel<4><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    case 4: quad_kernel<4><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    case 5: quad_kernel<5><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    case 6: quad_kernel<6><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    case 7: quad_kernel<7><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    default: quad_kernel<8><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
                 }
                 CU(ctx, cudaGetLastError());
                 quad_fix_kernel<<<unsigned(ctx->sm_count * 4), 128, 0, sq>>>(qa, eb);
