@@ -48,7 +48,7 @@ struct QuadItem {      // up to kQuadBlock consecutive sites of one locus
 
 constexpr int kQuadBlock = 256;  // sites per quad item (one warp takes an item)
 constexpr int kEpochsPerLaunch = 8;
-constexpr int kProfWarps = 4;  // warps per CTA of the profile kernel (warps are autonomous)
+constexpr int kProfWarps = 1;  // warps per CTA of the profile kernel (warps are autonomous)
 constexpr int kB = 32;         // lo extent of a time tile
 constexpr int kUStride = kB + 2;
 
@@ -87,7 +87,7 @@ struct ProfCfg {
     static constexpr int WarpDoubles = 32 * (kUStride + WStride) + 64;  // U, W tables + the active-rate queue
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
     // resident 4-warp CTAs per SM the register budget is sized for (shared memory allows 3 / 2 at RH = 4 / 8)
-    static constexpr int MinBlocks = RH >= 8 ? 2 : (RH == 4 ? 3 : 4);
+    static constexpr int MinBlocks = (RH >= 8 ? 2 : (RH == 4 ? 3 : 4)) * 4 / kProfWarps;
 };
 
 __device__ __forceinline__ void st_shared_v2(double* p, double x, double y)
@@ -558,10 +558,10 @@ __device__ __forceinline__ bool gk21_collapsed(const EpochBatch& eb, int e, doub
 //
 // NE = eb.n (0..kEpochsPerLaunch) is a template parameter so that the per-site computation is one straight-line
 // block the scheduler can interleave (the NE exponentials of the common factors in particular).
-constexpr int kQuadWarps = 4;  // warps per CTA
+constexpr int kQuadWarps = 1;  // warps per CTA
 
 template <int NE>
-__global__ void __launch_bounds__(kQuadWarps * 32, 3) quad_kernel(const QuadArgs args, const EpochBatch eb)
+__global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(const QuadArgs args, const EpochBatch eb)
 {
     constexpr int NA = NE > 0 ? 2 * NE : 1;
     __shared__ double s_q[kQuadWarps][64];                 // queue of active rates

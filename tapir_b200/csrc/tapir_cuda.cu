@@ -396,7 +396,7 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         if ((env = getenv("TAPIR_CUDA_TRACE"))) ctx->trace = atoi(env) != 0;
         if ((env = getenv("TAPIR_PROF_TRACE")) && env[0]) {
             ctx->prof_trace_path = env;
-            ctx->prof_trace_words = size_t(prop.multiProcessorCount) * 4 * kProfWarps * 32;
+            ctx->prof_trace_words = size_t(prop.multiProcessorCount) * 16 * 32;
             if (cudaMalloc(&ctx->prof_trace, ctx->prof_trace_words * 8) != cudaSuccess) ctx->prof_trace = nullptr;
             else cudaMemset(ctx->prof_trace, 0, ctx->prof_trace_words * 8);
             ctx->use_graphs = 0;
@@ -703,10 +703,10 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
                 qa.queue = ln.d_counter.as<uint32_t>() + 2 + 2 * k;
                 ++k;
                 const int64_t want = (plan.n_quad_items + kQuadWarps - 1) / kQuadWarps;
-                int q_per_sm = 3;
+                int q_per_sm = 12 / kQuadWarps;  // 12 warps per SM (168 registers)
                 if (const char* env = getenv("TAPIR_QUAD_CTAS_PER_SM")) {  // tuning override
                     const int v = atoi(env);
-                    if (v >= 1 && v <= 3) q_per_sm = v;
+                    if (v >= 1 && v <= q_per_sm) q_per_sm = v;
                 }
                 const unsigned qgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(ctx->sm_count) * q_per_sm)));
                 switch (eb.n) {
