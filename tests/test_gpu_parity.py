@@ -191,12 +191,13 @@ def test_edge_cases(eng):
     assert np.array_equal(res.pi_times[:, 0], res.pi_net[:, 99]) and np.array_equal(res.pi_times[:, 1], res.pi_net[:, 0])
 
 
-def test_many_epochs_and_mixed_widths(eng):
+@pytest.mark.parametrize("n_epochs", [6, 7, 8, 19])   # one launch of 6, 7, 8 epochs; 19 = 8 + 8 + 3
+def test_many_epochs_and_mixed_widths(eng, n_epochs):
     from oracle import capi
     rng = np.random.default_rng(5)
     rates = np.concatenate([rng.gamma(0.5, 0.004, 400), [0.3, 1.5, 4.0]])
     off = np.array([0, rates.size], dtype=np.int64)
-    epochs = [[i, i + w] for i, w in zip(range(0, 170, 9), [10, 3, 10, 25, 7] * 4)]
+    epochs = [[i, i + w] for i, w in zip(range(0, 170, 9), [10, 3, 10, 25, 7] * 4)][:n_epochs]
     res = eng.run(off, rates, 50, [1], epochs, want_profile=False)
     assert res.pi_net is None
     si, se, _ = capi.epochs(rates, epochs)
