@@ -51,6 +51,17 @@ __device__ __constant__ double c_dlx[10] = {0.01164385095729883,  -0.03322305065
                                             0.07271400573536937,  -0.07453068863786105,  0.06949599071580352, -0.05831660161169685,
                                             0.04203221728258857,  -0.022001412023543238};
 
+// Power series of the Kronrod pair sums in y = c h (quad_kernel's slow-site branch, y x_0 log2(e) < 1/2):
+//   wgk_10 + sum_j wgk_j (e^{y x_j} + e^{-y x_j})  = sum_n c_ak[n] y^{2n},     c_ak[n] = (2 sum_j wgk_j x_j^{2n} [+ wgk_10]) / (2n)!
+//   sum_j wgk_j x_j (e^{y x_j} - e^{-y x_j})       = sum_n c_bk[n] y^{2n+1},   c_bk[n] = 2 sum_j wgk_j x_j^{2n+2} / (2n+1)!
+// (the rule's moments, 80-digit decimal arithmetic on the doubles above; they agree with the moments of dx on [-1,1],
+// 2/(2n+1), to the last bit or two -- the rule is exact far beyond degree 14).  Seven terms: truncation < 3e-19 at
+// the largest y of the branch.
+__device__ __constant__ double c_ak[7] = {2.0, 0.33333333333333337, 0.016666666666666666, 0.0003968253968253969,
+                                          5.511463844797179e-06, 5.010421677088345e-08, 3.2118087673643237e-10};
+__device__ __constant__ double c_bk[7] = {0.6666666666666667, 0.06666666666666667, 0.002380952380952381, 4.4091710758377435e-05,
+                                          5.010421677088345e-07, 3.854170520837188e-09, 2.1412058449095492e-11};
+
 // Host copies of the abscissae (the host precomputes centre -/+ h*x_j per epoch).
 static const double h_xgk[10] = {
     0.995657163025808080735527280689003, 0.973906528517171720077964012084452,

@@ -502,8 +502,34 @@ __device__ __forceinline__ bool gk21_shared_exp(const EpochBatch& eb, int e, dou
 // the node-by-node sum by rounding only (a different association, ~1e-16 relative).
 struct PanelSums {
     double Ak, Bk, dA, dB;
+    double e0rel;           // series branch: bound of |resk - resg| / resk that stands in for dA, dB (else 0)
     double D4, R4, D5, R5;  // the two node pairs the proof looks at
 };
+
+// Slow sites (y x_0 log2(e) < 1/2 for the whole warp, the bulk of UCE-like rates): the pair sums are entire
+// functions of y with known series (c_ak, c_bk: the rule's moments), seven terms each, so the ten exponential pairs
+// are not formed at all -- only the two pairs the floor proof looks at.  resk - resg is then not computed: in exact
+// arithmetic it is below 1e-27 resk here (Kronrod and Gauss both integrate the polynomial part exactly), and what
+// dqk21 sees is the rounding noise of its two sums, at most ~25 eps resk; the proof runs with the bound 32 eps resk
+// (it then needs resasc > 2.3e-8 resk, which only an integrand flat to eight digits across the epoch misses --
+// the warp then takes the node-by-node path like any other unproved case).
+__device__ __forceinline__ void panel_sums_series(double h, double y, PanelSums& ps)
+{
+    const double s = y * y;
+    double pa = c_ak[6], pb = c_bk[6];
+#pragma unroll
+    for (int n = 5; n >= 0; --n) {
+        pa = fma(pa, s, c_ak[n]);
+        pb = fma(pb, s, c_bk[n]);
+    }
+    ps.Ak = pa;
+    ps.Bk = (pb * y) * h;
+    ps.dA = 0.0;
+    ps.dB = 0.0;
+    ps.e0rel = 32.0 * kEpmach;
+    exp_pm_small(y * c_xgk[4], ps.D4, ps.R4);
+    exp_pm_small(y * c_xgk[5], ps.D5, ps.R5);
+}
 
 __device__ __forceinline__ void panel_sums(double h, const double (&D)[10], const double (&R)[10], PanelSums& ps)
 {
@@ -523,6 +549,7 @@ __device__ __forceinline__ void panel_sums(double h, const double (&D)[10], cons
     ps.Bk = (bk0 + bk1) * h;
     ps.dA = da0 + da1;
     ps.dB = (db0 + db1) * h;
+    ps.e0rel = 0.0;
     ps.D4 = D[4]; ps.R4 = R[4]; ps.D5 = D[5]; ps.R5 = R[5];
 }
 
@@ -531,7 +558,7 @@ __device__ __forceinline__ bool gk21_collapsed(const EpochBatch& eb, int e, doub
 {
     const double fc = eb.center[e];
     const double resk = fma(fc, ps.Ak, -ps.Bk);
-    const double e0 = fabs(fma(fc, ps.dA, -ps.dB));
+    const double e0 = fma(ps.e0rel, resk, fabs(fma(fc, ps.dA, -ps.dB)));
     const double reskh = resk * 0.5;
     const double unit = __hiloint2double((2046 - ((__double2hiint(resk) >> 20) & 0x7ff)) << 20, 0);  // ~ 1 / resk
     const double n = (200.0 * e0) * unit, fl = ((kEpmach * 50.0) * resk) * unit;
@@ -641,16 +668,15 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
                         if (eb.new_half[e]) {
                             double D[10], R[10];
                             const double y = cs * eb.half[e];
-                            // slow sites (the bulk of UCE-like data): every y x_j is below ln(2)/2, where the range
-                            // reduction is the identity -- same bits without it (x_0 log2 e = 1.4364...)
+                            // slow sites (the bulk of UCE-like data), every y x_j below ln(2)/2 (x_0 log2 e = 1.4364...):
+                            // the sums from their power series, no node tables
                             if (__all_sync(0xffffffffu, y * 1.4365 < 0.4999)) {
-#pragma unroll
-                                for (int j = 0; j < 10; ++j) exp_pm_small(y * c_xgk[j], D[j], R[j]);
+                                panel_sums_series(eb.half[e], y, ps);
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
+                                panel_sums(eb.half[e], D, R, ps);
                             }
-                            panel_sums(eb.half[e], D, R, ps);
                         }
                         // common factor a e^{-c centre} h; |c * centre| <= 600 on this path
                         const double scale = (as * exp_bounded(-(cs * eb.center[e]))) * eb.half[e];
