@@ -382,6 +382,403 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
     }
 }
 
+
+// finite, and 16 r^2 neither 0 nor Inf -- decided on the bit pattern: 16*(r*r) == 0 up to |r| = 0x1e56a09e667f3bcc
+// (1.57e-162) and is finite up to |r| = 0x5fcfffffffffffff (3.35e153); NaN and Inf compare above both
+__device__ __forceinline__ bool rate_is_active(double r)
+{
+    // on the two 32-bit halves, so that no part of the test is scheduled on the FP64 pipe
+    const uint32_t hi = uint32_t(__double2hiint(r)) & 0x7fffffffu, lo = uint32_t(__double2loint(r));
+    const bool above = hi > 0x1e56a09eu || (hi == 0x1e56a09eu && lo > 0x667f3bccu);
+    return above && hi <= 0x5fcfffffu;
+}
+
+// ------------------------------------------------------------------------------------------
+// PI profile
+// ------------------------------------------------------------------------------------------
+// power tables of one group: lane = site; rows of lanes >= cnt are U = 0, W = 1 (they add exactly 0)
+template <int RH>
+__device__ __forceinline__ void prof_build_tables(double lam, bool ok, int64_t T0, double t0d, double* myU, double* myW)
+{
+    constexpr int H = 8 * RH;
+    double a = 16.0 * (lam * lam);
+    const double c = ok ? 4.0 * lam : 0.0;
+    a = ok ? a : 0.0;
+    const double q = exp_full(-c);
+    const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
+    const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
+    const double qB = q16 * q16;  // q^32
+    double xa = u0, xb = u0 * q16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        st_shared_v2(myU + 2 * k, xa, xa * q);
+        st_shared_v2(myU + 16 + 2 * k, xb, xb * q);
+        xa *= q2;
+        xb *= q2;
+    }
+    if constexpr (RH >= 2) {
+        const double qB2 = qB * qB;
+        double qBh = qB2;  // -> qB^(H/2)
+#pragma unroll
+        for (int k = 2; k < H / 2; k *= 2) qBh *= qBh;
+        double wa = 1.0, wb = qBh;
+#pragma unroll
+        for (int k = 0; k < H / 4; ++k) {
+            st_shared_v2(myW + 2 * k, wa, wa * qB);
+            st_shared_v2(myW + H / 2 + 2 * k, wb, wb * qB);
+            wa *= qB2;
+            wb *= qB2;
+        }
+    } else {
+        const double qB2 = qB * qB;
+        double wa = 1.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            st_shared_v2(myW + 2 * k, wa, wa * qB);
+            wa *= qB2;
+        }
+    }
+}
+
+// acc(lo,hi) += sum_s U[s][lo] * W[s][hi] over nk k-steps of 4 sites
+template <int RH>
+__device__ __forceinline__ void prof_contract(double (&acc)[4][RH][2], const double* fragU, const double* fragW, int nk)
+{
+    constexpr int WS = ProfCfg<RH>::WStride, US = kUStride;
+    auto fetch = [&](double (&a)[4], double (&b)[RH], int step) {
+        const double* up = fragU + step * (4 * US);
+        const double* wp = fragW + step * (4 * WS);
+        const double2 u01 = *reinterpret_cast<const double2*>(up);
+        const double2 u23 = *reinterpret_cast<const double2*>(up + 2);
+        a[0] = u01.x; a[1] = u01.y; a[2] = u23.x; a[3] = u23.y;
+        if constexpr (RH == 1) {
+            b[0] = wp[0];
+        } else {
+#pragma unroll
+            for (int r = 0; r < RH / 2; ++r) {
+                const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
+                b[2 * r] = v.x; b[2 * r + 1] = v.y;
+            }
+        }
+    };
+    auto mma_step = [&](const double (&a)[4], const double (&b)[RH]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < RH; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    };
+    double a0[4], b0[RH], a1[4], b1[RH];
+    fetch(a0, b0, 0);
+    for (int s = 0; s < nk; s += 2) {
+        fetch(a1, b1, s + 1);
+        mma_step(a0, b0);
+        fetch(a0, b0, min(s + 2, 7));
+        mma_step(a1, b1);
+    }
+}
+
+// one item's accumulators -> pi_net (times t) and the tile maximum, or the split workspace
+template <int RH>
+__device__ __forceinline__ void prof_epilogue(const ProfArgs& args, const double (&acc)[4][RH][2], int locus, int tile, int slot,
+                                              int lane)
+{
+    constexpr int TT = ProfCfg<RH>::TT;
+    const int fk = lane & 3, fg = lane >> 2;
+    const int64_t T0 = int64_t(tile) * TT;
+    const double t0d = double(T0);
+    const int lo0 = 4 * chunk_pair(fg);
+    if (slot >= 0) {
+        double* out = args.ws + size_t(slot) * TT;
+#pragma unroll
+        for (int j = 0; j < RH; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
+                double* o = out + hi * 32 + lo0;
+                *reinterpret_cast<double2*>(o) = make_double2(acc[0][j][c], acc[1][j][c]);
+                *reinterpret_cast<double2*>(o + 2) = make_double2(acc[2][j][c], acc[3][j][c]);
+            }
+        return;
+    }
+    const int64_t row = int64_t(locus) * args.T;
+    double* out = args.pi_net + row;
+    const bool vec_ok = ((row & 1) == 0);
+    long long best_bits = -1;
+    int best_i = 0;
+    const int64_t t_left = args.T - T0;
+    const int t_end = int(t_left < int64_t(TT) ? t_left : int64_t(TT));
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < RH; ++j) {
+            const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
+            const int o = hi * 32 + lo0;
+            const double td = t0d + double(o);
+            double v[4];
+            v[0] = acc[0][j][c] * td;
+            v[1] = acc[1][j][c] * (td + 1.0);
+            v[2] = acc[2][j][c] * (td + 2.0);
+            v[3] = acc[3][j][c] * (td + 3.0);
+            double* dst = out + T0 + o;
+            if (o + 3 < t_end && vec_ok) {
+                *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+                *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (o + i < t_end) dst[i] = v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long bits = __double_as_longlong(v[i]);
+                if (o + i < t_end && bits > best_bits) {
+                    best_bits = bits;
+                    best_i = o + i;
+                }
+            }
+        }
+    int64_t best_t = T0 + best_i;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const long long ob = __shfl_xor_sync(0xffffffffu, best_bits, off);
+        const int64_t ot = __shfl_xor_sync(0xffffffffu, best_t, off);
+        if (ob > best_bits || (ob == best_bits && ot < best_t)) { best_bits = ob; best_t = ot; }
+    }
+    if (lane == 0) {
+        const int64_t k = int64_t(locus) * args.n_tiles + tile;
+        args.tile_max[k] = __longlong_as_double(best_bits);
+        args.tile_arg[k] = best_t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PI profile, moment form: slow sites cost half the DMMAs
+// ------------------------------------------------------------------------------------------
+// Inside a 32-point block of the time tile, t = T0 + 32 hi + 16 + d (d = lo - 16), a slowly decaying site is a
+// polynomial in d:  a q^t = [a e^{-c T0}] [q^{32 hi + 16}] e^{-c d},  e^{-c d} = sum_k (-16 c)^k / k! (d/16)^k.
+// For 16 c <= 1.25 (rate <= 0.0195: 99.8 % of the active sites of UCE-like data) sixteen terms leave a remainder
+// below 2e-12 of the term, so the site is represented by 16 moments  U'[k] = a e^{-c T0} (-16 c)^k / k!  instead
+// of 32 powers q^lo, the contraction over sites
+//        M[k][hi] = sum_s U'[s][k] W'[s][hi],      W'[s][hi] = q^{32 hi + 16}
+// needs 2 x RH instead of 4 x RH DMMAs per four sites, and one small product per item turns moments back into times:
+//        out[lo][hi] = sum_k ((lo - 16)/16)^k M[k][hi]        (64 DMMAs for RH = 4, against ~1400 for the sites).
+// The few faster sites of the item are then added by the power-table contraction of profile_kernel (second pass
+// over the item's rates, skipped when there is none) on top of the transformed accumulators, and the epilogue is
+// profile_kernel's.  All arithmetic is IEEE double; the result differs from profile_kernel's by the series
+// remainder and a different association of the same sums (observed <= 1e-13 relative).
+constexpr int kMomStride = 18;  // doubles per moment row (16 + 2: rows 144 bytes apart, conflict-free 16-byte fragments)
+
+// a slow site: 16 c = 64 r <= 1.25, i.e. r < 0x3F94000000000000 (0.01953125), r >= 0 -- on the bit pattern
+__device__ __forceinline__ bool rate_is_slow(double r) { return uint32_t(__double2hiint(r)) < 0x3F940000u; }
+
+template <int RH>
+__global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profile_mom_kernel(const ProfArgs args)
+{
+    using Cfg = ProfCfg<RH>;
+    constexpr int H = Cfg::H, TT = Cfg::TT, WS = Cfg::WStride, US = kUStride, MS = kMomStride;
+    static_assert(RH >= 2, "moment form: tiles of 512 points or more");
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int fk = lane & 3, fg = lane >> 2;
+    double* Us = smem + size_t(warp) * Cfg::WarpDoubles;
+    double* Ws = Us + 32 * US;
+    double* Qs = Ws + 32 * WS;
+    double* myU = Us + lane * US;
+    double* myM = Us + lane * MS;
+    double* myW = Ws + lane * WS;
+    const double* fragU = Us + fk * US + 4 * chunk_pair(fg);
+    const double* fragM = Us + fk * MS + 2 * chunk_quad(fg);
+    const double* fragW = Ws + fk * WS + RH * w_chunk<RH>(fg);
+
+    for (;;) {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(args.counter, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= uint32_t(args.n_items)) break;
+        const ProfItem item = args.items[it];
+        const int64_t T0 = int64_t(item.tile) * TT;
+        const double t0d = double(T0);
+        const double* rp = args.rates + item.site_begin;
+
+        // ---------------- pass 1: slow sites in moment form ----------------
+        // accM[i][j][c]: moment = 2 chunk_quad(fg) + i, hi = RH w_chunk(2 fk + c) + j
+        double accM[2][RH][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < RH; ++j) accM[i][j][0] = accM[i][j][1] = 0.0;
+        int n_fast = 0;
+        {
+            int qh = 0, qn = 0;
+            double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
+            double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
+            for (int base = 0;; base += 32) {
+                const bool more = base < item.n_sites;
+                if (more) {
+                    const double lam_new = lam_in;
+                    lam_in = lam_in2;
+                    {
+                        const int nb = base + 64 + lane;
+                        lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                    }
+                    const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
+                    const bool slow = act && rate_is_slow(lam_new);
+                    const unsigned ballot = __ballot_sync(0xffffffffu, slow);
+                    n_fast += __popc(__ballot_sync(0xffffffffu, act && !slow));
+                    if (slow) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                    qn += __popc(ballot);
+                    __syncwarp();
+                }
+                while (qn - qh >= 32 || (!more && qn > qh)) {
+                    const int cnt = min(32, qn - qh);
+                    const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
+                    qh += cnt;
+                    {
+                        // rows of lanes >= cnt: moments 0, W' = 1
+                        const bool ok = lane < cnt;
+                        const double c = ok ? 4.0 * lam : 0.0;
+                        const double a = ok ? 16.0 * (lam * lam) : 0.0;
+                        const double q = exp_full(-c);
+                        const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
+                        const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
+                        const double qB = q16 * q16, qB2 = qB * qB;
+                        double qBh = qB2;  // -> qB^(H/2)
+#pragma unroll
+                        for (int k = 2; k < H / 2; k *= 2) qBh *= qBh;
+                        // moments u0 z^k / k!, z = -16 c: even and odd chains
+                        const double z = -16.0 * c, z2 = z * z;
+                        double me = u0, mo = u0 * z;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            st_shared_v2(myM + 2 * k, me, mo);
+                            me *= z2 * (1.0 / double((2 * k + 1) * (2 * k + 2)));
+                            mo *= z2 * (1.0 / double((2 * k + 2) * (2 * k + 3)));
+                        }
+                        // W'[hi] = q^16 (q^32)^hi
+                        double wa = q16, wb = q16 * qBh;
+#pragma unroll
+                        for (int k = 0; k < H / 4; ++k) {
+                            st_shared_v2(myW + 2 * k, wa, wa * qB);
+                            st_shared_v2(myW + H / 2 + 2 * k, wb, wb * qB);
+                            wa *= qB2;
+                            wb *= qB2;
+                        }
+                    }
+                    __syncwarp();
+                    {
+                        auto fetch = [&](double (&a)[2], double (&b)[RH], int step) {
+                            const double2 m01 = *reinterpret_cast<const double2*>(fragM + step * (4 * MS));
+                            a[0] = m01.x; a[1] = m01.y;
+                            const double* wp = fragW + step * (4 * WS);
+#pragma unroll
+                            for (int r = 0; r < RH / 2; ++r) {
+                                const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
+                                b[2 * r] = v.x; b[2 * r + 1] = v.y;
+                            }
+                        };
+                        auto mma_step = [&](const double (&a)[2], const double (&b)[RH]) {
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                for (int j = 0; j < RH; ++j) dmma884(accM[i][j][0], accM[i][j][1], a[i], b[j]);
+                        };
+                        const int nk = (cnt + 3) >> 2;
+                        double a0[2], b0[RH], a1[2], b1[RH];
+                        fetch(a0, b0, 0);
+                        for (int s = 0; s < nk; s += 2) {
+                            fetch(a1, b1, s + 1);
+                            mma_step(a0, b0);
+                            fetch(a0, b0, min(s + 2, 7));
+                            mma_step(a1, b1);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (!more) break;
+            }
+        }
+
+        // ---------------- moments -> times: acc[lo][hi] = sum_k ((lo - 16)/16)^k M[k][hi] ----------------
+        double acc[4][RH][2];
+        {
+            double* Ms = Us;  // [16][WS], the table area is free now
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < RH; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        Ms[(2 * chunk_quad(fg) + i) * WS + RH * w_chunk<RH>(2 * fk + c) + j] = accM[i][j][c];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < RH; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            // this lane's A fragment of step ks is x_i^(4 ks + fk), x_i = (lo_i - 16) / 16 (exact)
+            double pw[4], x4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double x = double(4 * chunk_pair(fg) + i - 16) * 0.0625;
+                const double xx = x * x;
+                pw[i] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;
+                x4[i] = xx * xx;
+            }
+            const double* mrow = Ms + fk * WS + RH * w_chunk<RH>(fg);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                double b[RH];
+#pragma unroll
+                for (int r = 0; r < RH / 2; ++r) {
+                    const double2 v = *reinterpret_cast<const double2*>(mrow + ks * (4 * WS) + 2 * r);
+                    b[2 * r] = v.x; b[2 * r + 1] = v.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int j = 0; j < RH; ++j) dmma884(acc[i][j][0], acc[i][j][1], pw[i], b[j]);
+                    pw[i] *= x4[i];
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---------------- pass 2: the item's fast sites, power tables as in profile_kernel ----------------
+        if (n_fast > 0) {
+            int qh = 0, qn = 0;
+            double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
+            double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
+            for (int base = 0;; base += 32) {
+                const bool more = base < item.n_sites;
+                if (more) {
+                    const double lam_new = lam_in;
+                    lam_in = lam_in2;
+                    {
+                        const int nb = base + 64 + lane;
+                        lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                    }
+                    const bool fast = rate_is_active(lam_new) && !rate_is_slow(lam_new);
+                    const unsigned ballot = __ballot_sync(0xffffffffu, fast);
+                    if (fast) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                    qn += __popc(ballot);
+                    __syncwarp();
+                }
+                while (qn - qh >= 32 || (!more && qn > qh)) {
+                    const int cnt = min(32, qn - qh);
+                    const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
+                    qh += cnt;
+                    prof_build_tables<RH>(lam, lane < cnt, T0, t0d, myU, myW);
+                    __syncwarp();
+                    prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2);
+                    __syncwarp();
+                }
+                if (!more) break;
+            }
+        }
+        prof_epilogue<RH>(args, acc, item.locus, item.tile, item.slot, lane);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // epoch integrals
 // ------------------------------------------------------------------------------------------

@@ -139,6 +139,7 @@ struct tapir_cuda_ctx {
     long long* prof_trace = nullptr;  // TAPIR_PROF_TRACE=<file>: per-warp time stamps of profile_kernel, dumped by tapir_cuda_compute
     size_t prof_trace_words = 0;
     std::string prof_trace_path;
+    int prof_mom = 1;        // tiles of 512+ points use profile_mom_kernel (slow sites in moment form); TAPIR_PROF_MOM=0: profile_kernel
     int trace = 0;           // TAPIR_CUDA_TRACE=1: tapir_cuda_run prints the timeline of its chunks to stderr
     std::string last_error;
     Lane lanes[kLanes];
@@ -250,6 +251,18 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
         }
         profile_kernel<RH, true><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
         return cudaGetLastError();
+    }
+    if constexpr (RH >= 2) {
+        if (ctx->prof_mom) {  // moment form (same grid, same shared memory)
+            static bool mom_configured[64] = {false};
+            if (!mom_configured[ctx->device & 63]) {
+                e = cudaFuncSetAttribute(profile_mom_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
+                if (e != cudaSuccess) return e;
+                mom_configured[ctx->device & 63] = true;
+            }
+            profile_mom_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
+            return cudaGetLastError();
+        }
     }
     profile_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
     return cudaGetLastError();
@@ -394,6 +407,7 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         if ((env = getenv("TAPIR_CUDA_LANES"))) ctx->n_lanes = std::max(1, std::min(kLanes, atoi(env)));
         if ((env = getenv("TAPIR_CUDA_RAMP"))) ctx->ramp = atoi(env);
         if ((env = getenv("TAPIR_CUDA_TRACE"))) ctx->trace = atoi(env) != 0;
+        if ((env = getenv("TAPIR_PROF_MOM"))) ctx->prof_mom = atoi(env) != 0;
         if ((env = getenv("TAPIR_PROF_TRACE")) && env[0]) {
             ctx->prof_trace_path = env;
             ctx->prof_trace_words = size_t(prop.multiProcessorCount) * 16 * 32;
