@@ -570,13 +570,15 @@ constexpr int kMomStride = 18;  // doubles per moment row (16 + 2: rows 144 byte
 
 // a slow site: 16 c = 64 r <= 1.25, i.e. r < 0x3F94000000000000 (0.01953125), r >= 0 -- on the bit pattern
 __device__ __forceinline__ bool rate_is_slow(double r) { return uint32_t(__double2hiint(r)) < 0x3F940000u; }
+// a very slow site: 64 c = 256 r <= 1.25, r < 0x3F74000000000000 (0.0048828125): sixteen moments per 128-point block
+__device__ __forceinline__ bool rate_is_very_slow(double r) { return uint32_t(__double2hiint(r)) < 0x3F740000u; }
 
 template <int RH>
 __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profile_mom_kernel(const ProfArgs args)
 {
     using Cfg = ProfCfg<RH>;
     constexpr int H = Cfg::H, TT = Cfg::TT, WS = Cfg::WStride, US = kUStride, MS = kMomStride;
-    static_assert(RH >= 2, "moment form: tiles of 512 points or more");
+    static_assert(RH >= 4, "moment form: tiles of 1024 points or more");
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -601,15 +603,20 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
         const double t0d = double(T0);
         const double* rp = args.rates + item.site_begin;
 
-        // ---------------- pass 1: slow sites in moment form ----------------
-        // accM[i][j][c]: moment = 2 chunk_quad(fg) + i, hi = RH w_chunk(2 fk + c) + j
-        double accM[2][RH][2];
+        // ---------------- pass A: very slow sites, sixteen moments per 128-point block ----------------
+        // t = T0 + 128 hb + 64 + d:  a q^t = [a e^{-c T0}] [q^{128 hb + 64}] sum_k (-64 c)^k / k! (d/64)^k, so the
+        // site meets only NB = TT/128 columns: 2 x NT DMMAs per four sites (NT = NB/8), an eighth of profile_kernel's.
+        constexpr int NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
+        double accA[2][NT][2];
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < RH; ++j) accM[i][j][0] = accM[i][j][1] = 0.0;
-        int n_fast = 0;
+            for (int j = 0; j < NT; ++j) accA[i][j][0] = accA[i][j][1] = 0.0;
+        int n_mid = 0, n_fast = 0;  // slow but not very slow; neither
         {
+            double* WAs = Us + 32 * MS;  // W' of this pass: [32][WA]
+            double* myWA = WAs + lane * WA;
+            const double* fragWA = WAs + fk * WA + NT * w_chunk<NT>(fg);
             int qh = 0, qn = 0;
             double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
             double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
@@ -623,9 +630,151 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                         lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
                     }
                     const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
+                    const bool vslow = act && rate_is_very_slow(lam_new);
                     const bool slow = act && rate_is_slow(lam_new);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, slow);
+                    const unsigned ballot = __ballot_sync(0xffffffffu, vslow);
+                    n_mid += __popc(__ballot_sync(0xffffffffu, slow && !vslow));
                     n_fast += __popc(__ballot_sync(0xffffffffu, act && !slow));
+                    if (vslow) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                    qn += __popc(ballot);
+                    __syncwarp();
+                }
+                while (qn - qh >= 32 || (!more && qn > qh)) {
+                    const int cnt = min(32, qn - qh);
+                    const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
+                    qh += cnt;
+                    {
+                        const bool ok = lane < cnt;
+                        const double c = ok ? 4.0 * lam : 0.0;
+                        const double a = ok ? 16.0 * (lam * lam) : 0.0;
+                        const double q = exp_full(-c);
+                        const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
+                        const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
+                        const double q32 = q16 * q16, q64 = q32 * q32, q128 = q64 * q64, q256 = q128 * q128;
+                        const double z = -64.0 * c, z2 = z * z;
+                        double me = u0, mo = u0 * z;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            st_shared_v2(myM + 2 * k, me, mo);
+                            me *= z2 * (1.0 / double((2 * k + 1) * (2 * k + 2)));
+                            mo *= z2 * (1.0 / double((2 * k + 2) * (2 * k + 3)));
+                        }
+                        // W'[hb] = q^64 (q^128)^hb
+                        double w = q64;
+#pragma unroll
+                        for (int k = 0; k < NB / 2; ++k) {
+                            st_shared_v2(myWA + 2 * k, w, w * q128);
+                            w *= q256;
+                        }
+                    }
+                    __syncwarp();
+                    {
+                        auto fetch = [&](double (&a)[2], double (&b)[NT], int step) {
+                            const double2 m01 = *reinterpret_cast<const double2*>(fragM + step * (4 * MS));
+                            a[0] = m01.x; a[1] = m01.y;
+                            const double* wp = fragWA + step * (4 * WA);
+                            if constexpr (NT == 1) {
+                                b[0] = wp[0];
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < NT / 2; ++r) {
+                                    const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
+                                    b[2 * r] = v.x; b[2 * r + 1] = v.y;
+                                }
+                            }
+                        };
+                        const int nk = (cnt + 3) >> 2;
+                        double a0[2], b0[NT];
+                        for (int st = 0; st < nk; ++st) {
+                            fetch(a0, b0, st);
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) dmma884(accA[i][j][0], accA[i][j][1], a0[i], b0[j]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (!more) break;
+            }
+        }
+
+        // ---------------- A moments -> times, natural layout [128 hb + t], then into the accumulator layout ----------------
+        double acc[4][RH][2];
+        {
+            constexpr int SA = NB + 4;
+            double* MA = Us;         // [16][SA]
+            double* lin = Us + 512;  // [TT]
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        MA[(2 * chunk_quad(fg) + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c];
+            __syncwarp();
+            double bf[4][NT];  // B fragments: M[4 ks + fk][8 nt + fg]
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bf[ks][nt] = MA[(4 * ks + fk) * SA + 8 * nt + fg];
+#pragma unroll 2
+            for (int mt = 0; mt < 16; ++mt) {
+                // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact)
+                const double x = double(8 * mt + fg - 64) * 0.015625;
+                const double xx = x * x, x4 = xx * xx;
+                double pw = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;
+                double d[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) d[nt][0] = d[nt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dmma884(d[nt][0], d[nt][1], pw, bf[ks][nt]);
+                    pw *= x4;
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) lin[128 * (8 * nt + 2 * fk + c) + 8 * mt + fg] = d[nt][c];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < RH; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
+                    const double* src = lin + 32 * hi + 4 * chunk_pair(fg);
+                    const double2 v01 = *reinterpret_cast<const double2*>(src);
+                    const double2 v23 = *reinterpret_cast<const double2*>(src + 2);
+                    acc[0][j][c] = v01.x; acc[1][j][c] = v01.y; acc[2][j][c] = v23.x; acc[3][j][c] = v23.y;
+                }
+            __syncwarp();
+        }
+
+        // ---------------- pass C: slow (not very slow) sites, sixteen moments per 32-point block ----------------
+        // accM[i][j][c]: moment = 2 chunk_quad(fg) + i, hi = RH w_chunk(2 fk + c) + j
+        if (n_mid > 0) {
+        double accM[2][RH][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < RH; ++j) accM[i][j][0] = accM[i][j][1] = 0.0;
+        {
+            int qh = 0, qn = 0;
+            double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
+            double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
+            for (int base = 0;; base += 32) {
+                const bool more = base < item.n_sites;
+                if (more) {
+                    const double lam_new = lam_in;
+                    lam_in = lam_in2;
+                    {
+                        const int nb = base + 64 + lane;
+                        lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                    }
+                    const bool slow = rate_is_active(lam_new) && rate_is_slow(lam_new) && !rate_is_very_slow(lam_new);
+                    const unsigned ballot = __ballot_sync(0xffffffffu, slow);
                     if (slow) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
                     qn += __popc(ballot);
                     __syncwarp();
@@ -699,8 +848,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
             }
         }
 
-        // ---------------- moments -> times: acc[lo][hi] = sum_k ((lo - 16)/16)^k M[k][hi] ----------------
-        double acc[4][RH][2];
+        // ---------------- C moments -> times: acc[lo][hi] += sum_k ((lo - 16)/16)^k M[k][hi] ----------------
         {
             double* Ms = Us;  // [16][WS], the table area is free now
 #pragma unroll
@@ -711,10 +859,6 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                     for (int c = 0; c < 2; ++c)
                         Ms[(2 * chunk_quad(fg) + i) * WS + RH * w_chunk<RH>(2 * fk + c) + j] = accM[i][j][c];
             __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < RH; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
             // this lane's A fragment of step ks is x_i^(4 ks + fk), x_i = (lo_i - 16) / 16 (exact)
             double pw[4], x4[4];
 #pragma unroll
@@ -742,6 +886,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
             }
             __syncwarp();
         }
+        }  // n_mid > 0
 
         // ---------------- pass 2: the item's fast sites, power tables as in profile_kernel ----------------
         if (n_fast > 0) {

@@ -139,7 +139,7 @@ struct tapir_cuda_ctx {
     long long* prof_trace = nullptr;  // TAPIR_PROF_TRACE=<file>: per-warp time stamps of profile_kernel, dumped by tapir_cuda_compute
     size_t prof_trace_words = 0;
     std::string prof_trace_path;
-    int prof_mom = 1;        // tiles of 512+ points use profile_mom_kernel (slow sites in moment form); TAPIR_PROF_MOM=0: profile_kernel
+    int prof_mom = 1;        // tiles of 1024+ points use profile_mom_kernel (slow sites in moment form); TAPIR_PROF_MOM=0: profile_kernel
     int trace = 0;           // TAPIR_CUDA_TRACE=1: tapir_cuda_run prints the timeline of its chunks to stderr
     std::string last_error;
     Lane lanes[kLanes];
@@ -252,7 +252,7 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
         profile_kernel<RH, true><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
         return cudaGetLastError();
     }
-    if constexpr (RH >= 2) {
+    if constexpr (RH >= 4) {
         if (ctx->prof_mom) {  // moment form (same grid, same shared memory)
             static bool mom_configured[64] = {false};
             if (!mom_configured[ctx->device & 63]) {
