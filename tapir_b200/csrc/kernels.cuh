@@ -552,33 +552,36 @@ __device__ __forceinline__ void prof_epilogue(const ProfArgs& args, const double
 }
 
 // ------------------------------------------------------------------------------------------
-// PI profile, moment form: slow sites cost half the DMMAs
+// PI profile, moment form
 // ------------------------------------------------------------------------------------------
-// Inside a 32-point block of the time tile, t = T0 + 32 hi + 16 + d (d = lo - 16), a slowly decaying site is a
-// polynomial in d:  a q^t = [a e^{-c T0}] [q^{32 hi + 16}] e^{-c d},  e^{-c d} = sum_k (-16 c)^k / k! (d/16)^k.
-// For 16 c <= 1.25 (rate <= 0.0195: 99.8 % of the active sites of UCE-like data) sixteen terms leave a remainder
-// below 2e-12 of the term, so the site is represented by 16 moments  U'[k] = a e^{-c T0} (-16 c)^k / k!  instead
-// of 32 powers q^lo, the contraction over sites
-//        M[k][hi] = sum_s U'[s][k] W'[s][hi],      W'[s][hi] = q^{32 hi + 16}
-// needs 2 x RH instead of 4 x RH DMMAs per four sites, and one small product per item turns moments back into times:
-//        out[lo][hi] = sum_k ((lo - 16)/16)^k M[k][hi]        (64 DMMAs for RH = 4, against ~1400 for the sites).
-// The few faster sites of the item are then added by the power-table contraction of profile_kernel (second pass
-// over the item's rates, skipped when there is none) on top of the transformed accumulators, and the epilogue is
-// profile_kernel's.  All arithmetic is IEEE double; the result differs from profile_kernel's by the series
-// remainder and a different association of the same sums (observed <= 1e-13 relative).
-constexpr int kMomStride = 18;  // doubles per moment row (16 + 2: rows 144 bytes apart, conflict-free 16-byte fragments)
+// Inside a 128-point block of the time tile, t = T0 + 128 hb + 64 + d, a slowly decaying site is a polynomial in d:
+//   a q^t = [a e^{-c T0}] [q^{128 hb + 64}] e^{-c d},      e^{-c d} = sum_k (-64 c)^k / k! (d/64)^k.
+// For 64 c <= 5 (rate < 0.0195: 99.8 % of the active sites of UCE-like data) 32 terms leave a remainder below 1.3e-11
+// of the term (5^32/32! against e^{-5}; the alternating sum loses < 4 digits to cancellation, ~1e-12), so the site is
+// represented by 32 moments  U'[k] = a e^{-c T0} (-64 c)^k / k!  and meets only NB = TT/128 columns
+//   W'[hb] = q^{128 hb + 64}:      M[k][hb] = sum_s U'[s][k] W'[s][hb]      -- 4 x NT DMMAs per four sites (NT = NB/8),
+// a quarter of profile_kernel's 4 x RH (RH = 4 NT), with a W table a quarter as long.  One product per item turns
+// moments back into times,  out[128 hb + t] = sum_k ((t - 64)/64)^k M[k][hb]  (128 NT DMMAs, against ~1400 RH/4 for the
+// sites of a 350-site locus), written through shared memory into profile_kernel's accumulator layout.  The few faster
+// sites of the item are then added by profile_kernel's power-table contraction (second pass over the item's rates,
+// skipped when there is none) and the epilogue is profile_kernel's.  All arithmetic is IEEE double; the result differs
+// from profile_kernel's by the series remainder, the cancellation noted above and a different association of the
+// same sums (observed <= 1e-12 relative; the parity gate is 1e-9).
+constexpr int kMomStride = 34;  // doubles per moment row (32 + 2: rows 272 bytes apart, conflict-free 16-byte fragments)
 
-// a slow site: 16 c = 64 r <= 1.25, i.e. r < 0x3F94000000000000 (0.01953125), r >= 0 -- on the bit pattern
+// a slow site: 64 c = 256 r <= 5, i.e. r < 0x3F94000000000000 (0.01953125), r >= 0 -- on the bit pattern
 __device__ __forceinline__ bool rate_is_slow(double r) { return uint32_t(__double2hiint(r)) < 0x3F940000u; }
-// a very slow site: 64 c = 256 r <= 1.25, r < 0x3F74000000000000 (0.0048828125): sixteen moments per 128-point block
-__device__ __forceinline__ bool rate_is_very_slow(double r) { return uint32_t(__double2hiint(r)) < 0x3F740000u; }
 
-template <int RH>
+// TRACE (measurement only): [0] SM id, [1] entry, [12] exit, [13] items done; for the warp's second item
+// [16] claimed, [17] moment pass done, [18] moments -> times done, [19] fast-site pass done, [20] epilogue done,
+// [22] groups of the moment pass, [24] n_fast
+template <int RH, bool TRACE = false>
 __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profile_mom_kernel(const ProfArgs args)
 {
     using Cfg = ProfCfg<RH>;
-    constexpr int H = Cfg::H, TT = Cfg::TT, WS = Cfg::WStride, US = kUStride, MS = kMomStride;
+    constexpr int TT = Cfg::TT, WS = Cfg::WStride, US = kUStride, MS = kMomStride;
     static_assert(RH >= 4, "moment form: tiles of 1024 points or more");
+    constexpr int NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -587,11 +590,32 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
     double* Ws = Us + 32 * US;
     double* Qs = Ws + 32 * WS;
     double* myU = Us + lane * US;
-    double* myM = Us + lane * MS;
     double* myW = Ws + lane * WS;
     const double* fragU = Us + fk * US + 4 * chunk_pair(fg);
-    const double* fragM = Us + fk * MS + 2 * chunk_quad(fg);
     const double* fragW = Ws + fk * WS + RH * w_chunk<RH>(fg);
+    // moment pass: U' [32][MS] where profile_kernel keeps U (same stride), W' [32][WA] behind it
+    double* myM = Us + lane * MS;
+    double* WAs = Us + 32 * MS;
+    double* myWA = WAs + lane * WA;
+    const double* fragM = Us + fk * MS + 4 * chunk_pair(fg);
+    const double* fragWA = WAs + fk * WA + NT * w_chunk<NT>(fg);
+    long long* tr = nullptr;
+    int n_done = 0, n_groups = 0;
+    if constexpr (TRACE) {
+        tr = args.trace + (size_t(blockIdx.x) * kProfWarps + warp) * 32;
+        if (lane == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr[0] = smid;
+            tr[1] = clock64();
+        }
+    }
+    auto stamp = [&](int slot) {
+        if constexpr (TRACE) {
+            __syncwarp();
+            if (lane == 0 && n_done == 1) tr[slot] = clock64();
+        }
+    };
 
     for (;;) {
         uint32_t it = 0;
@@ -602,21 +626,18 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
         const int64_t T0 = int64_t(item.tile) * TT;
         const double t0d = double(T0);
         const double* rp = args.rates + item.site_begin;
+        stamp(16);
+        n_groups = 0;
 
-        // ---------------- pass A: very slow sites, sixteen moments per 128-point block ----------------
-        // t = T0 + 128 hb + 64 + d:  a q^t = [a e^{-c T0}] [q^{128 hb + 64}] sum_k (-64 c)^k / k! (d/64)^k, so the
-        // site meets only NB = TT/128 columns: 2 x NT DMMAs per four sites (NT = NB/8), an eighth of profile_kernel's.
-        constexpr int NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
-        double accA[2][NT][2];
+        // ---------------- moment pass: slow sites ----------------
+        // accA[i][j][c]: moment = 4 chunk_pair(fg) + i, hb = NT w_chunk<NT>(2 fk + c) + j
+        double accA[4][NT][2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < NT; ++j) accA[i][j][0] = accA[i][j][1] = 0.0;
-        int n_mid = 0, n_fast = 0;  // slow but not very slow; neither
+        int n_fast = 0;
         {
-            double* WAs = Us + 32 * MS;  // W' of this pass: [32][WA]
-            double* myWA = WAs + lane * WA;
-            const double* fragWA = WAs + fk * WA + NT * w_chunk<NT>(fg);
             int qh = 0, qn = 0;
             double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
             double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
@@ -630,12 +651,10 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                         lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
                     }
                     const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
-                    const bool vslow = act && rate_is_very_slow(lam_new);
                     const bool slow = act && rate_is_slow(lam_new);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, vslow);
-                    n_mid += __popc(__ballot_sync(0xffffffffu, slow && !vslow));
+                    const unsigned ballot = __ballot_sync(0xffffffffu, slow);
                     n_fast += __popc(__ballot_sync(0xffffffffu, act && !slow));
-                    if (vslow) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                    if (slow) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
                     qn += __popc(ballot);
                     __syncwarp();
                 }
@@ -644,6 +663,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                     const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
                     qh += cnt;
                     {
+                        // rows of lanes >= cnt: moments 0, W' = 1
                         const bool ok = lane < cnt;
                         const double c = ok ? 4.0 * lam : 0.0;
                         const double a = ok ? 16.0 * (lam * lam) : 0.0;
@@ -651,13 +671,18 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                         const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
                         const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
                         const double q32 = q16 * q16, q64 = q32 * q32, q128 = q64 * q64, q256 = q128 * q128;
-                        const double z = -64.0 * c, z2 = z * z;
-                        double me = u0, mo = u0 * z;
+                        // moments u0 z^k / k!, z = -64 c: four chains of stride 4
+                        const double z = -64.0 * c, z2 = z * z, z4 = z2 * z2;
+                        double m0 = u0, m1 = u0 * z, m2 = (u0 * z2) * 0.5, m3 = (m1 * z2) * (1.0 / 6.0);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            st_shared_v2(myM + 2 * k, me, mo);
-                            me *= z2 * (1.0 / double((2 * k + 1) * (2 * k + 2)));
-                            mo *= z2 * (1.0 / double((2 * k + 2) * (2 * k + 3)));
+                            st_shared_v2(myM + 4 * k, m0, m1);
+                            st_shared_v2(myM + 4 * k + 2, m2, m3);
+                            const int b = 4 * k;  // m_{b+r+4} = m_{b+r} z^4 / ((b+r+1)(b+r+2)(b+r+3)(b+r+4))
+                            m0 *= z4 * (1.0 / (double(b + 1) * double(b + 2) * double(b + 3) * double(b + 4)));
+                            m1 *= z4 * (1.0 / (double(b + 2) * double(b + 3) * double(b + 4) * double(b + 5)));
+                            m2 *= z4 * (1.0 / (double(b + 3) * double(b + 4) * double(b + 5) * double(b + 6)));
+                            m3 *= z4 * (1.0 / (double(b + 4) * double(b + 5) * double(b + 6) * double(b + 7)));
                         }
                         // W'[hb] = q^64 (q^128)^hb
                         double w = q64;
@@ -667,11 +692,14 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                             w *= q256;
                         }
                     }
+                    ++n_groups;
                     __syncwarp();
                     {
-                        auto fetch = [&](double (&a)[2], double (&b)[NT], int step) {
-                            const double2 m01 = *reinterpret_cast<const double2*>(fragM + step * (4 * MS));
-                            a[0] = m01.x; a[1] = m01.y;
+                        auto fetch = [&](double (&a)[4], double (&b)[NT], int step) {
+                            const double* mp = fragM + step * (4 * MS);
+                            const double2 m01 = *reinterpret_cast<const double2*>(mp);
+                            const double2 m23 = *reinterpret_cast<const double2*>(mp + 2);
+                            a[0] = m01.x; a[1] = m01.y; a[2] = m23.x; a[3] = m23.y;
                             const double* wp = fragWA + step * (4 * WA);
                             if constexpr (NT == 1) {
                                 b[0] = wp[0];
@@ -683,14 +711,20 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                                 }
                             }
                         };
+                        auto mma_step = [&](const double (&a)[4], const double (&b)[NT]) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) dmma884(accA[i][j][0], accA[i][j][1], a[i], b[j]);
+                        };
                         const int nk = (cnt + 3) >> 2;
-                        double a0[2], b0[NT];
-                        for (int st = 0; st < nk; ++st) {
-                            fetch(a0, b0, st);
-#pragma unroll
-                            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                                for (int j = 0; j < NT; ++j) dmma884(accA[i][j][0], accA[i][j][1], a0[i], b0[j]);
+                        double a0[4], b0[NT], a1[4], b1[NT];
+                        fetch(a0, b0, 0);
+                        for (int st = 0; st < nk; st += 2) {
+                            fetch(a1, b1, st + 1);
+                            mma_step(a0, b0);
+                            fetch(a0, b0, min(st + 2, 7));
+                            mma_step(a1, b1);
                         }
                     }
                     __syncwarp();
@@ -698,24 +732,26 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 if (!more) break;
             }
         }
+        stamp(17);
 
-        // ---------------- A moments -> times, natural layout [128 hb + t], then into the accumulator layout ----------------
+        // ---------------- moments -> times, natural layout [128 hb + t], then into the accumulator layout ----------------
         double acc[4][RH][2];
         {
             constexpr int SA = NB + 4;
-            double* MA = Us;         // [16][SA]
-            double* lin = Us + 512;  // [TT]
+            double* MA = Us;          // [32][SA]
+            double* lin = Us + 1024;  // [TT]
+            static_assert(32 * SA <= 1024 && 1024 + TT <= Cfg::WarpDoubles, "moment scratch fits the table area");
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
-                        MA[(2 * chunk_quad(fg) + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c];
+                        MA[(4 * chunk_pair(fg) + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c];
             __syncwarp();
-            double bf[4][NT];  // B fragments: M[4 ks + fk][8 nt + fg]
+            double bf[8][NT];  // B fragments: M[4 ks + fk][8 nt + fg]
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
+            for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) bf[ks][nt] = MA[(4 * ks + fk) * SA + 8 * nt + fg];
 #pragma unroll 2
@@ -728,7 +764,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) d[nt][0] = d[nt][1] = 0.0;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
+                for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dmma884(d[nt][0], d[nt][1], pw, bf[ks][nt]);
                     pw *= x4;
@@ -751,144 +787,9 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 }
             __syncwarp();
         }
+        stamp(18);
 
-        // ---------------- pass C: slow (not very slow) sites, sixteen moments per 32-point block ----------------
-        // accM[i][j][c]: moment = 2 chunk_quad(fg) + i, hi = RH w_chunk(2 fk + c) + j
-        if (n_mid > 0) {
-        double accM[2][RH][2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < RH; ++j) accM[i][j][0] = accM[i][j][1] = 0.0;
-        {
-            int qh = 0, qn = 0;
-            double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
-            double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
-            for (int base = 0;; base += 32) {
-                const bool more = base < item.n_sites;
-                if (more) {
-                    const double lam_new = lam_in;
-                    lam_in = lam_in2;
-                    {
-                        const int nb = base + 64 + lane;
-                        lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
-                    }
-                    const bool slow = rate_is_active(lam_new) && rate_is_slow(lam_new) && !rate_is_very_slow(lam_new);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, slow);
-                    if (slow) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
-                    qn += __popc(ballot);
-                    __syncwarp();
-                }
-                while (qn - qh >= 32 || (!more && qn > qh)) {
-                    const int cnt = min(32, qn - qh);
-                    const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
-                    qh += cnt;
-                    {
-                        // rows of lanes >= cnt: moments 0, W' = 1
-                        const bool ok = lane < cnt;
-                        const double c = ok ? 4.0 * lam : 0.0;
-                        const double a = ok ? 16.0 * (lam * lam) : 0.0;
-                        const double q = exp_full(-c);
-                        const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
-                        const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8;
-                        const double qB = q16 * q16, qB2 = qB * qB;
-                        double qBh = qB2;  // -> qB^(H/2)
-#pragma unroll
-                        for (int k = 2; k < H / 2; k *= 2) qBh *= qBh;
-                        // moments u0 z^k / k!, z = -16 c: even and odd chains
-                        const double z = -16.0 * c, z2 = z * z;
-                        double me = u0, mo = u0 * z;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            st_shared_v2(myM + 2 * k, me, mo);
-                            me *= z2 * (1.0 / double((2 * k + 1) * (2 * k + 2)));
-                            mo *= z2 * (1.0 / double((2 * k + 2) * (2 * k + 3)));
-                        }
-                        // W'[hi] = q^16 (q^32)^hi
-                        double wa = q16, wb = q16 * qBh;
-#pragma unroll
-                        for (int k = 0; k < H / 4; ++k) {
-                            st_shared_v2(myW + 2 * k, wa, wa * qB);
-                            st_shared_v2(myW + H / 2 + 2 * k, wb, wb * qB);
-                            wa *= qB2;
-                            wb *= qB2;
-                        }
-                    }
-                    __syncwarp();
-                    {
-                        auto fetch = [&](double (&a)[2], double (&b)[RH], int step) {
-                            const double2 m01 = *reinterpret_cast<const double2*>(fragM + step * (4 * MS));
-                            a[0] = m01.x; a[1] = m01.y;
-                            const double* wp = fragW + step * (4 * WS);
-#pragma unroll
-                            for (int r = 0; r < RH / 2; ++r) {
-                                const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
-                                b[2 * r] = v.x; b[2 * r + 1] = v.y;
-                            }
-                        };
-                        auto mma_step = [&](const double (&a)[2], const double (&b)[RH]) {
-#pragma unroll
-                            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                                for (int j = 0; j < RH; ++j) dmma884(accM[i][j][0], accM[i][j][1], a[i], b[j]);
-                        };
-                        const int nk = (cnt + 3) >> 2;
-                        double a0[2], b0[RH], a1[2], b1[RH];
-                        fetch(a0, b0, 0);
-                        for (int s = 0; s < nk; s += 2) {
-                            fetch(a1, b1, s + 1);
-                            mma_step(a0, b0);
-                            fetch(a0, b0, min(s + 2, 7));
-                            mma_step(a1, b1);
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (!more) break;
-            }
-        }
-
-        // ---------------- C moments -> times: acc[lo][hi] += sum_k ((lo - 16)/16)^k M[k][hi] ----------------
-        {
-            double* Ms = Us;  // [16][WS], the table area is free now
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < RH; ++j)
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        Ms[(2 * chunk_quad(fg) + i) * WS + RH * w_chunk<RH>(2 * fk + c) + j] = accM[i][j][c];
-            __syncwarp();
-            // this lane's A fragment of step ks is x_i^(4 ks + fk), x_i = (lo_i - 16) / 16 (exact)
-            double pw[4], x4[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double x = double(4 * chunk_pair(fg) + i - 16) * 0.0625;
-                const double xx = x * x;
-                pw[i] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;
-                x4[i] = xx * xx;
-            }
-            const double* mrow = Ms + fk * WS + RH * w_chunk<RH>(fg);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                double b[RH];
-#pragma unroll
-                for (int r = 0; r < RH / 2; ++r) {
-                    const double2 v = *reinterpret_cast<const double2*>(mrow + ks * (4 * WS) + 2 * r);
-                    b[2 * r] = v.x; b[2 * r + 1] = v.y;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                    for (int j = 0; j < RH; ++j) dmma884(acc[i][j][0], acc[i][j][1], pw[i], b[j]);
-                    pw[i] *= x4[i];
-                }
-            }
-            __syncwarp();
-        }
-        }  // n_mid > 0
-
-        // ---------------- pass 2: the item's fast sites, power tables as in profile_kernel ----------------
+        // ---------------- the item's fast sites, power tables as in profile_kernel ----------------
         if (n_fast > 0) {
             int qh = 0, qn = 0;
             double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
@@ -920,7 +821,16 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 if (!more) break;
             }
         }
+        stamp(19);
         prof_epilogue<RH>(args, acc, item.locus, item.tile, item.slot, lane);
+        stamp(20);
+        if constexpr (TRACE) {
+            if (lane == 0 && n_done == 1) { tr[22] = n_groups; tr[24] = n_fast; }
+            ++n_done;
+        }
+    }
+    if constexpr (TRACE) {
+        if (lane == 0) { tr[12] = clock64(); tr[13] = n_done; }
     }
 }
 

@@ -242,6 +242,28 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
     const int64_t need = (n_items + kProfWarps - 1) / kProfWarps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if constexpr (RH >= 4) {
+        if (ctx->prof_mom) {  // moment form (same grid, same shared memory)
+            static bool mom_configured[64] = {false};
+            if (!mom_configured[ctx->device & 63]) {
+                e = cudaFuncSetAttribute(profile_mom_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
+                if (e != cudaSuccess) return e;
+                mom_configured[ctx->device & 63] = true;
+            }
+            if (pa.trace) {  // measurement only
+                static bool mom_trace_configured[64] = {false};
+                if (!mom_trace_configured[ctx->device & 63]) {
+                    e = cudaFuncSetAttribute(profile_mom_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
+                    if (e != cudaSuccess) return e;
+                    mom_trace_configured[ctx->device & 63] = true;
+                }
+                profile_mom_kernel<RH, true><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
+            } else {
+                profile_mom_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
+            }
+            return cudaGetLastError();
+        }
+    }
     if (pa.trace) {  // measurement only
         static bool trace_configured[64] = {false};
         if (!trace_configured[ctx->device & 63]) {
@@ -251,18 +273,6 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
         }
         profile_kernel<RH, true><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
         return cudaGetLastError();
-    }
-    if constexpr (RH >= 4) {
-        if (ctx->prof_mom) {  // moment form (same grid, same shared memory)
-            static bool mom_configured[64] = {false};
-            if (!mom_configured[ctx->device & 63]) {
-                e = cudaFuncSetAttribute(profile_mom_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
-                if (e != cudaSuccess) return e;
-                mom_configured[ctx->device & 63] = true;
-            }
-            profile_mom_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
-            return cudaGetLastError();
-        }
     }
     profile_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
     return cudaGetLastError();

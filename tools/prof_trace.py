@@ -68,6 +68,8 @@ print("SM busy span (cycles):", q(sm_span))
 g = tr[:, 16:32].reshape(-1, 4, 4)
 ok = (n_done >= 2) & (g[:, :, 2].min(axis=1) > 0)
 gg = g[ok]
+if not ok.any():
+    gg = np.zeros((1, 4, 4), dtype=np.int64)
 pop_to_built = (gg[:, :, 1] - gg[:, :, 0]).ravel()
 built_to_done = (gg[:, :, 2] - gg[:, :, 1]).ravel()
 done_to_pop = (gg[:, 1:, 0] - gg[:, :-1, 2]).ravel()
@@ -76,3 +78,14 @@ print("  group popped -> tables built (exp chain, power tables, __syncwarp)", q(
 print("  tables built -> contracted (128 DMMA = 2048 pipe cycles)          ", q(built_to_done))
 print("  contracted -> next group popped (rate rounds, queue)              ", q(done_to_pop))
 print("  whole group                                                       ", q((gg[:, 1:, 0] - gg[:, :-1, 0]).ravel()))
+
+# profile_mom_kernel: phases of the warp's second item
+m = (n_done >= 2) & (tr[:, 20] > 0)
+if m.any():
+    ph = tr[m]
+    names = ["moment pass (slow sites)", "moments -> times", "fast-site pass", "epilogue"]
+    print("moment kernel, second item of a warp (cycles): groups of the moment pass p50 %d, n_fast p50 %d" % (
+        np.percentile(ph[:, 22], 50), np.percentile(ph[:, 24], 50)))
+    for k, nm in enumerate(names):
+        print("  %-28s" % nm, q(ph[:, 17 + k] - ph[:, 16 + k]))
+    print("  %-28s" % "whole item", q(ph[:, 20] - ph[:, 16]))
