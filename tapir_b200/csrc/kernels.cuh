@@ -599,6 +599,8 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
     double* myWA = WAs + lane * WA;
     const double* fragM = Us + fk * MS + 4 * chunk_pair(fg);
     const double* fragWA = WAs + fk * WA + NT * w_chunk<NT>(fg);
+    double* Fs = Us + 1024 + TT;  // up to 32 fast rates of the item, behind the scratch of the moments -> times step
+    static_assert(1024 + TT + 32 <= 32 * (US + WS), "fast-site list fits behind the scratch");
     long long* tr = nullptr;
     int n_done = 0, n_groups = 0;
     if constexpr (TRACE) {
@@ -631,11 +633,12 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
 
         // ---------------- moment pass: slow sites ----------------
         // accA[i][j][c]: moment = 4 chunk_pair(fg) + i, hb = NT w_chunk<NT>(2 fk + c) + j
-        double accA[4][NT][2];
+        // (two sets, for the even and the odd k-steps: with NT = 1 a single set is a dependent chain of four DMMAs)
+        double accA[4][NT][2], accB[4][NT][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < NT; ++j) accA[i][j][0] = accA[i][j][1] = 0.0;
+            for (int j = 0; j < NT; ++j) accA[i][j][0] = accA[i][j][1] = accB[i][j][0] = accB[i][j][1] = 0.0;
         int n_fast = 0;
         {
             int qh = 0, qn = 0;
@@ -653,7 +656,12 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                     const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
                     const bool slow = act && rate_is_slow(lam_new);
                     const unsigned ballot = __ballot_sync(0xffffffffu, slow);
-                    n_fast += __popc(__ballot_sync(0xffffffffu, act && !slow));
+                    {   // the first 32 fast sites are kept aside, so that their pass need not stream the item again
+                        const unsigned bf = __ballot_sync(0xffffffffu, act && !slow);
+                        const int pos = n_fast + __popc(bf & ((1u << lane) - 1u));
+                        if (act && !slow && pos < 32) Fs[pos] = lam_new;
+                        n_fast += __popc(bf);
+                    }
                     if (slow) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
                     qn += __popc(ballot);
                     __syncwarp();
@@ -711,20 +719,20 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                                 }
                             }
                         };
-                        auto mma_step = [&](const double (&a)[4], const double (&b)[NT]) {
+                        auto mma_step = [&](double (&ac)[4][NT][2], const double (&a)[4], const double (&b)[NT]) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                                for (int j = 0; j < NT; ++j) dmma884(accA[i][j][0], accA[i][j][1], a[i], b[j]);
+                                for (int j = 0; j < NT; ++j) dmma884(ac[i][j][0], ac[i][j][1], a[i], b[j]);
                         };
-                        const int nk = (cnt + 3) >> 2;
+                        const int nk = (cnt + 3) >> 2;  // rows past cnt are zero, so an odd count rounds up
                         double a0[4], b0[NT], a1[4], b1[NT];
                         fetch(a0, b0, 0);
                         for (int st = 0; st < nk; st += 2) {
                             fetch(a1, b1, st + 1);
-                            mma_step(a0, b0);
+                            mma_step(accA, a0, b0);
                             fetch(a0, b0, min(st + 2, 7));
-                            mma_step(a1, b1);
+                            mma_step(accB, a1, b1);
                         }
                     }
                     __syncwarp();
@@ -747,32 +755,41 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
-                        MA[(4 * chunk_pair(fg) + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c];
+                        MA[(4 * chunk_pair(fg) + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c] + accB[i][j][c];
             __syncwarp();
             double bf[8][NT];  // B fragments: M[4 ks + fk][8 nt + fg]
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) bf[ks][nt] = MA[(4 * ks + fk) * SA + 8 * nt + fg];
-#pragma unroll 2
-            for (int mt = 0; mt < 16; ++mt) {
-                // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact)
-                const double x = double(8 * mt + fg - 64) * 0.015625;
-                const double xx = x * x, x4 = xx * xx;
-                double pw = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;
-                double d[NT][2];
+            // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact);
+            // eight row tiles at a time, so that the eight DMMAs of a tile are not one dependent chain
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                double pw[8], x4[8], d[8][NT][2];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) d[nt][0] = d[nt][1] = 0.0;
+                for (int m = 0; m < 8; ++m) {
+                    const double x = double(8 * (8 * half + m) + fg - 64) * 0.015625;
+                    const double xx = x * x;
+                    x4[m] = xx * xx;
+                    pw[m] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma884(d[nt][0], d[nt][1], pw, bf[ks][nt]);
-                    pw *= x4;
+                    for (int nt = 0; nt < NT; ++nt) d[m][nt][0] = d[m][nt][1] = 0.0;
                 }
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+                for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) lin[128 * (8 * nt + 2 * fk + c) + 8 * mt + fg] = d[nt][c];
+                    for (int m = 0; m < 8; ++m) {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) dmma884(d[m][nt][0], d[m][nt][1], pw[m], bf[ks][nt]);
+                        pw[m] *= x4[m];
+                    }
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) lin[128 * (8 * nt + 2 * fk + c) + 8 * (8 * half + m) + fg] = d[m][nt][c];
             }
             __syncwarp();
 #pragma unroll
@@ -790,7 +807,14 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
         stamp(18);
 
         // ---------------- the item's fast sites, power tables as in profile_kernel ----------------
-        if (n_fast > 0) {
+        if (n_fast > 0 && n_fast <= 32) {
+            const double lam = (lane < n_fast) ? Fs[lane] : 0.0;
+            __syncwarp();  // the list lies inside the table area
+            prof_build_tables<RH>(lam, lane < n_fast, T0, t0d, myU, myW);
+            __syncwarp();
+            prof_contract<RH>(acc, fragU, fragW, (n_fast + 3) >> 2);
+            __syncwarp();
+        } else if (n_fast > 32) {
             int qh = 0, qn = 0;
             double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
             double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
