@@ -487,18 +487,18 @@ def run_ours(args, rank, world, local_rank):
                               "ms_per_step is the shipped two-stream configuration"},
         "roofline": {
             "bound": "tensor", "pipe": "FP64 (DMMA sub-pipe of the tensor pipe; shared with DFMA on B200)",
-            "kernel": "profile_mom_kernel" if T >= 512 else "profile_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "kernel": "profile_mom_kernel" if T >= 1000 else "profile_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": profile_traffic(args.workload),
             "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has HBM and bf16 entries only; "
                            "tools/microbench/fp64_pipes.cu: DMMA 37.0, DFMA 36.6 TFLOP/s, one shared pipe)",
             "algorithmic": "2 flop (1 FP64 FMA) per site*timepoint eval of a site with a non-zero finite rate: "
                            "%d of the launch's %d evals (zero-rate and culled sites add exactly 0 and are dropped after "
-                           "the load).  profile_mom_kernel EXECUTES about half of them: sites with rate <= 0.0195 enter "
-                           "the contraction as 16 Taylor moments per 32-point block instead of 32 powers, so the fraction "
-                           "is the direct formulation's work over the FP64 peak and can exceed what the pipe could do "
-                           "without that reformulation" % (evals_active, evals_rank),
-            "executed_over_algorithmic": None if T < 512 else round(
-                (0.5 * n_slow + (n_active - n_slow)) / max(n_active, 1), 4),
+                           "the load).  profile_mom_kernel EXECUTES about a quarter of them: a site with rate < 0.0195 "
+                           "enters the contraction as 32 Taylor moments per 128-point block of the time tile instead of 32 "
+                           "powers per 32-point block (DESIGN.md 3.1), so this fraction measures the direct formulation's "
+                           "work against the FP64 peak and may exceed 1" % (evals_active, evals_rank),
+            "executed_over_algorithmic": None if T < 1000 else round(
+                (0.25 * n_slow + (n_active - n_slow)) / max(n_active, 1), 4),
             "active_site_fraction": n_active / max(nnz, 1),
             "quad_kernel": {"ms": quad_ms / args.steps, "site_epochs_per_s": nnz * len(epochs) / (quad_ms / args.steps * 1e-3)},
             # the same evals/s against the ceiling of the reference's formulation, one FP64 exp per
