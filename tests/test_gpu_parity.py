@@ -288,6 +288,33 @@ def test_mixed_error_estimates_within_a_warp(eng):
     assert np.array_equal(res.integral, again.integral) and np.array_equal(res.abserr, again.abserr)
 
 
+@pytest.mark.parametrize("case", ["below_threshold", "straddling", "slow_plus_fast", "all_fast", "more_than_32_fast"])
+def test_moment_form_classes(eng, case):
+    """profile_mom_kernel represents a site with rate < 0.01953125 by 32 Taylor moments per 128-point block and adds
+    the faster sites by the power-table contraction (the first 32 from a side list, more by a second stream of the
+    item).  Rates at the threshold carry the largest series remainder (predicted 1.3e-11)."""
+    from oracle import capi
+    from tapir_b200.engine import pack_csr
+    rng = np.random.default_rng(31)
+    T = 1000
+    if case == "below_threshold":
+        loci = [rng.uniform(0.0190, 0.01953, 300) for _ in range(4)]
+    elif case == "straddling":
+        loci = [rng.uniform(0.015, 0.025, 300) for _ in range(4)]
+    elif case == "slow_plus_fast":
+        loci = [np.concatenate([rng.gamma(0.5, 0.004, 300), rng.uniform(0.05, 3.0, 7)]) for _ in range(4)]
+    elif case == "all_fast":
+        loci = [rng.uniform(0.02, 1.0, 150) for _ in range(4)]
+    else:
+        loci = [rng.permutation(np.concatenate([rng.gamma(0.5, 0.004, 200), rng.uniform(0.02, 0.5, 45)])) for _ in range(4)]
+    off, rates = pack_csr(loci, pinned=False)
+    res = eng.run(off, rates, T, [1, 500, 999], [[32, 42]], want_profile=True)
+    pi_net, _, _ = capi.batch(off, rates, T, [[32, 42]])
+    assert rel(res.pi_net, pi_net) < 5e-11
+    assert np.array_equal(res.argmax_t, np.argmax(pi_net, axis=1))
+    assert np.array_equal(res.pi_times, res.pi_net[:, [1, 500, 999]])
+
+
 def test_chunked_run_equals_single_pass(eng):
     """tapir_cuda_run cuts a large batch into chunks that alternate between two lanes (copies overlap
     kernels); the result must be bit-identical to the unchunked staged path, ragged loci included."""
