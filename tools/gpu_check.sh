@@ -13,6 +13,6 @@ timeout 300 $CMD > gpurun_out/${tag}_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_ncu_list.log 2>&1
 echo "ncu list rc=$?"
 timeout 300 $CMD > gpurun_out/${tag}_plain2.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'profile_kernel|quad_kernel' -s 2 -c 2 -o gpurun_out/${tag}_prof -f $CMD > gpurun_out/${tag}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'profile_mom_kernel|quad_kernel' -s 2 -c 2 -o gpurun_out/${tag}_prof -f $CMD > gpurun_out/${tag}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out
