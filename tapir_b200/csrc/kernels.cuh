@@ -642,16 +642,20 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
         int n_fast = 0;
         {
             int qh = 0, qn = 0;
-            double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
-            double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
+            // rates are fetched four rounds ahead: a group of this pass lasts about as long as one DRAM access
+            constexpr int kAhead = 4;
+            double lam_q[kAhead];
+#pragma unroll
+            for (int k = 0; k < kAhead; ++k) lam_q[k] = (32 * k + lane < item.n_sites) ? __ldg(rp + 32 * k + lane) : 0.0;
             for (int base = 0;; base += 32) {
                 const bool more = base < item.n_sites;
                 if (more) {
-                    const double lam_new = lam_in;
-                    lam_in = lam_in2;
+                    const double lam_new = lam_q[0];
+#pragma unroll
+                    for (int k = 0; k + 1 < kAhead; ++k) lam_q[k] = lam_q[k + 1];
                     {
-                        const int nb = base + 64 + lane;
-                        lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                        const int nb = base + 32 * kAhead + lane;
+                        lam_q[kAhead - 1] = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
                     }
                     const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
                     const bool slow = act && rate_is_slow(lam_new);
