@@ -569,6 +569,23 @@ __device__ __forceinline__ void prof_epilogue(const ProfArgs& args, const double
 // same sums (observed <= 1e-12 relative; the parity gate is 1e-9).
 constexpr int kMomStride = 34;  // doubles per moment row (32 + 2: rows 272 bytes apart, conflict-free 16-byte fragments)
 
+// Shared memory of one warp of profile_mom_kernel: the moment tables U' [32][34] + W' [32][WA]; later, over them, the
+// scratch of the moments -> times step ([32][NB+4] moments, then [TT] times) and the 16-site power tables of the
+// fast-site pass; behind all of them the list of up to 32 fast rates (filled during the moment pass, read after the
+// scratch has been used) and the 64-entry compaction queue.  12.25 KB for RH = 4: sixteen warps per SM.
+template <int RH>
+struct MomCfg {
+    static constexpr int TT = ProfCfg<RH>::TT, NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
+    static constexpr int Tables = 32 * kMomStride + 32 * WA;
+    static constexpr int FastOff = Tables > TT ? Tables : TT;
+    static constexpr int QueueOff = FastOff + 32;
+    static constexpr int WarpDoubles = QueueOff + 64;
+    static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
+    static constexpr int MinBlocks = (RH == 4 ? 14 : 8) / kProfWarps;  // 144 / 255 registers
+    static_assert(16 * (kUStride + ProfCfg<RH>::WStride) <= FastOff, "16-site power tables fit below the fast-site list");
+    static_assert(32 * (NB + 4) <= FastOff, "moment scratch fits");
+};
+
 // a slow site: 64 c = 256 r <= 5, i.e. r < 0x3F94000000000000 (0.01953125), r >= 0 -- on the bit pattern
 __device__ __forceinline__ bool rate_is_slow(double r) { return uint32_t(__double2hiint(r)) < 0x3F940000u; }
 
@@ -576,21 +593,23 @@ __device__ __forceinline__ bool rate_is_slow(double r) { return uint32_t(__doubl
 // [16] claimed, [17] moment pass done, [18] moments -> times done, [19] fast-site pass done, [20] epilogue done,
 // [22] groups of the moment pass, [24] n_fast
 template <int RH, bool TRACE = false>
-__global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profile_mom_kernel(const ProfArgs args)
+__global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profile_mom_kernel(const ProfArgs args)
 {
     using Cfg = ProfCfg<RH>;
+    using Mom = MomCfg<RH>;
     constexpr int TT = Cfg::TT, WS = Cfg::WStride, US = kUStride, MS = kMomStride;
     static_assert(RH >= 4, "moment form: tiles of 1024 points or more");
-    constexpr int NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
+    constexpr int NB = Mom::NB, NT = Mom::NT, WA = Mom::WA;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int fk = lane & 3, fg = lane >> 2;
-    double* Us = smem + size_t(warp) * Cfg::WarpDoubles;
-    double* Ws = Us + 32 * US;
-    double* Qs = Ws + 32 * WS;
-    double* myU = Us + lane * US;
-    double* myW = Ws + lane * WS;
+    double* Us = smem + size_t(warp) * Mom::WarpDoubles;
+    double* Qs = Us + Mom::QueueOff;
+    // fast-site pass: power tables of 16 sites, U [16][US] then W [16][WS]
+    double* Ws = Us + 16 * US;
+    double* myU = Us + (lane & 15) * US;
+    double* myW = Ws + (lane & 15) * WS;
     const double* fragU = Us + fk * US + 4 * chunk_pair(fg);
     const double* fragW = Ws + fk * WS + RH * w_chunk<RH>(fg);
     // moment pass: U' [32][MS] where profile_kernel keeps U (same stride), W' [32][WA] behind it
@@ -599,8 +618,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
     double* myWA = WAs + lane * WA;
     const double* fragM = Us + fk * MS + 4 * chunk_pair(fg);
     const double* fragWA = WAs + fk * WA + NT * w_chunk<NT>(fg);
-    double* Fs = Us + 1024 + TT;  // up to 32 fast rates of the item, behind the scratch of the moments -> times step
-    static_assert(1024 + TT + 32 <= 32 * (US + WS), "fast-site list fits behind the scratch");
+    double* Fs = Us + Mom::FastOff;  // up to 32 fast rates of the item, behind everything that is written before they are read
     long long* tr = nullptr;
     int n_done = 0, n_groups = 0;
     if constexpr (TRACE) {
@@ -746,9 +764,8 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
         double acc[4][RH][2];
         {
             constexpr int SA = NB + 4;
-            double* MA = Us;          // [32][SA]
-            double* lin = Us + 1024;  // [TT]
-            static_assert(32 * SA <= 1024 && 1024 + TT <= Cfg::WarpDoubles, "moment scratch fits the table area");
+            double* MA = Us;   // [32][SA]
+            double* lin = Us;  // [TT], once the B fragments are in registers
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -762,6 +779,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
             for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) bf[ks][nt] = MA[(4 * ks + fk) * SA + 8 * nt + fg];
+            __syncwarp();
             // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact);
             // eight row tiles at a time, so that the eight DMMAs of a tile are not one dependent chain
 #pragma unroll 1
@@ -811,12 +829,13 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
 
         // ---------------- the item's fast sites, power tables as in profile_kernel ----------------
         if (n_fast > 0 && n_fast <= 32) {
-            const double lam = (lane < n_fast) ? Fs[lane] : 0.0;
-            __syncwarp();  // the list lies inside the table area
-            prof_build_tables<RH>(lam, lane < n_fast, T0, t0d, myU, myW);
-            __syncwarp();
-            prof_contract<RH>(acc, fragU, fragW, (n_fast + 3) >> 2);
-            __syncwarp();
+            for (int g0 = 0; g0 < n_fast; g0 += 16) {
+                const int cnt = min(16, n_fast - g0);
+                if (lane < 16) prof_build_tables<RH>((lane < cnt) ? Fs[g0 + lane] : 0.0, lane < cnt, T0, t0d, myU, myW);
+                __syncwarp();
+                prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2);
+                __syncwarp();
+            }
         } else if (n_fast > 32) {
             int qh = 0, qn = 0;
             double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
@@ -836,11 +855,12 @@ __global__ void __launch_bounds__(kProfWarps * 32, ProfCfg<RH>::MinBlocks) profi
                     qn += __popc(ballot);
                     __syncwarp();
                 }
-                while (qn - qh >= 32 || (!more && qn > qh)) {
-                    const int cnt = min(32, qn - qh);
+                while (qn - qh >= 16 || (!more && qn > qh)) {
+                    const int cnt = min(16, qn - qh);
                     const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
                     qh += cnt;
-                    prof_build_tables<RH>(lam, lane < cnt, T0, t0d, myU, myW);
+                    __syncwarp();
+                    if (lane < 16) prof_build_tables<RH>(lam, lane < cnt, T0, t0d, myU, myW);
                     __syncwarp();
                     prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2);
                     __syncwarp();

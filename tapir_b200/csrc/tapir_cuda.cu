@@ -243,24 +243,30 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if constexpr (RH >= 4) {
-        if (ctx->prof_mom) {  // moment form (same grid, same shared memory)
+        if (ctx->prof_mom) {  // moment form: its own shared-memory layout and occupancy
+            using Mom = MomCfg<RH>;
             static bool mom_configured[64] = {false};
+            static int mom_per_sm[64] = {0};
             if (!mom_configured[ctx->device & 63]) {
-                e = cudaFuncSetAttribute(profile_mom_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
+                e = cudaFuncSetAttribute(profile_mom_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom::SmemBytes));
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(profile_mom_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom::SmemBytes));
+                if (e == cudaSuccess)
+                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mom_per_sm[ctx->device & 63], profile_mom_kernel<RH>,
+                                                                      kProfWarps * 32, Mom::SmemBytes);
                 if (e != cudaSuccess) return e;
                 mom_configured[ctx->device & 63] = true;
             }
-            if (pa.trace) {  // measurement only
-                static bool mom_trace_configured[64] = {false};
-                if (!mom_trace_configured[ctx->device & 63]) {
-                    e = cudaFuncSetAttribute(profile_mom_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
-                    if (e != cudaSuccess) return e;
-                    mom_trace_configured[ctx->device & 63] = true;
-                }
-                profile_mom_kernel<RH, true><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
-            } else {
-                profile_mom_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
+            int mper = std::max(1, mom_per_sm[ctx->device & 63]);
+            if (const char* env = getenv("TAPIR_PROF_CTAS_PER_SM")) {
+                const int v = atoi(env);
+                if (v >= 1 && v < mper) mper = v;
             }
+            const int64_t mgrid = std::max<int64_t>(1, std::min<int64_t>(need, int64_t(ctx->sm_count) * mper));
+            if (pa.trace)
+                profile_mom_kernel<RH, true><<<unsigned(mgrid), kProfWarps * 32, Mom::SmemBytes, ln.stream>>>(pa);
+            else
+                profile_mom_kernel<RH><<<unsigned(mgrid), kProfWarps * 32, Mom::SmemBytes, ln.stream>>>(pa);
             return cudaGetLastError();
         }
     }
@@ -420,7 +426,7 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         if ((env = getenv("TAPIR_PROF_MOM"))) ctx->prof_mom = atoi(env) != 0;
         if ((env = getenv("TAPIR_PROF_TRACE")) && env[0]) {
             ctx->prof_trace_path = env;
-            ctx->prof_trace_words = size_t(prop.multiProcessorCount) * 16 * 32;
+            ctx->prof_trace_words = size_t(prop.multiProcessorCount) * 32 * 32;
             if (cudaMalloc(&ctx->prof_trace, ctx->prof_trace_words * 8) != cudaSuccess) ctx->prof_trace = nullptr;
             else cudaMemset(ctx->prof_trace, 0, ctx->prof_trace_words * 8);
             ctx->use_graphs = 0;
