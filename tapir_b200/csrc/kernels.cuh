@@ -2,7 +2,9 @@
 //
 //   profile_kernel<RH>   pi_net[l,t] = t * sum_i a_i q_i^t           (compute.py:46-48 + nansum,
 //                        with a_i = 16 r_i^2, q_i = exp(-4 r_i)        bin/tapir_compute.py:119)
-//   quad_kernel<NE>      first GK21 panel of every (site, epoch)     (compute.py:50-52, 81-94)
+//   profile_mom_kernel<RH>  the same profile for tiles of 1024+ grid points (the shipped default there): slow
+//                        sites as 32 Taylor moments per 128-point block, a quarter of profile_kernel's DMMAs
+//   quad_kernel<NE>      first GK21 panel of every (site, epoch), collapsed (compute.py:50-52, 81-94)
 //   quad_fix_kernel      full QAGS for the sites QAGS would bisect   (scipy.integrate.quad = QUADPACK dqagse)
 //   finalize_kernel      per-locus reductions, --times picks, maxima (compute.py:76-79, README.rst:178-185)
 //   rank_kernel, epoch_count_kernel   top-N loci per interval, loci per max-PI epoch
