@@ -1,0 +1,96 @@
+"""CPU checks of the algebra the CUDA kernels rely on (no GPU): the constant tables of gk21.cuh are re-derived in
+high-precision decimal arithmetic, and the moment form of profile_mom_kernel is restated in numpy and compared with
+the direct evaluation at the slow/fast threshold, where its series remainder is largest."""
+import os
+import re
+from decimal import Decimal as D, getcontext
+from math import factorial
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+getcontext().prec = 80
+
+
+def _array(name, text):
+    m = re.search(r"c_%s\[\d+\]\s*=\s*\{(.*?)\};" % name, text, re.S)
+    assert m, name
+    return [float(v) for v in re.findall(r"[-+]?\d\.?\d*(?:[eE][-+]?\d+)?", m.group(1))]
+
+
+def _rule():
+    text = open(os.path.join(ROOT, "tapir_b200", "csrc", "gk21.cuh")).read()
+    c = {n: _array(n, text) for n in ("xgk", "wgk", "wg", "wx", "dl", "dlx", "ak", "bk")}
+    assert [len(c[n]) for n in ("xgk", "wgk", "wg", "wx", "dl", "dlx", "ak", "bk")] == [10, 11, 5, 10, 10, 10, 7, 7]
+    return c
+
+
+def test_gk21_product_constants():
+    c = _rule()
+    x, w, g = [D(v) for v in c["xgk"]], [D(v) for v in c["wgk"]], [D(v) for v in c["wg"]]
+    for j in range(10):
+        dl = w[j] - (g[(j - 1) // 2] if j % 2 == 1 else 0)
+        assert c["wx"][j] == float(w[j] * x[j])
+        assert c["dl"][j] == float(dl)
+        assert c["dlx"][j] == float(dl * x[j])
+    # Kronrod and Gauss both integrate constants exactly: the difference weights sum to zero
+    assert abs(float(2 * sum(D(v) for v in c["dl"]) + w[10])) < 1e-16
+
+
+def test_gk21_series_coefficients():
+    """c_ak / c_bk: moments of the Kronrod rule; seven terms reproduce the pair sums below y x_0 log2(e) = 1/2."""
+    c = _rule()
+    x, w = [D(v) for v in c["xgk"]], [D(v) for v in c["wgk"]]
+    for n in range(7):
+        ak = (2 * sum(w[j] * x[j] ** (2 * n) for j in range(10)) + (w[10] if n == 0 else 0)) / factorial(2 * n)
+        bk = 2 * sum(w[j] * x[j] ** (2 * n + 2) for j in range(10)) / factorial(2 * n + 1)
+        assert c["ak"][n] == float(ak) and c["bk"][n] == float(bk)
+    for y in (0.348, 0.1, 1e-3):
+        yd = D(y)
+        direct_a = w[10] + sum(w[j] * ((yd * x[j]).exp() + (-yd * x[j]).exp()) for j in range(10))
+        direct_b = sum(w[j] * x[j] * ((yd * x[j]).exp() - (-yd * x[j]).exp()) for j in range(10))
+        sa = sum(D(c["ak"][n]) * yd ** (2 * n) for n in range(7))
+        sb = sum(D(c["bk"][n]) * yd ** (2 * n + 1) for n in range(7))
+        assert abs(sa - direct_a) / direct_a < D("3e-16") and abs(sb - direct_b) / direct_b < D("3e-16")
+
+
+def _moment_form(rates, T0, TT=1024):
+    """numpy restatement of profile_mom_kernel's arithmetic for one tile: sum_s a_s q_s^t for t = T0 .. T0 + TT - 1."""
+    lam = np.asarray(rates, dtype=np.float64)
+    a, c = 16.0 * lam * lam, 4.0 * lam
+    u0 = a * np.exp(-(c * float(T0)))
+    z = -64.0 * c
+    q64 = np.exp(z)
+    nb = TT // 128
+    m = np.empty((32, lam.size))
+    z2 = z * z
+    z4 = z2 * z2
+    m[0], m[1], m[2], m[3] = u0, u0 * z, u0 * z2, (u0 * z) * z2
+    for k in range(4, 32):
+        m[k] = m[k - 4] * z4
+    w = np.empty((nb, lam.size))
+    w[0] = q64
+    q128 = q64 * q64
+    for hb in range(1, nb):
+        w[hb] = w[hb - 1] * q128
+    M = m @ w.T                                   # [32][nb], the contraction over sites
+    t = np.arange(128, dtype=np.float64)
+    x = (t - 64.0) / 64.0
+    P = np.empty((128, 32))
+    for k in range(32):
+        P[:, k] = x ** k / float(factorial(k))
+    return (P @ M).T.reshape(-1)                  # [128 hb + t]
+
+
+def test_moment_form_remainder_at_the_threshold():
+    rng = np.random.default_rng(3)
+    thr = float(np.uint64(0x3F94000000000000).view(np.float64))
+    assert thr == 0.01953125                      # rate_is_slow: 64 c = 256 r <= 5
+    for rates in (rng.uniform(0.0190, thr, 64), rng.gamma(0.5, 0.004, 400).clip(1e-9, thr * 0.999),
+                  np.array([1e-7, 1e-5, thr * 0.9999])):
+        for T0 in (0, 1024, 4096):
+            got = _moment_form(rates, T0)
+            t = T0 + np.arange(1024, dtype=np.float64)
+            want = (16.0 * rates[:, None] ** 2 * np.exp(-4.0 * rates[:, None] * t[None, :])).sum(axis=0)
+            err = np.max(np.abs(got - want) / want)
+            assert err < 5e-11, (T0, err)         # remainder 5^32/32! against e^-5 = 1.3e-11
