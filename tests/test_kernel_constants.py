@@ -94,3 +94,65 @@ def test_moment_form_remainder_at_the_threshold():
             want = (16.0 * rates[:, None] ** 2 * np.exp(-4.0 * rates[:, None] * t[None, :])).sum(axis=0)
             err = np.max(np.abs(got - want) / want)
             assert err < 5e-11, (T0, err)         # remainder 5^32/32! against e^-5 = 1.3e-11
+
+
+def _collapsed_panel(c, lam, a_lim, b_lim, series):
+    """numpy restatement of quad_kernel's collapsed GK21 panel (gk21_collapsed + panel_sums[_series]) for one site and
+    one epoch -> (result, abserr, proved)."""
+    eps, uflow = np.finfo(float).eps, np.finfo(float).tiny
+    x, w = np.array(c["xgk"]), np.array(c["wgk"])
+    fc, h = 0.5 * (a_lim + b_lim), 0.5 * (b_lim - a_lim)
+    a, cc = 16.0 * lam * lam, 4.0 * lam
+    y = cc * h
+    R, Dn = np.exp(y * x), np.exp(-y * x)
+    if series:
+        s = y * y
+        pa, pb = c["ak"][6], c["bk"][6]
+        for n in range(5, -1, -1):
+            pa, pb = pa * s + c["ak"][n], pb * s + c["bk"][n]
+        Ak, Bk, dA, dB, e0rel = pa, (pb * y) * h, 0.0, 0.0, 32.0 * eps
+    else:
+        S, Dl = R + Dn, R - Dn
+        Ak = w[10] + np.dot(w[:10], S)
+        Bk = np.dot(np.array(c["wx"]), Dl) * h
+        dA = w[10] + np.dot(np.array(c["dl"]), S)
+        dB = np.dot(np.array(c["dlx"]), Dl) * h
+        e0rel = 0.0
+    scale = (a * np.exp(-(cc * fc))) * h
+    resk = fc * Ak - Bk
+    e0 = e0rel * resk + abs(fc * dA - dB)
+    reskh = 0.5 * resk
+    n, fl = 200.0 * e0 / resk, 50.0 * eps
+    f14, f24 = (fc - h * x[4]) * R[4], (fc + h * x[4]) * Dn[4]
+    f15, f25 = (fc - h * x[5]) * R[5], (fc + h * x[5]) * Dn[5]
+    lb = (w[4] * (abs(f14 - reskh) + abs(f24 - reskh)) + w[5] * (abs(f15 - reskh) + abs(f25 - reskh))) / resk
+    res = resk * scale
+    proved = bool(res > uflow / (50.0 * eps) and n < lb and n ** 3 <= fl * fl * lb and lb > fl)
+    return res, 50.0 * eps * res, proved
+
+
+def test_collapsed_panel_against_quadpack():
+    """Whenever the floor proof of the collapsed panel holds, QUADPACK's dqk21 (oracle C port) returns the same
+    integral to rounding and exactly the rounding floor as its error estimate -- on both table branches."""
+    from oracle import capi
+    c = _rule()
+    eps = np.finfo(float).eps
+    rng = np.random.default_rng(17)
+    n_proved = n_unproved = 0
+    epochs = [(32, 42), (88, 98), (164, 174), (0, 10), (5, 45), (10, 110), (1, 2)]
+    for lam in np.concatenate([rng.gamma(0.5, 0.004, 300), rng.uniform(0.01, 0.5, 150), [1e-6, 1e-4, 2.5e-3]]):
+        if lam <= 0.0:
+            continue
+        for (a_lim, b_lim) in epochs:
+            y = 4.0 * lam * 0.5 * (b_lim - a_lim)
+            for series in ((True, False) if y * 1.4365 < 0.4999 else (False,)):
+                res, err, proved = _collapsed_panel(c, lam, a_lim, b_lim, series)
+                q_res, q_err, q_resabs, q_resasc = capi.qk21(float(a_lim), float(b_lim), float(lam))
+                if proved:
+                    n_proved += 1
+                    assert abs(res - q_res) <= 1e-13 * abs(q_res), (lam, a_lim, b_lim, series)
+                    assert abs(q_err - 50.0 * eps * q_resabs) <= 1e-12 * q_err, (lam, a_lim, b_lim, series, q_err)
+                    assert q_err != q_resasc
+                else:
+                    n_unproved += 1
+    assert n_proved > 2000 and n_unproved > 100, (n_proved, n_unproved)
