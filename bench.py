@@ -154,7 +154,7 @@ class ClockSampler:
 
 
 def profile_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one profile_kernel launch from the committed ncu --set full
+    """dram__bytes_read.sum + dram__bytes_write.sum of one profile-kernel launch from the committed ncu --set full
     capture of this workload (profiles/*_ncu_full_<workload>.txt), or None."""
     import glob
     import re
@@ -165,7 +165,7 @@ def profile_traffic(workload):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for line in open(files[-1]):
         if line.startswith("== "):
-            inside = "profile_kernel" in line
+            inside = "profile_kernel" in line or "profile_mom_kernel" in line
         m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
         if inside and m:
             total += float(m.group(2)) * scale.get(m.group(3), 1.0)
