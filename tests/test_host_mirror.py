@@ -210,3 +210,14 @@ def test_load_rates_hyphy_mode_with_stub_binary(tmp_path):
     assert np.array_equal(rates, golden["fixture/test-culled-rates"][5:60], equal_nan=True)
     with pytest.raises(Exception, match="hyphy not found"):
         driver.load_rates([None, str(tmp_path / "nope"), "t", towrite, out, 1, aln, [], [], 3, {}])
+
+
+def test_bench_reads_profile_kernel_traffic_from_the_committed_ncu_summary():
+    """bench.py's roofline.traffic comes from profiles/*_ncu_full_cfg2.txt; the block of the shipped profile kernel
+    (profile_mom_kernel, or profile_kernel in older captures) must be found."""
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    t = bench.profile_traffic("cfg2")
+    assert t is not None and 2.0e7 < t < 3.0e7        # 20 MB of rates read once, under 1 MB written (L2-resident profile)
