@@ -26,58 +26,48 @@ tr = np.fromfile(path, dtype=np.int64).reshape(-1, 32)
 tr = tr[tr[:, 1] != 0]
 W = tr.shape[0]
 smid, t_in, t_claim, t_first, t_exit, n_done = tr[:, 0], tr[:, 1], tr[:, 2], tr[:, 3], tr[:, 12], tr[:, 13]
-print("warps %d, SMs %d, items done %d" % (W, np.unique(smid).size, n_done.sum()))
+is_mom = bool((tr[:, 20] > 0).any())       # profile_mom_kernel stamps the phases of the second item instead
+print("kernel: %s; warps %d (one-warp CTAs), SMs %d, items done %d" % (
+    "profile_mom_kernel" if is_mom else "profile_kernel", W, np.unique(smid).size, n_done.sum()))
 sm_t0 = {s: t_in[smid == s].min() for s in np.unique(smid)}
 base = np.array([sm_t0[s] for s in smid])
 def q(x): return "min %.0f  p50 %.0f  p90 %.0f  max %.0f" % (x.min(), np.percentile(x, 50), np.percentile(x, 90), x.max())
 print("cycles since the SM's first warp entered:")
 print("  entry            ", q(t_in - base))
-print("  first claim done ", q(t_claim - base))
-print("  first group popped", q(t_first - base))
+if not is_mom:
+    print("  first claim done ", q(t_claim - base))
+    print("  first group popped", q(t_first - base))
 print("  exit             ", q(t_exit - base))
 print("items per warp histogram:", np.bincount(n_done))
-# per-item durations
-ends = tr[:, 4:12]
-dur = []
-for w in range(W):
-    prev = t_claim[w]
-    for k in range(min(n_done[w], 8)):
-        dur.append((k, ends[w, k] - (t_in[w] if k == 0 else ends[w, k - 1])))
-dur = np.array(dur)
-for k in range(dur[:, 0].max() + 1):
-    d = dur[dur[:, 0] == k, 1]
-    print("  item %d of a warp: n %5d  duration %s" % (k, d.size, q(d)))
-# per sub-partition: a CTA's warp w runs on sub-partition w; group warps by (sm, warp index in CTA)
-# the trace rows are ordered (block, warp): row index % 4 = warp in CTA
-widx = np.arange(tr.shape[0]) % 4
-key = smid * 4 + widx
-span_exit = []
-items_smsp = []
-for kk in np.unique(key):
-    m = key == kk
-    span_exit.append((t_exit[m] - base[m]).max())
-    items_smsp.append(n_done[m].sum())
-span_exit, items_smsp = np.array(span_exit), np.array(items_smsp)
-print("sub-partitions %d: items %s; last exit %s" % (span_exit.size, np.bincount(items_smsp), q(span_exit)))
-for n in np.unique(items_smsp):
-    print("  sub-partitions with %d items: %4d, last exit %s" % (n, (items_smsp == n).sum(), q(span_exit[items_smsp == n])))
-sm_span = np.array([ (t_exit[smid == s] - sm_t0[s]).max() for s in np.unique(smid)])
+if not is_mom:
+    ends = tr[:, 4:12]
+    dur = []
+    for w in range(W):
+        for k in range(min(n_done[w], 8)):
+            dur.append((k, ends[w, k] - (t_in[w] if k == 0 else ends[w, k - 1])))
+    dur = np.array(dur)
+    for k in range(dur[:, 0].max() + 1):
+        d = dur[dur[:, 0] == k, 1]
+        print("  item %d of a warp: n %5d  duration %s" % (k, d.size, q(d)))
+# per SM (the trace does not record which sub-partition a one-warp CTA landed on)
+items_sm = np.array([n_done[smid == s].sum() for s in np.unique(smid)])
+sm_span = np.array([(t_exit[smid == s] - sm_t0[s]).max() for s in np.unique(smid)])
+print("items per SM: min %d  p50 %d  max %d (%.2f per sub-partition on average)" % (
+    items_sm.min(), np.percentile(items_sm, 50), items_sm.max(), items_sm.mean() / 4.0))
 print("SM busy span (cycles):", q(sm_span))
-
-# inside the second item of a warp: groups 2..5 (steady state, three warps per sub-partition)
+# inside the second item of a warp: groups 2..5 (profile_kernel's stamps; steady state, warps sharing a sub-partition)
 g = tr[:, 16:32].reshape(-1, 4, 4)
-ok = (n_done >= 2) & (g[:, :, 2].min(axis=1) > 0)
-gg = g[ok]
-if not ok.any():
-    gg = np.zeros((1, 4, 4), dtype=np.int64)
-pop_to_built = (gg[:, :, 1] - gg[:, :, 0]).ravel()
-built_to_done = (gg[:, :, 2] - gg[:, :, 1]).ravel()
-done_to_pop = (gg[:, 1:, 0] - gg[:, :-1, 2]).ravel()
-print("second item, groups 2..5 (cycles):")
-print("  group popped -> tables built (exp chain, power tables, __syncwarp)", q(pop_to_built))
-print("  tables built -> contracted (128 DMMA = 2048 pipe cycles)          ", q(built_to_done))
-print("  contracted -> next group popped (rate rounds, queue)              ", q(done_to_pop))
-print("  whole group                                                       ", q((gg[:, 1:, 0] - gg[:, :-1, 0]).ravel()))
+ok = (n_done >= 2) & (g[:, :, 2].min(axis=1) > 0) & (tr[:, 20] == 0)
+if ok.any():
+    gg = g[ok]
+    pop_to_built = (gg[:, :, 1] - gg[:, :, 0]).ravel()
+    built_to_done = (gg[:, :, 2] - gg[:, :, 1]).ravel()
+    done_to_pop = (gg[:, 1:, 0] - gg[:, :-1, 2]).ravel()
+    print("second item, groups 2..5 (cycles):")
+    print("  group popped -> tables built (exp chain, power tables, __syncwarp)", q(pop_to_built))
+    print("  tables built -> contracted (128 DMMA = 2048 pipe cycles)          ", q(built_to_done))
+    print("  contracted -> next group popped (rate rounds, queue)              ", q(done_to_pop))
+    print("  whole group                                                       ", q((gg[:, 1:, 0] - gg[:, :-1, 0]).ravel()))
 
 # profile_mom_kernel: phases of the warp's second item
 m = (n_done >= 2) & (tr[:, 20] > 0)
