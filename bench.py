@@ -465,6 +465,8 @@ def run_ours(args, rank, world, local_rank):
     total_loci = L * world
     peaks, peak_src = measured_peaks()
     prof_s = prof_ms / args.steps * 1e-3
+    # what tapir_cuda_compute reports it launched (tapir_timing), not a guess from the grid size
+    kernel_name = "%s<%d>" % ("profile_mom_kernel" if tm.profile_moment_form else "profile_kernel", tm.profile_tile_points // 256)
     achieved_tf = 2.0 * evals_active / prof_s / 1e12      # one FP64 FMA per (active site, timepoint): DESIGN.md
     line = {
         "metric": METRIC, "value": total_evals / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -487,7 +489,7 @@ def run_ours(args, rank, world, local_rank):
                               "ms_per_step is the shipped two-stream configuration"},
         "roofline": {
             "bound": "tensor", "pipe": "FP64 (DMMA sub-pipe of the tensor pipe; shared with DFMA on B200)",
-            "kernel": "profile_mom_kernel" if T >= 1000 else "profile_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "kernel": kernel_name, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": profile_traffic(args.workload),
             "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has HBM and bf16 entries only; "
                            "tools/microbench/fp64_pipes.cu: DMMA 37.0, DFMA 36.6 TFLOP/s, one shared pipe)",

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TAPIR_CUDA_ABI_VERSION 1
+#define TAPIR_CUDA_ABI_VERSION 2
 
 /* error codes */
 #define TAPIR_OK 0
@@ -85,7 +85,11 @@ typedef struct tapir_timing {
     float quad_ms;     /* GK21/QAGS epoch-integral kernel(s) */
     float finalize_ms; /* per-locus reduction / picks / maxima kernel */
     int32_t launches;  /* kernel launches issued */
-    int32_t reserved;
+    /* what was launched for the profile: points per time tile (256 .. 2048), 1 = profile_mom_kernel (moment form) /
+     * 0 = profile_kernel (direct form), and how many of the batch's epochs took their sums from the moments */
+    int32_t profile_tile_points;
+    int32_t profile_moment_form;
+    int32_t moment_epochs;
 } tapir_timing;
 
 int tapir_cuda_version(void);
@@ -151,6 +155,22 @@ int tapir_cuda_nansum_rows(tapir_cuda_ctx *ctx, const double *matrix, int64_t n_
 /* vectorize(get_integral_over_times)(a, b, rates) -> integral[n], abserr[n], panels[n] (QAGS `last`) */
 int tapir_cuda_site_integrals(tapir_cuda_ctx *ctx, double a, double b, const double *rates, int64_t n,
                               double *integral, double *abserr, int32_t *panels);
+
+/* --- plan of the moment-functional epoch integrals (host only, no device needed; what tapir_cuda_upload decides
+ * per epoch when the profile runs in moment form, exported so that tests can pin it against QUADPACK) ---
+ * For the epoch [a, b] on a grid of n_tiles tiles of tile_points points: eligible != 0 when the sum over a locus'
+ * slowly decaying sites of scipy.integrate.quad's value (tapir/compute.py:50-52, 81-94) is taken as
+ * sum_j p[j] M[j][hb] from the 32 moments of block hb of tile `tile` (block centre tb); only sites with
+ * r_min <= rate <= r_max outside [w_lo, w_hi] (and below the moment class bound 0.01953125) are served that way. */
+typedef struct tapir_mom_epoch {
+    int32_t eligible;
+    int32_t tile, hb;
+    double tb;
+    double p[32];
+    double r_min, r_max;
+    double w_lo, w_hi;
+} tapir_mom_epoch;
+int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, tapir_mom_epoch *out);
 
 /* --- batched rate ingest (host only, no device needed): parse_site_rates' read half (compute.py:30-39) for
  * n_files HyPhy site-rate JSON files on n_threads threads into one CSR pack.  offsets[n_files + 1] is always

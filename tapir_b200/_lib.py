@@ -47,7 +47,23 @@ class Timing(ctypes.Structure):
         ("quad_ms", ctypes.c_float),
         ("finalize_ms", ctypes.c_float),
         ("launches", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("profile_tile_points", ctypes.c_int32),
+        ("profile_moment_form", ctypes.c_int32),
+        ("moment_epochs", ctypes.c_int32),
+    ]
+
+
+class MomEpoch(ctypes.Structure):
+    _fields_ = [
+        ("eligible", ctypes.c_int32),
+        ("tile", ctypes.c_int32),
+        ("hb", ctypes.c_int32),
+        ("tb", ctypes.c_double),
+        ("p", ctypes.c_double * 32),
+        ("r_min", ctypes.c_double),
+        ("r_max", ctypes.c_double),
+        ("w_lo", ctypes.c_double),
+        ("w_hi", ctypes.c_double),
     ]
 
 
@@ -78,6 +94,7 @@ SYMBOLS = {
     "tapir_cuda_pi_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "tapir_cuda_nansum_rows": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "tapir_cuda_site_integrals": (ctypes.c_int, [_vp, _dbl, _dbl, _vp, _i64, _vp, _vp, _vp]),
+    "tapir_mom_epoch_plan": (ctypes.c_int, [_dbl, _dbl, _i64, ctypes.c_int32, ctypes.POINTER(MomEpoch)]),
     "tapir_ingest_rates": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), _i64, ctypes.c_int, _dbl, _vp, _vp, _i64,
                                           ctypes.POINTER(_i64)]),
     "tapir_ingest_last_error": (ctypes.c_char_p, []),

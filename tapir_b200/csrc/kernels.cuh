@@ -40,6 +40,13 @@ struct ProfItem {      // one (locus, time tile, site range)
     int32_t locus;
     int32_t tile;        // time tile index: T0 = tile * TT
     int32_t slot;        // >= 0: row of the split workspace to write raw partial sums to; -1: direct
+    int32_t part;        // row of mom_int this item's moment-functional epoch sums go to (locus' first row + split index)
+    int32_t pad_;
+};
+
+// One epoch served by the moment functional (mom_epoch.h): the anchor block of its centre and the output column.
+struct MomEpochDev {
+    int32_t col, tile, hb, pad_;
 };
 
 struct QuadItem {      // up to kQuadBlock consecutive sites of one locus
@@ -65,6 +72,15 @@ struct EpochBatch {
     double center[kEpochsPerLaunch], half[kEpochsPerLaunch];
     double tm[kEpochsPerLaunch][10], tp[kEpochsPerLaunch][10];  // centre -/+ half*xgk[j] as dqk21 forms them
     int32_t new_half[kEpochsPerLaunch];  // half-length differs from the previous epoch in the batch
+    // moment-functional epochs (mom_epoch.h): a site of profile_mom_kernel's moment class whose rate lies in
+    // [rmin, rmax] and outside [wlo, whi] is integrated through the locus' moments, not here (rates compared as
+    // bit patterns: non-negative doubles order like unsigned integers)
+    int32_t mom_any;                     // some epoch of this launch is served by the moments
+    int32_t mom[kEpochsPerLaunch];
+    unsigned long long rmin_bits[kEpochsPerLaunch], rmax_bits[kEpochsPerLaunch];
+    unsigned long long wlo_bits[kEpochsPerLaunch], whi_bits[kEpochsPerLaunch];
+    double tb[kEpochsPerLaunch];         // centre of the anchor block (absolute time)
+    const double* mom_p;                 // device [e_total][32]: coefficients of the functional, row = output column
 };
 
 struct ProfArgs {
@@ -79,6 +95,12 @@ struct ProfArgs {
     int32_t n_items;
     int32_t n_tiles;
     long long* trace;    // measurement only (TAPIR_PROF_TRACE, profile_kernel<RH, true>): 32 words per warp
+    // moment-functional epoch sums (profile_mom_kernel only; n_mom_epochs = 0 otherwise)
+    const MomEpochDev* mom_epochs;
+    const double* mom_p;  // [e_total][32]
+    double* mom_int;      // [parts][e_total]
+    int32_t n_mom_epochs;
+    int32_t e_total;
 };
 
 template <int RH>
@@ -781,6 +803,17 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
             for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) bf[ks][nt] = MA[(4 * ks + fk) * SA + 8 * nt + fg];
+            // Epoch integrals of the item's slow sites: for every epoch whose centre lies in this tile the sum of the
+            // sites' first GK21 panels is a linear functional of the moments of the block around the centre
+            // (mom_epoch.h) -- one 32-term dot product per epoch, summed by a fixed shuffle tree.
+            for (int me = 0; me < args.n_mom_epochs; ++me) {
+                const MomEpochDev ep = args.mom_epochs[me];
+                if (ep.tile != item.tile) continue;
+                double v = __ldg(args.mom_p + 32 * ep.col + lane) * MA[lane * SA + ep.hb];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                if (lane == 0) args.mom_int[size_t(item.part) * args.e_total + ep.col] = v;
+            }
             __syncwarp();
             // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact);
             // eight row tiles at a time, so that the eight DMMAs of a tile are not one dependent chain
@@ -1100,6 +1133,21 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
     double* q = s_q[warp];
     uint16_t* qsrc = s_src[warp];
     const int row = 2 * eb.e_total + 4;
+    // bit e: the site takes the per-site path for epoch e (all epochs unless the moment functional serves it)
+    auto need_mask = [&](double lam) -> uint32_t {
+        const uint32_t all = (NE > 0) ? ((1u << NE) - 1u) : 1u;
+        if (!eb.mom_any) return all;
+        if (!(rate_is_active(lam) && rate_is_slow(lam))) return all;
+        const unsigned long long rb = (unsigned long long)__double_as_longlong(lam);
+        uint32_t need = 0;
+#pragma unroll 1
+        for (int e = 0; e < eb.n; ++e) {
+            const bool served = eb.mom[e] && rb >= eb.rmin_bits[e] && rb <= eb.rmax_bits[e] &&
+                                !(rb >= eb.wlo_bits[e] && rb <= eb.whi_bits[e]);
+            need |= served ? 0u : (1u << e);
+        }
+        return need;
+    };
 
     for (;;) {
         int it = 0;
@@ -1134,7 +1182,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
                 rs += notnan ? lam : 0.0;
                 nn += notnan ? 1.0 : 0.0;
                 nf += fin ? 1.0 : 0.0;
-                const bool act = fin && (16.0 * (lam * lam) != 0.0);
+                const bool act = fin && (16.0 * (lam * lam) != 0.0) && need_mask(lam) != 0u;
                 const unsigned ballot = __ballot_sync(0xffffffffu, act);
                 if (act) {
                     const int pos = (qn + __popc(ballot & ((1u << lane) - 1u))) & 63;
@@ -1156,6 +1204,8 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
                     // fast path: all exponent arguments stay well inside the normal range, every node value >= 0
                     const bool fast = on && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
                     const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps idle lanes' arithmetic finite
+                    const uint32_t need = on ? need_mask(lam2) : 0u;
+                    const bool in_moments = on && eb.mom_any && rate_is_active(lam2) && rate_is_slow(lam2);
                     PanelSums ps;
                     // one copy of the GK21 code, looped over the epochs: the fully unrolled form (4 x ~350
                     // instructions) thrashed the instruction cache once the warps ran out of step (18 % of the
@@ -1182,7 +1232,9 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
                         // common factor a e^{-c centre} h; |c * centre| <= 600 on this path
                         const double scale = (as * exp_bounded(-(cs * eb.center[e]))) * eb.half[e];
                         double result, abserr, resabs, resasc = 0.0;
-                        bool by_floor = gk21_collapsed(eb, e, scale, fast, ps, result, abserr);
+                        const bool wanted = (need >> e) & 1u;   // this (site, epoch) is not served by the moments
+                        const bool live = fast && wanted;
+                        bool by_floor = gk21_collapsed(eb, e, scale, live, ps, result, abserr);
                         if (!by_floor) {
                             // rare: some site's estimate is not the floor.  The node tables are rebuilt here (same
                             // function, same argument, same values) instead of being kept alive across the epochs.
@@ -1190,14 +1242,30 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
                             const double y = cs * eb.half[e];
 #pragma unroll
                             for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);
-                            by_floor = gk21_shared_exp(eb, e, scale, fast, D, R, result, abserr, resabs, resasc);
+                            by_floor = gk21_shared_exp(eb, e, scale, live, D, R, result, abserr, resabs, resasc);
                         }
                         // by_floor: abserr = 50 eps resabs <= 100 eps resabs and abserr != resasc, so dqagse's test
                         // (round-off exit above errbnd, plain acceptance below) passes either way
-                        const bool keep = fast && (by_floor || qags_first_panel_final(result, abserr, resabs, resasc));
-                        s_acc[warp][2 * e][lane] += keep ? result : 0.0;
-                        s_acc[warp][2 * e + 1][lane] += keep ? abserr : 0.0;
-                        if (on && !keep)  // rare: hand the site (by its position in the item) to quad_fix_kernel
+                        const bool keep = live && (by_floor || qags_first_panel_final(result, abserr, resabs, resasc));
+                        double vi = keep ? result : 0.0, ve = keep ? abserr : 0.0;
+                        if (eb.mom_any && eb.mom[e]) {
+                            // a site of the moment class that is integrated here (rate inside the epoch's window or
+                            // outside its range) is also part of the locus' moments: take out what the functional
+                            // adds for it -- a e^{-c tb} P(z), z = -64 c, the same polynomial on the same site
+                            const bool sub = in_moments && wanted;
+                            if (__any_sync(0xffffffffu, sub)) {
+                                const double* pc = eb.mom_p + 32 * eb.col[e];
+                                const double z = -64.0 * c;
+                                double hz = __ldg(pc + 31);
+#pragma unroll 1
+                                for (int k = 30; k >= 0; --k) hz = fma(hz, z, __ldg(pc + k));
+                                const double pv = (a * exp(-(c * eb.tb[e]))) * hz;
+                                if (sub) { vi -= pv; ve -= (kEpmach * 50.0) * pv; }
+                            }
+                        }
+                        s_acc[warp][2 * e][lane] += vi;
+                        s_acc[warp][2 * e + 1][lane] += ve;
+                        if (on && wanted && !keep)  // rare: hand the site (by its position in the item) to quad_fix_kernel
                             atomicOr(&s_flag[warp][e][src >> 5], 1u << (src & 31));
                     }
                     __syncwarp();
@@ -1315,6 +1383,10 @@ struct FinalArgs {
     double* mean_rate;
     int64_t* n_finite;
     int64_t* n_multi;
+    // moment-functional epoch sums written by profile_mom_kernel: rows part_base[l] .. part_base[l+1]-1 of mom_int
+    const int64_t* part_base;    // [L+1]
+    const double* mom_int;       // [parts][E]
+    unsigned long long mom_mask; // bit e: epoch e is served by the moments
 };
 
 __global__ void __launch_bounds__(128) finalize_kernel(const FinalArgs fa)
@@ -1370,6 +1442,14 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalArgs fa)
         for (int64_t q = q0; q < q1; ++q) {
             si += fa.qpart[q * row + 2 * e];
             se += fa.qpart[q * row + 2 * e + 1];
+        }
+        if ((fa.mom_mask >> e) & 1ull) {
+            // the locus' slow sites: sum of their first GK21 panels from the moments; every one of them has the
+            // rounding floor 50 eps resabs (= 50 eps result, the integrand is >= 0) as QUADPACK's error estimate
+            double sm = 0.0;
+            for (int64_t p = fa.part_base[l]; p < fa.part_base[l + 1]; ++p) sm += fa.mom_int[p * fa.E + e];
+            si += sm;
+            se += (kEpmach * 50.0) * sm;
         }
         fa.integral[l * fa.E + e] = si;
         fa.abserr[l * fa.E + e] = se;

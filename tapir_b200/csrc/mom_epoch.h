@@ -1,0 +1,178 @@
+// mom_epoch.h -- host-side plan of the moment-functional epoch integrals (no CUDA in this file).
+//
+// profile_mom_kernel represents a slowly decaying site (rate < 0.01953125) of a time tile by 32 moments per 128-point
+// block,  M[k][hb] = sum_s a_s e^{-c_s T0} (-64 c_s)^k e^{-c_s (128 hb + 64)}  (kernels.cuh).  For such a site the
+// first GK21 panel over an epoch [A, B] (centre C, half-length h; tapir/compute.py:50-52 = scipy quad = QUADPACK
+// dqk21) is, with y = c h and the rule's pair sums written as their power series (gk21.cuh, c_ak / c_bk),
+//
+//     V_s = a h e^{-cC} [ C sum_n ak_n y^{2n}  -  h y sum_n bk_n y^{2n} ],
+//
+// and with  e^{-cC} = e^{-c T0} e^{-c(128 hb + 64)} e^{-c d},  d = C - (T0 + 128 hb + 64) in [-64, 64)  and
+// z = -64 c  (so y = -z h/64) it is a polynomial in z times the site's moment weights:
+//
+//     sum_s V_s = sum_j p_j M[j][hb],   P(z) = h [sum_k (d/64)^k z^k / k!] [sum_n C ak_n (h/64)^{2n} z^{2n}
+//                                                                         + h bk_n (h/64)^{2n+1} z^{2n+1}]  mod z^32.
+//
+// So the epoch sums of compute.py:81-94 over all such sites are one 32-term dot product per (locus, epoch) with
+// the moments the profile needs anyway -- no per-site exponential, no second pass over the rates.
+//
+// What QUADPACK returns for the site must still be this panel with the rounding floor as its error estimate
+// (abserr = 50 eps resabs, accepted by dqagse as is).  quad_kernel proves that per site from a lower bound of
+// resasc (kernels.cuh, gk21_collapsed); here the same proof is carried out once per EPOCH as a statement about
+// rates:  with e0 <= 32 eps resk (y <= 1: Kronrod and Gauss agree to < 1e-19, what dqk21 sees is rounding noise)
+// the floor wins and resasc > floor whenever  resasc / resk >= 2.33e-8, and
+//
+//     resasc/resk >= sum_{j=4,5} wgk_j (|f1_j - m| + |f2_j - m|) / resk >= (2 h / resk_rel) sum_j wgk_j x_j |phi_j(c)|,
+//     phi_j(c) = c C sinhc(c h x_j) - cosh(c h x_j),     resk_rel = C Ak(y) - h y Bk(y) <= 3.1 C   (y <= 1),
+//
+// which only fails in a narrow window of rates around c = 1/C (the site whose PI curve peaks at the epoch centre).
+// The plan returns that window (with a 40x margin on the threshold); sites inside it, above r_max or below r_min
+// take the per-site path of quad_kernel for this epoch, and their polynomial value is subtracted there.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+namespace tapir {
+
+constexpr double kMomRateBound = 0.01953125;  // 64 c <= 5: the moment class of profile_mom_kernel (rate_is_slow)
+constexpr int kMomTerms = 32;
+
+struct MomEpochPlan {
+    int32_t eligible;    // 0: every site takes the per-site path for this epoch
+    int32_t tile, hb;    // anchor block: the 128-point block that contains the epoch centre
+    double tb;           // its centre, T0 + 128 hb + 64 (absolute time)
+    double p[kMomTerms]; // integral = sum_j p[j] M[j][hb]
+    double r_min, r_max; // rates of the moment class that may use the functional: r_min <= r <= r_max ...
+    double w_lo, w_hi;   // ... except w_lo <= r <= w_hi (empty when w_lo > w_hi)
+};
+
+namespace momdetail {
+static const long double kX[10] = {
+    0.995657163025808080735527280689003L, 0.973906528517171720077964012084452L, 0.930157491355708226001207180059508L,
+    0.865063366688984510732096688423493L, 0.780817726586416897063717578345042L, 0.679409568299024406234327365114874L,
+    0.562757134668604683339000099272694L, 0.433395394129247190799265943165784L, 0.294392862701460198131126603103866L,
+    0.148874338981631210884826001129720L};
+static const long double kW[11] = {
+    0.011694638867371874278064396062192L, 0.032558162307964727478818972459390L, 0.054755896574351996031381300244580L,
+    0.075039674810919952767043140916190L, 0.093125454583697605535065465083366L, 0.109387158802297641899210590325805L,
+    0.123491976262065851077958109585166L, 0.134709217311473325928054001771707L, 0.142775938577060080797094273138717L,
+    0.147739104901338491374841515972068L, 0.149445554002916905664936468389821L};
+
+// S(c) = sum_{j=4,5} wgk_j x_j |phi_j(c)|
+inline long double phi(int j, long double c, long double C, long double h)
+{
+    const long double u = c * h * kX[j];
+    const long double sinhc = (u < 1e-4L) ? 1.0L + u * u / 6.0L : sinhl(u) / u;
+    return c * C * sinhc - coshl(u);
+}
+inline long double S(long double c, long double C, long double h)
+{
+    return kW[4] * kX[4] * fabsl(phi(4, c, C, h)) + kW[5] * kX[5] * fabsl(phi(5, c, C, h));
+}
+}  // namespace momdetail
+
+// Plan of the epoch [a, b] on a grid of n_tiles tiles of TT points (TT a multiple of 128).
+inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, MomEpochPlan* out)
+{
+    using namespace momdetail;
+    std::memset(out, 0, sizeof *out);
+    out->w_lo = 1.0;
+    out->w_hi = 0.0;
+    if (!(a >= 0.0) || !(b > a) || !std::isfinite(b)) return;
+    const long double C = 0.5L * ((long double)a + (long double)b), h = 0.5L * ((long double)b - (long double)a);
+    // the rounded centre / half-length are what dqk21 (and quad_kernel) use: keep to epochs where they are exact
+    if (double(C) != 0.5 * (a + b) || double(h) != 0.5 * (b - a) || (long double)double(C) != C || (long double)double(h) != h) return;
+    if (h < 0.5L || h > 32.0L) return;
+    if (!(C < (long double)n_tiles * TT)) return;
+    const int64_t gb = int64_t(floorl(C / 128.0L));
+    const int nb = TT / 128;
+    const long double tb = 128.0L * gb + 64.0L, d = C - tb;
+    // ---- rate range ----
+    long double r_max = kMomRateBound;                        // class bound (exclusive; applied by the class test)
+    r_max = fminl(r_max, 1.0L / (4.0L * h));                  // y = c h <= 1
+    r_max = fminl(r_max, 5.0L / (4.0L * (fabsl(d) + h)));     // series remainder as for the profile: (|d| + h) c <= 5
+    r_max = fminl(r_max, 150.0L / (long double)b);            // c b <= 600: every exponential stays a normal number
+    const long double r_min = 2.5e-16L;                       // a = 16 r^2 >= 1e-30: result > uflow / (50 eps)
+    if (!(r_max > 1e-12L)) return;
+    // ---- window of rates where the floor proof may fail ----
+    const long double tau = 1e-6L * 3.1L * C / (2.0L * h);    // S(c) >= tau  =>  resasc / resk >= 1e-6 >= 40 x 2.33e-8
+    const long double c_max = 4.0L * r_max;
+    if (!(S(0.0L, C, h) > 2.0L * tau)) return;                // the whole range would be window (C/h ~ 1e5)
+    long double root[2];
+    for (int k = 0; k < 2; ++k) {
+        const int j = 4 + k;
+        if (phi(j, c_max, C, h) <= 0.0L) { root[k] = HUGE_VALL; continue; }
+        long double lo = 0.0L, hi = c_max;                    // phi(0+) = -1 < 0 < phi(c_max); phi_j increases (C >= h)
+        for (int it = 0; it < 200; ++it) {
+            const long double mid = 0.5L * (lo + hi);
+            if (phi(j, mid, C, h) <= 0.0L) lo = mid; else hi = mid;
+        }
+        root[k] = 0.5L * (lo + hi);
+    }
+    const long double c_first = fminl(root[0], root[1]), c_last = fmaxl(root[0], root[1]);
+    long double c_lo, c_hi;
+    {   // below the first root S decreases from S(0): last point with S >= tau
+        const long double cA = fminl(c_first, c_max);
+        if (S(cA, C, h) >= tau) c_lo = cA;
+        else {
+            long double lo = 0.0L, hi = cA;
+            for (int it = 0; it < 200; ++it) {
+                const long double mid = 0.5L * (lo + hi);
+                if (S(mid, C, h) >= tau) lo = mid; else hi = mid;
+            }
+            c_lo = lo;
+        }
+    }
+    if (c_last >= c_max) c_hi = (c_first > c_max && S(c_max, C, h) >= tau) ? -1.0L : c_max;
+    else if (S(c_max, C, h) < tau) c_hi = c_max;
+    else {  // above the last root S increases: first point with S >= tau
+        long double lo = c_last, hi = c_max;
+        for (int it = 0; it < 200; ++it) {
+            const long double mid = 0.5L * (lo + hi);
+            if (S(mid, C, h) >= tau) hi = mid; else lo = mid;
+        }
+        c_hi = hi;
+    }
+    double w_lo = 1.0, w_hi = 0.0;
+    if (c_hi >= c_lo) {
+        w_lo = double(c_lo / 4.0L * (1.0L - 1e-9L));
+        w_hi = double(c_hi / 4.0L * (1.0L + 1e-9L));
+        if (w_lo <= double(r_min) && w_hi >= double(r_max)) return;   // nothing left
+    }
+    // ---- the functional ----
+    long double E[kMomTerms], G[kMomTerms], fact = 1.0L, dk = 1.0L;
+    for (int k = 0; k < kMomTerms; ++k) {
+        if (k) { fact *= k; dk *= d / 64.0L; }
+        E[k] = dk / fact;
+        G[k] = 0.0L;
+    }
+    const long double r = h / 64.0L;
+    long double f2n = 1.0L, rp = 1.0L;  // (2n)!, r^{2n}
+    for (int n = 0; 2 * n < kMomTerms; ++n) {
+        if (n) { f2n *= (2 * n - 1) * (2 * n); rp *= r * r; }
+        long double sa = (n == 0) ? kW[10] : 0.0L, sb = 0.0L;
+        for (int j = 0; j < 10; ++j) {
+            const long double x2n = powl(kX[j], 2 * n);
+            sa += 2.0L * kW[j] * x2n;
+            sb += 2.0L * kW[j] * x2n * kX[j] * kX[j];
+        }
+        G[2 * n] = C * (sa / f2n) * rp;                                              // C ak_n (h/64)^{2n}
+        if (2 * n + 1 < kMomTerms) G[2 * n + 1] = h * (sb / (f2n * (2 * n + 1))) * rp * r;   // h bk_n (h/64)^{2n+1}
+    }
+    for (int j = 0; j < kMomTerms; ++j) {
+        long double s = 0.0L;
+        for (int k = 0; k <= j; ++k) s += E[k] * G[j - k];
+        out->p[j] = double(h * s);
+    }
+    out->eligible = 1;
+    out->tile = int32_t(gb / nb);
+    out->hb = int32_t(gb % nb);
+    out->tb = double(tb);
+    out->r_min = double(r_min);
+    out->r_max = double(r_max);
+    out->w_lo = w_lo;
+    out->w_hi = w_hi;
+}
+
+}  // namespace tapir

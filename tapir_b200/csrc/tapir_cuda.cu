@@ -17,6 +17,7 @@
 #include <chrono>
 
 #include "kernels.cuh"
+#include "mom_epoch.h"
 
 using namespace tapir;
 
@@ -89,9 +90,13 @@ struct Plan {
     int32_t K = 0, E = 0;
     uint32_t flags = 0;
     int rh = 4;       // profile kernel variant
+    bool mom_form = false;  // profile_mom_kernel<rh> (moment form) instead of profile_kernel<rh>
     int32_t TT = 1024, n_tiles = 1;
-    int64_t n_prof_items = 0, n_quad_items = 0, ws_rows = 0;
+    int64_t n_prof_items = 0, n_quad_items = 0, ws_rows = 0, n_parts = 0;
     std::vector<EpochBatch> batches;
+    std::vector<MomEpochPlan> mom;   // per epoch (input order): is it served by the moment functional, and how
+    int32_t n_mom = 0;
+    uint64_t mom_mask = 0;
     size_t small_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, small_bytes = 0;  // layout of d_small / h_small
     bool valid = false;
 };
@@ -113,9 +118,9 @@ struct Lane {
     Plan plan;
     // inputs: the rate stream, and ONE buffer holding every work list (a single H2D copy per batch)
     DevBuf d_rates, d_work, d_counter;
-    DevView d_prof_items, d_quad_items, d_nsplit, d_ws_base, d_qitem_begin, d_time_idx;
+    DevView d_prof_items, d_quad_items, d_nsplit, d_ws_base, d_qitem_begin, d_time_idx, d_part_base, d_mom_epochs, d_mom_p;
     // intermediates
-    DevBuf d_ws, d_tile_max, d_tile_arg, d_qpart, d_fix;
+    DevBuf d_ws, d_tile_max, d_tile_arg, d_qpart, d_fix, d_mom_int;
     // results: the profile, and ONE buffer holding every small per-locus vector (a single D2H copy per batch)
     DevBuf d_pi_net, d_small;
     DevView d_pi_times, d_integral, d_abserr, d_max_pi, d_argmax_t, d_argmax_epoch, d_mean_rate, d_n_finite, d_n_multi;
@@ -124,7 +129,8 @@ struct Lane {
     tapir_results pending_out = {};
     int64_t pending_row0 = 0;
     bool pending = false;
-    DevBuf* all_bufs[10] = {&d_rates, &d_work, &d_counter, &d_ws, &d_tile_max, &d_tile_arg, &d_qpart, &d_fix, &d_pi_net, &d_small};
+    DevBuf* all_bufs[11] = {&d_rates, &d_work, &d_counter, &d_ws, &d_tile_max, &d_tile_arg, &d_qpart, &d_fix, &d_pi_net, &d_small,
+                            &d_mom_int};
 };
 
 constexpr int kLanes = 8;  // upper bound; ctx->n_lanes of them rotate (TAPIR_CUDA_LANES)
@@ -139,7 +145,13 @@ struct tapir_cuda_ctx {
     long long* prof_trace = nullptr;  // TAPIR_PROF_TRACE=<file>: per-warp time stamps of profile_kernel, dumped by tapir_cuda_compute
     size_t prof_trace_words = 0;
     std::string prof_trace_path;
-    int prof_mom = 1;        // tiles of 1024+ points use profile_mom_kernel (slow sites in moment form); TAPIR_PROF_MOM=0: profile_kernel
+    int prof_mom = 1;        // the tile-size model may pick profile_mom_kernel (slow sites in moment form); TAPIR_PROF_MOM=0: never
+    int mom_int = 1;         // epoch integrals of the moment class from the locus' moments (mom_epoch.h); TAPIR_MOM_INT=0: per site
+    int last_rh = 0, last_mom_form = 0, last_n_mom = 0;  // what the last tapir_cuda_compute launched (tapir_timing)
+    // per-device launch configuration, filled once in tapir_cuda_create (index: log2(RH))
+    int prof_per_sm[4] = {0, 0, 0, 0}, mom_per_sm[4] = {0, 0, 0, 0};
+    int prof_ctas_cap = 0, quad_ctas_cap = 0;  // TAPIR_PROF_CTAS_PER_SM / TAPIR_QUAD_CTAS_PER_SM (co-residency experiments)
+    int force_rh = 0;                          // TAPIR_CUDA_RH
     int trace = 0;           // TAPIR_CUDA_TRACE=1: tapir_cuda_run prints the timeline of its chunks to stderr
     std::string last_error;
     Lane lanes[kLanes];
@@ -198,90 +210,94 @@ int bind(tapir_cuda_ctx* ctx)
     return TAPIR_OK;
 }
 
-// Estimated FP64 instructions per site for one time tile of the RH variant (table build + FMAs).
-double tile_cost(int rh, int64_t T)
+// Tile-size model.  Cost of one locus' profile in FP64 lane-operations per site, for the direct form
+// (profile_kernel<RH>: TT = 256 RH points per tile, one FMA per (site, point) plus the power tables) and for the
+// moment form (profile_mom_kernel<RH>, RH >= 4: a quarter of the FMAs, cheaper tables, plus a per-item moments ->
+// times product of 128 TT/1024 DMMAs that is shared by the item's sites).  `sites` = mean sites per locus.
+// Calibrated against profiles/r02_tile_sweep.txt.
+double tile_cost(int rh, bool mom, int64_t T, double sites)
 {
     const int64_t TT = 32 * 8 * rh;
     const int64_t nt = (T + TT - 1) / TT;
-    const double gen = 45.0 + 32.0 + 8.0 * rh + (nt > 1 ? 28.0 : 0.0);
-    return double(nt) * (double(TT) + gen);
+    const double s = std::max(sites, 1.0);
+    if (!mom) {
+        const double gen = 45.0 + 32.0 + 8.0 * rh + (nt > 1 ? 28.0 : 0.0);
+        return double(nt) * (double(TT) + gen + double(TT) / s);
+    }
+    const double gen = 75.0 + 2.0 * double(TT / 128) + (nt > 1 ? 28.0 : 0.0);
+    const double per_item = 32768.0 * double(TT / 1024) + double(TT);   // moments -> times, epilogue
+    return double(nt) * (0.25 * double(TT) + gen + per_item / s);
 }
 
-int choose_rh(int64_t T)
-{
-    int best = 1;
-    double bc = tile_cost(1, T);
-    for (int rh : {2, 4, 8}) {
-        const double c = tile_cost(rh, T);
-        if (c < bc) { bc = c; best = rh; }
-    }
-    return best;
-}
+void choose_tile(const tapir_cuda_ctx* ctx, int64_t T, double sites, int& rh_out, bool& mom_out);
 
 template <int RH>
-cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, int64_t n_items)
+cudaError_t configure_profile(tapir_cuda_ctx* ctx, int idx)
 {
-    static bool configured[64] = {false};
     using Cfg = ProfCfg<RH>;
-    if (!configured[ctx->device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(profile_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(Cfg::SmemBytes));
-        if (e != cudaSuccess) return e;
-        configured[ctx->device & 63] = true;
-    }
-    int per_sm = 0;
-    cudaError_t e =
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, profile_kernel<RH>, kProfWarps * 32, Cfg::SmemBytes);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    if (const char* env = getenv("TAPIR_PROF_CTAS_PER_SM")) {  // tuning override (co-residency experiments)
-        const int v = atoi(env);
-        if (v >= 1 && v < per_sm) per_sm = v;
-    }
-    int64_t grid = int64_t(ctx->sm_count) * per_sm;
-    const int64_t need = (n_items + kProfWarps - 1) / kProfWarps;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
+    cudaError_t e = cudaFuncSetAttribute(profile_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prof_per_sm[idx], profile_kernel<RH>, kProfWarps * 32, Cfg::SmemBytes);
+    if (e == cudaSuccess && ctx->prof_trace)
+        e = cudaFuncSetAttribute(profile_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
     if constexpr (RH >= 4) {
-        if (ctx->prof_mom) {  // moment form: its own shared-memory layout and occupancy
+        using Mom = MomCfg<RH>;
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(profile_mom_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom::SmemBytes));
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->mom_per_sm[idx], profile_mom_kernel<RH>, kProfWarps * 32, Mom::SmemBytes);
+        if (e == cudaSuccess && ctx->prof_trace)
+            e = cudaFuncSetAttribute(profile_mom_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom::SmemBytes));
+    }
+    return e;
+}
+
+int rh_index(int rh) { return rh == 1 ? 0 : rh == 2 ? 1 : rh == 4 ? 2 : 3; }
+
+template <int RH>
+cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, int64_t n_items, bool mom)
+{
+    using Cfg = ProfCfg<RH>;
+    const int idx = rh_index(RH);
+    int per_sm = std::max(1, mom ? ctx->mom_per_sm[idx] : ctx->prof_per_sm[idx]);
+    if (ctx->prof_ctas_cap >= 1 && ctx->prof_ctas_cap < per_sm) per_sm = ctx->prof_ctas_cap;  // TAPIR_PROF_CTAS_PER_SM
+    const int64_t need = (n_items + kProfWarps - 1) / kProfWarps;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(need, int64_t(ctx->sm_count) * per_sm));
+    if constexpr (RH >= 4) {
+        if (mom) {
             using Mom = MomCfg<RH>;
-            static bool mom_configured[64] = {false};
-            static int mom_per_sm[64] = {0};
-            if (!mom_configured[ctx->device & 63]) {
-                e = cudaFuncSetAttribute(profile_mom_kernel<RH>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom::SmemBytes));
-                if (e == cudaSuccess)
-                    e = cudaFuncSetAttribute(profile_mom_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom::SmemBytes));
-                if (e == cudaSuccess)
-                    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mom_per_sm[ctx->device & 63], profile_mom_kernel<RH>,
-                                                                      kProfWarps * 32, Mom::SmemBytes);
-                if (e != cudaSuccess) return e;
-                mom_configured[ctx->device & 63] = true;
-            }
-            int mper = std::max(1, mom_per_sm[ctx->device & 63]);
-            if (const char* env = getenv("TAPIR_PROF_CTAS_PER_SM")) {
-                const int v = atoi(env);
-                if (v >= 1 && v < mper) mper = v;
-            }
-            const int64_t mgrid = std::max<int64_t>(1, std::min<int64_t>(need, int64_t(ctx->sm_count) * mper));
             if (pa.trace)
-                profile_mom_kernel<RH, true><<<unsigned(mgrid), kProfWarps * 32, Mom::SmemBytes, ln.stream>>>(pa);
+                profile_mom_kernel<RH, true><<<unsigned(grid), kProfWarps * 32, Mom::SmemBytes, ln.stream>>>(pa);
             else
-                profile_mom_kernel<RH><<<unsigned(mgrid), kProfWarps * 32, Mom::SmemBytes, ln.stream>>>(pa);
+                profile_mom_kernel<RH><<<unsigned(grid), kProfWarps * 32, Mom::SmemBytes, ln.stream>>>(pa);
             return cudaGetLastError();
         }
     }
-    if (pa.trace) {  // measurement only
-        static bool trace_configured[64] = {false};
-        if (!trace_configured[ctx->device & 63]) {
-            e = cudaFuncSetAttribute(profile_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SmemBytes));
-            if (e != cudaSuccess) return e;
-            trace_configured[ctx->device & 63] = true;
-        }
+    if (pa.trace)  // measurement only
         profile_kernel<RH, true><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
-        return cudaGetLastError();
-    }
-    profile_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
+    else
+        profile_kernel<RH><<<unsigned(grid), kProfWarps * 32, Cfg::SmemBytes, ln.stream>>>(pa);
     return cudaGetLastError();
+}
+
+void choose_tile(const tapir_cuda_ctx* ctx, int64_t T, double sites, int& rh_out, bool& mom_out)
+{
+    rh_out = 1;
+    mom_out = false;
+    double best = tile_cost(1, false, T, sites);
+    for (int rh : {2, 4, 8}) {
+        const double c = tile_cost(rh, false, T, sites);
+        if (c < best) { best = c; rh_out = rh; mom_out = false; }
+    }
+    if (ctx->prof_mom)
+        for (int rh : {4, 8}) {
+            const double c = tile_cost(rh, true, T, sites);
+            if (c < best) { best = c; rh_out = rh; mom_out = true; }
+        }
+    if (ctx->force_rh) {  // TAPIR_CUDA_RH: 1, 2, 4 or 8
+        rh_out = ctx->force_rh;
+        mom_out = ctx->prof_mom && rh_out >= 4;
+    }
 }
 
 void fill_batches(Plan& plan, const double* epoch_ab)
@@ -317,6 +333,17 @@ void fill_batches(Plan& plan, const double* epoch_ab)
                 eb.tp[k][j] = eb.center[k] + absc;
             }
             eb.new_half[k] = (k == 0) || (eb.half[k] != eb.half[k - 1]);
+            if (size_t(e) < plan.mom.size() && plan.mom[e].eligible) {
+                const MomEpochPlan& mp = plan.mom[e];
+                auto bits = [](double v) { unsigned long long u; memcpy(&u, &v, 8); return u; };
+                eb.mom_any = 1;
+                eb.mom[k] = 1;
+                eb.rmin_bits[k] = bits(mp.r_min);
+                eb.rmax_bits[k] = bits(mp.r_max);
+                eb.wlo_bits[k] = bits(mp.w_lo);
+                eb.whi_bits[k] = bits(mp.w_hi);
+                eb.tb[k] = mp.tb;
+            }
             if (a < 0.0) eb.nonneg = 0;
             eb.bmax = std::max(eb.bmax, std::max(std::fabs(a), std::fabs(b)));
         }
@@ -424,6 +451,13 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         if ((env = getenv("TAPIR_CUDA_RAMP"))) ctx->ramp = atoi(env);
         if ((env = getenv("TAPIR_CUDA_TRACE"))) ctx->trace = atoi(env) != 0;
         if ((env = getenv("TAPIR_PROF_MOM"))) ctx->prof_mom = atoi(env) != 0;
+        if ((env = getenv("TAPIR_MOM_INT"))) ctx->mom_int = atoi(env) != 0;
+        if ((env = getenv("TAPIR_PROF_CTAS_PER_SM"))) ctx->prof_ctas_cap = atoi(env);
+        if ((env = getenv("TAPIR_QUAD_CTAS_PER_SM"))) ctx->quad_ctas_cap = atoi(env);
+        if ((env = getenv("TAPIR_CUDA_RH"))) {
+            const int v = atoi(env);
+            if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_rh = v;
+        }
         if ((env = getenv("TAPIR_PROF_TRACE")) && env[0]) {
             ctx->prof_trace_path = env;
             ctx->prof_trace_words = size_t(prop.multiProcessorCount) * 32 * 32;
@@ -432,7 +466,11 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
             ctx->use_graphs = 0;
         }
     }
-    e = cudaSuccess;
+    // launch configuration of the profile kernels on this device (shared-memory opt-in, resident CTAs per SM)
+    e = configure_profile<1>(ctx, 0);
+    if (e == cudaSuccess) e = configure_profile<2>(ctx, 1);
+    if (e == cudaSuccess) e = configure_profile<4>(ctx, 2);
+    if (e == cudaSuccess) e = configure_profile<8>(ctx, 3);
     for (Lane& ln : ctx->lanes) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.stream_q, cudaStreamNonBlocking);
@@ -483,6 +521,7 @@ int tapir_cuda_destroy(tapir_cuda_ctx* ctx)
     if (ctx->stream_h2d) { cudaStreamSynchronize(ctx->stream_h2d); cudaStreamDestroy(ctx->stream_h2d); }
     if (ctx->stream_d2h) { cudaStreamSynchronize(ctx->stream_d2h); cudaStreamDestroy(ctx->stream_d2h); }
     if (ctx->gather_mapped) cudaIpcCloseMemHandle(ctx->gather_mapped);
+    if (ctx->prof_trace) cudaFree(ctx->prof_trace);
     DevBuf* bufs[] = {&ctx->d_scratch_a, &ctx->d_scratch_b, &ctx->d_scratch_c, &ctx->d_flush, &ctx->d_counter, &ctx->d_gather};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev)
@@ -541,13 +580,22 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     plan.E = p->n_epochs;
     plan.flags = p->flags;
     plan.nnz = plan.L ? off[plan.L] - base : 0;
-    plan.rh = choose_rh(std::max<int64_t>(plan.T, 1));
-    if (const char* env = getenv("TAPIR_CUDA_RH")) {  // tuning override: 1, 2, 4 or 8
-        const int v = atoi(env);
-        if (v == 1 || v == 2 || v == 4 || v == 8) plan.rh = v;
-    }
+    choose_tile(ctx, std::max<int64_t>(plan.T, 1), plan.L ? double(plan.nnz) / double(plan.L) : 1.0, plan.rh, plan.mom_form);
     plan.TT = 32 * 8 * plan.rh;
     plan.n_tiles = int32_t(std::max<int64_t>(1, (plan.T + plan.TT - 1) / plan.TT));
+    // epochs whose sums come out of the profile's moments (mom_epoch.h); the others, and the sites outside an
+    // epoch's rate range, are integrated per site by quad_kernel
+    plan.mom.assign(size_t(plan.E), MomEpochPlan());
+    plan.n_mom = 0;
+    plan.mom_mask = 0;
+    if (ctx->mom_int && plan.mom_form && plan.T > 0 && plan.L > 0)
+        for (int e = 0; e < plan.E; ++e) {
+            mom_epoch_plan(p->epoch_ab[2 * e], p->epoch_ab[2 * e + 1], plan.n_tiles, plan.TT, &plan.mom[size_t(e)]);
+            if (plan.mom[size_t(e)].eligible) {
+                ++plan.n_mom;
+                plan.mom_mask |= uint64_t(1) << e;
+            }
+        }
     fill_batches(plan, p->epoch_ab);
     const int64_t L = plan.L;
 
@@ -562,14 +610,16 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
         chunk_sites = std::max<int64_t>(1024, ((chunk_sites + 31) / 32) * 32);
     }
     std::vector<int32_t> nsplit(L);
-    std::vector<int64_t> ws_base(L), qitem_begin(L + 1);
-    int64_t n_prof = 0, n_quad = 0, ws_rows = 0;
+    std::vector<int64_t> ws_base(L), qitem_begin(L + 1), part_base(L + 1);
+    int64_t n_prof = 0, n_quad = 0, ws_rows = 0, n_parts = 0;
     for (int64_t l = 0; l < L; ++l) {
         const int64_t s = off[l + 1] - off[l];
         if (s > INT32_MAX) return fail(ctx, TAPIR_E_INVALID, "locus %lld has too many sites", (long long)l);
         int64_t ns = (s + chunk_sites - 1) / chunk_sites;
         if (ns < 1) ns = 1;
         nsplit[l] = int32_t(ns);
+        part_base[l] = n_parts;
+        n_parts += ns;
         ws_base[l] = ws_rows;
         if (ns > 1) ws_rows += ns * plan.n_tiles;
         n_prof += ns * plan.n_tiles;
@@ -577,7 +627,9 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
         n_quad += (s + kQuadBlock - 1) / kQuadBlock;
     }
     qitem_begin[L] = n_quad;
-    if (n_prof >= (int64_t(1) << 31) || n_quad >= (int64_t(1) << 31))
+    part_base[L] = n_parts;
+    plan.n_parts = n_parts;
+    if (n_prof >= (int64_t(1) << 31) || n_quad >= (int64_t(1) << 31) || n_parts >= (int64_t(1) << 31))
         return fail(ctx, TAPIR_E_INVALID, "batch too large: split it into several calls");
     plan.n_prof_items = n_prof;
     plan.n_quad_items = n_quad;
@@ -587,9 +639,12 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     const size_t b_prof = size_t(n_prof) * sizeof(ProfItem), b_quad = size_t(n_quad) * sizeof(QuadItem);
     const size_t b_ns = size_t(L) * sizeof(int32_t), b_wb = size_t(L) * sizeof(int64_t);
     const size_t b_qb = size_t(L + 1) * sizeof(int64_t), b_ti = size_t(plan.K) * sizeof(int64_t);
+    const size_t b_pb = size_t(L + 1) * sizeof(int64_t), b_me = size_t(plan.n_mom) * sizeof(MomEpochDev);
+    const size_t b_mp = size_t(plan.E) * kMomTerms * sizeof(double);
     auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
     const size_t o_prof = 0, o_quad = o_prof + al(b_prof), o_ns = o_quad + al(b_quad), o_wb = o_ns + al(b_ns),
-                 o_qb = o_wb + al(b_wb), o_ti = o_qb + al(b_qb), total = o_ti + al(b_ti);
+                 o_qb = o_wb + al(b_wb), o_ti = o_qb + al(b_qb), o_pb = o_ti + al(b_ti), o_me = o_pb + al(b_pb),
+                 o_mp = o_me + al(b_me), total = o_mp + al(b_mp);
     CU(ctx, ln.h_stage.ensure(total));
     char* hs = ln.h_stage.as<char>();
     ProfItem* pi = reinterpret_cast<ProfItem*>(hs + o_prof);
@@ -612,6 +667,8 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
                     it.locus = int32_t(l);
                     it.tile = tile;
                     it.slot = ns > 1 ? int32_t(ws_base[l] + int64_t(tile) * ns + j) : -1;
+                    it.part = int32_t(part_base[l] + j);
+                    it.pad_ = 0;
                     pi[k++] = it;
                 }
             for (int64_t b0 = 0; b0 < s; b0 += kQuadBlock) {
@@ -629,6 +686,17 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     memcpy(hs + o_ns, nsplit.data(), b_ns);
     memcpy(hs + o_wb, ws_base.data(), b_wb);
     memcpy(hs + o_qb, qitem_begin.data(), b_qb);
+    memcpy(hs + o_pb, part_base.data(), b_pb);
+    {
+        MomEpochDev* me = reinterpret_cast<MomEpochDev*>(hs + o_me);
+        double* mp = reinterpret_cast<double*>(hs + o_mp);
+        int k = 0;
+        for (int e = 0; e < plan.E; ++e) {
+            const MomEpochPlan& m = plan.mom[size_t(e)];
+            for (int j = 0; j < kMomTerms; ++j) mp[size_t(e) * kMomTerms + j] = m.eligible ? m.p[j] : 0.0;
+            if (m.eligible) me[k++] = MomEpochDev{e, m.tile, m.hb, 0};
+        }
+    }
     {
         int64_t* ti = reinterpret_cast<int64_t*>(hs + o_ti);
         for (int k = 0; k < plan.K; ++k) ti[k] = p->time_idx[k] < 0 ? p->time_idx[k] + plan.T : p->time_idx[k];
@@ -651,6 +719,7 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     CU(ctx, ln.d_tile_arg.ensure(size_t(L) * plan.n_tiles * 8 + 8));
     CU(ctx, ln.d_qpart.ensure(size_t(n_quad) * qrow * 8 + 8));
     CU(ctx, ln.d_fix.ensure(size_t(n_quad) * kEpochsPerLaunch * sizeof(FixEntry) + 8));
+    CU(ctx, ln.d_mom_int.ensure(size_t(n_parts) * size_t(plan.E) * 8 + 8));
     CU(ctx, ln.d_pi_net.ensure(size_t(L) * plan.T * 8 + 16));
     CU(ctx, ln.d_small.ensure(plan.small_bytes + 8));
     CU(ctx, ln.h_small.ensure(plan.small_bytes + 8));
@@ -662,6 +731,10 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
         ln.d_ws_base.p = w + o_wb;
         ln.d_qitem_begin.p = w + o_qb;
         ln.d_time_idx.p = w + o_ti;
+        ln.d_part_base.p = w + o_pb;
+        ln.d_mom_epochs.p = w + o_me;
+        ln.d_mom_p.p = w + o_mp;
+        for (EpochBatch& eb : plan.batches) eb.mom_p = ln.d_mom_p.as<double>();
         char* r = ln.d_small.as<char>();
         DevView* views[9] = {&ln.d_pi_times, &ln.d_integral,  &ln.d_abserr,   &ln.d_max_pi,      &ln.d_argmax_t,
                              &ln.d_mean_rate, &ln.d_n_finite, &ln.d_n_multi, &ln.d_argmax_epoch};
@@ -708,12 +781,17 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
             pa.n_items = int32_t(plan.n_prof_items);
             pa.n_tiles = plan.n_tiles;
             pa.trace = ctx->prof_trace;
+            pa.mom_epochs = ln.d_mom_epochs.as<MomEpochDev>();
+            pa.mom_p = ln.d_mom_p.as<double>();
+            pa.mom_int = ln.d_mom_int.as<double>();
+            pa.n_mom_epochs = plan.mom_form ? plan.n_mom : 0;
+            pa.e_total = plan.E;
             cudaError_t e = cudaSuccess;
             switch (plan.rh) {
-                case 1: e = launch_profile<1>(ctx, ln, pa, plan.n_prof_items); break;
-                case 2: e = launch_profile<2>(ctx, ln, pa, plan.n_prof_items); break;
-                case 4: e = launch_profile<4>(ctx, ln, pa, plan.n_prof_items); break;
-                default: e = launch_profile<8>(ctx, ln, pa, plan.n_prof_items); break;
+                case 1: e = launch_profile<1>(ctx, ln, pa, plan.n_prof_items, false); break;
+                case 2: e = launch_profile<2>(ctx, ln, pa, plan.n_prof_items, false); break;
+                case 4: e = launch_profile<4>(ctx, ln, pa, plan.n_prof_items, plan.mom_form); break;
+                default: e = launch_profile<8>(ctx, ln, pa, plan.n_prof_items, plan.mom_form); break;
             }
             CU(ctx, e);
             ++launches;
@@ -734,10 +812,7 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
                 ++k;
                 const int64_t want = (plan.n_quad_items + kQuadWarps - 1) / kQuadWarps;
                 int q_per_sm = 12 / kQuadWarps;  // 12 warps per SM (168 registers)
-                if (const char* env = getenv("TAPIR_QUAD_CTAS_PER_SM")) {  // tuning override
-                    const int v = atoi(env);
-                    if (v >= 1 && v <= q_per_sm) q_per_sm = v;
-                }
+                if (ctx->quad_ctas_cap >= 1 && ctx->quad_ctas_cap <= q_per_sm) q_per_sm = ctx->quad_ctas_cap;
                 const unsigned qgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(ctx->sm_count) * q_per_sm)));
                 switch (eb.n) {
                     case 0: quad_kernel<0><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;  // rate statistics only
@@ -787,6 +862,9 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
             fa.mean_rate = ln.d_mean_rate.as<double>();
             fa.n_finite = ln.d_n_finite.as<int64_t>();
             fa.n_multi = ln.d_n_multi.as<int64_t>();
+            fa.part_base = ln.d_part_base.as<int64_t>();
+            fa.mom_int = ln.d_mom_int.as<double>();
+            fa.mom_mask = (plan.mom_form && plan.T > 0 && plan.n_prof_items > 0) ? plan.mom_mask : 0;
             const int64_t blocks = (plan.L * 32 + 127) / 128;
             finalize_kernel<<<unsigned(blocks), 128, 0, st>>>(fa);
             CU(ctx, cudaGetLastError());
@@ -870,6 +948,9 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync,
             CU(ctx, cudaEventElapsedTime(&timing->finalize_ms, ln.ev[2], ln.ev[3]));
         }
         timing->launches = launches;
+        timing->profile_tile_points = plan.TT;
+        timing->profile_moment_form = plan.mom_form ? 1 : 0;
+        timing->moment_epochs = plan.mom_form ? plan.n_mom : 0;
     }
     return TAPIR_OK;
 }
@@ -1300,6 +1381,16 @@ int tapir_cuda_fp64_peak(tapir_cuda_ctx* ctx, double* tflops, float* ms_out)
     const double flops = 2.0 * 64.0 * double(iters) * double(blocks) * double(threads);
     *tflops = flops / (double(best) * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
+    return TAPIR_OK;
+}
+
+int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, tapir_mom_epoch* out)
+{
+    static_assert(sizeof(tapir_mom_epoch) == sizeof(MomEpochPlan), "public and internal plan structs agree");
+    if (!out || n_tiles < 1 || tile_points < 1024 || tile_points % 1024) return fail(nullptr, TAPIR_E_INVALID, "bad plan geometry");
+    MomEpochPlan mp;
+    mom_epoch_plan(a, b, n_tiles, tile_points, &mp);
+    memcpy(out, &mp, sizeof mp);
     return TAPIR_OK;
 }
 

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_symbols():
     text = open(os.path.join(ROOT, "include", "tapir_cuda.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(tapir_(?:cuda|ingest)_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(tapir_(?:cuda|ingest|mom)_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_library_exports_every_header_symbol():
@@ -24,14 +24,15 @@ def test_library_exports_every_header_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_lib.SYMBOLS) == names          # the ctypes table covers the whole header
-    assert lib.tapir_cuda_version() == 1
+    assert lib.tapir_cuda_version() == 2
 
 
 def test_struct_layouts_match_header():
     from tapir_b200 import _lib
     assert ctypes.sizeof(_lib.Problem) == 72
     assert ctypes.sizeof(_lib.Results) == 80
-    assert ctypes.sizeof(_lib.Timing) == 24
+    assert ctypes.sizeof(_lib.Timing) == 32
+    assert ctypes.sizeof(_lib.MomEpoch) == 312
 
 
 def test_no_device_fails_loudly():

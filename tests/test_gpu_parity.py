@@ -495,3 +495,115 @@ def test_properties_cfg3_ragged_large(eng):
     one = eng.run(np.array([0, rates.size], dtype=np.int64), rates, T, synthetic.TIMES, synthetic.EPOCHS, want_profile=False)
     assert rel(one.integral[0], res.integral.sum(axis=0)) < 1e-11
     assert one.n_finite[0] == res.n_finite.sum()
+
+
+def test_cfg4_path_moment_form_2048_tiles_with_split_sites(eng):
+    """BASELINE config 4's code path at a size the CPU can check: few loci with very many sites on a grid of several
+    2,048-point tiles -> profile_mom_kernel<8> with every (locus, tile) split over site ranges into the workspace and
+    reduced in a fixed order by finalize_kernel; the profile is requested and compared."""
+    from oracle import capi
+    from tapir_b200 import synthetic
+    from tapir_b200.engine import pack_csr
+    rng = np.random.default_rng(44)
+    T = 5000
+    loci = [synthetic.uce_rates(rng, n, T, nan_frac=0.01) for n in (260000, 200003, 20000)]
+    loci[1][:40] = rng.uniform(0.02, 0.6, 40)             # more than 32 fast sites: second stream of the item
+    loci[2][:5] = [0.05, 0.0195, 0.019531, 0.3, 1.5]
+    off, rates = pack_csr(loci, pinned=False)
+    eng.upload(off, rates, T, [5, -1, 2047, 2048], synthetic.EPOCHS, want_profile=True)
+    tm = eng.compute()
+    assert tm.profile_moment_form == 1 and tm.profile_tile_points == 2048
+    res = eng.download()
+    tiles = (T + 2047) // 2048
+    ts = sorted(set([0, 1, T - 1] + [2048 * k for k in range(tiles)] + [min(T, 2048 * (k + 1)) - 1 for k in range(tiles)]
+                    + [int(x) for x in rng.integers(0, T, 48)]))
+    for l in range(3):
+        lam = rates[off[l]:off[l + 1]]
+        lam = lam[np.isfinite(lam)]
+        for t in ts:
+            want = float(np.sum(16 * lam * lam * t * np.exp(-4 * lam * t)))
+            assert abs(res.pi_net[l, t] - want) <= RTOL * abs(want) + FLOOR, (l, t)
+        si, se, _ = capi.epochs(lam, synthetic.EPOCHS)
+        assert rel(res.integral[l], si) < RTOL
+        np.testing.assert_allclose(res.abserr[l], se, rtol=ERR_RTOL, atol=1e-300)
+    pi_net, si, se = capi.batch(off[2:] - off[2], rates[off[2]:], T, synthetic.EPOCHS)   # the 20,000-site locus, every t
+    assert rel(res.pi_net[2], pi_net[0]) < RTOL
+    assert np.array_equal(res.argmax_t, np.argmax(res.pi_net, axis=1))
+    assert np.array_equal(res.max_pi, np.max(res.pi_net, axis=1))
+    assert np.array_equal(res.pi_times, res.pi_net[:, [5, T - 1, 2047, 2048]])
+    again = eng.run(off, rates, T, [5, -1, 2047, 2048], synthetic.EPOCHS, want_profile=True)
+    assert np.array_equal(res.pi_net, again.pi_net) and np.array_equal(res.integral, again.integral)   # deterministic
+
+
+def _mom_plan(a, b, n_tiles, tile_points):
+    import ctypes
+    from tapir_b200 import _lib
+    out = _lib.MomEpoch()
+    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, ctypes.byref(out)))
+    return out
+
+
+@pytest.mark.parametrize("T", [1000, 2048, 4096])
+def test_moment_functional_epoch_sums(eng, T):
+    """Epoch sums of the slow sites come out of the profile's moments (mom_epoch.h); sites inside an epoch's excluded
+    window, above its r_max, below its r_min, and faster sites are integrated per site, and the window sites'
+    polynomial value is taken out again.  Every class, on both sides of every boundary, in one batch -- together
+    with epochs the functional does not serve (wide, negative, beyond the grid) and more than eight epochs."""
+    from oracle import capi
+    from tapir_b200.engine import pack_csr
+    rng = np.random.default_rng(T)
+    epochs = [[32, 42], [88, 98], [164, 174], [0, 64], [120, 136], [1, 2], [0, 200], [-3, 5], [60, 68], [127, 129],
+              [T - 30, T - 20], [T + 50, T + 60], [3 * T // 4, 3 * T // 4 + 11]]
+    tile_points = 1024 if T <= 1024 else 2048
+    n_tiles = (T + tile_points - 1) // tile_points
+    plans = [_mom_plan(a, b, n_tiles, tile_points) for a, b in epochs]
+    assert sum(p.eligible for p in plans) >= 9 and not plans[6].eligible and not plans[7].eligible
+    special = [1e-20, 1e-100, 2.4e-16, 2.6e-16, 0.0195, 0.019531, 0.01953125, 0.0196, 0.3]
+    for p in plans:
+        if p.eligible:
+            for edge in (p.w_lo, p.w_hi, p.r_max):
+                special += [edge, np.nextafter(edge, 0.0), np.nextafter(edge, 1.0), edge * (1 - 1e-6), edge * (1 + 1e-6)]
+            special += list(rng.uniform(p.w_lo, p.w_hi, 6))
+    loci = [np.concatenate([rng.gamma(0.5, 4.0 / T, 500), special]),                 # UCE-like + every boundary
+            np.array(special * 3),                                                   # boundary sites only
+            rng.permutation(np.concatenate([rng.gamma(0.5, 0.004, 300), rng.uniform(0.02, 2.0, 50), special])),
+            rng.gamma(0.5, 4.0 / T, 257), np.zeros(10), np.array([0.0068])]
+    loci[0][::9] = 0.0
+    loci[0][5::31] = np.nan
+    off, rates = pack_csr(loci, pinned=False)
+    eng.upload(off, rates, T, [1], epochs, want_profile=False)
+    tm = eng.compute()
+    assert tm.profile_moment_form == 1 and tm.moment_epochs == sum(p.eligible for p in plans)
+    res = eng.download()
+    for l, lam in enumerate(loci):
+        si, se, nm = capi.epochs(lam[np.isfinite(lam)], epochs)
+        assert rel(res.integral[l], si) < RTOL, l
+        np.testing.assert_allclose(res.abserr[l], se, rtol=ERR_RTOL, atol=1e-300)
+        assert res.n_multi_panel[l] == int(nm.sum())
+        assert res.argmax_epoch[l] == int(np.argmax(si))
+    again = eng.run(off, rates, T, [1], epochs, want_profile=False)
+    assert np.array_equal(res.integral, again.integral) and np.array_equal(res.abserr, again.abserr)
+
+
+def test_moment_functional_agrees_with_per_site_path(eng, monkeypatch):
+    """The same batch with TAPIR_MOM_INT=0 (every site through quad_kernel): sums agree to rounding, counts exactly;
+    split loci included (one row of moment sums per site range)."""
+    from tapir_b200 import synthetic
+    from tapir_b200.engine import Engine, pack_csr
+    rng = np.random.default_rng(8)
+    T = 2048
+    loci = [synthetic.uce_rates(rng, n, T, nan_frac=0.03) for n in (150000, 90001, 700, 33)]
+    off, rates = pack_csr(loci, pinned=False)
+    a = eng.run(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+    monkeypatch.setenv("TAPIR_MOM_INT", "0")
+    plain = Engine(0)
+    try:
+        plain.upload(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
+        assert plain.compute().moment_epochs == 0
+        b = plain.download()
+    finally:
+        plain.close()
+    assert rel(a.integral, b.integral) < 1e-12 and rel(a.abserr, b.abserr) < 1e-9
+    assert np.array_equal(a.pi_net, b.pi_net) and np.array_equal(a.n_multi_panel, b.n_multi_panel)
+    assert np.array_equal(a.argmax_epoch, b.argmax_epoch) and np.array_equal(a.n_finite, b.n_finite)
+    np.testing.assert_array_equal(a.mean_rate, b.mean_rate)
