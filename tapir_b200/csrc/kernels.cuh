@@ -805,14 +805,32 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                 for (int nt = 0; nt < NT; ++nt) bf[ks][nt] = MA[(4 * ks + fk) * SA + 8 * nt + fg];
             // Epoch integrals of the item's slow sites: for every epoch whose centre lies in this tile the sum of the
             // sites' first GK21 panels is a linear functional of the moments of the block around the centre
-            // (mom_epoch.h) -- one 32-term dot product per epoch, summed by a fixed shuffle tree.
-            for (int me = 0; me < args.n_mom_epochs; ++me) {
-                const MomEpochDev ep = args.mom_epochs[me];
-                if (ep.tile != item.tile) continue;
-                double v = __ldg(args.mom_p + 32 * ep.col + lane) * MA[lane * SA + ep.hb];
+            // (mom_epoch.h),  I[e] = sum_k p[e][k] M[k][hb_e].  Eight epochs at a time as one more product on the B
+            // fragments that are in registers anyway: A = p (row fg = epoch, column 4 ks + fk), eight DMMAs per column
+            // tile; the lane that holds column hb_e of row e stores it.  The order of the additions is the MMA's, fixed.
+            for (int g0 = 0; g0 < args.n_mom_epochs; g0 += 8) {
+                const bool valid = g0 + fg < args.n_mom_epochs;
+                MomEpochDev ep;
+                ep.col = 0; ep.tile = -1; ep.hb = 0; ep.pad_ = 0;
+                if (valid) ep = args.mom_epochs[g0 + fg];
+                const double* pc = args.mom_p + 32 * ep.col + fk;
+                double pa[8];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-                if (lane == 0) args.mom_int[size_t(item.part) * args.e_total + ep.col] = v;
+                for (int ks = 0; ks < 8; ++ks) pa[ks] = valid ? __ldg(pc + 4 * ks) : 0.0;
+                double dd[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dd[nt][0] = dd[nt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dmma884(dd[nt][0], dd[nt][1], pa[ks], bf[ks][nt]);
+                if (valid && ep.tile == item.tile && ((ep.hb & 7) >> 1) == fk) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+                        if ((ep.hb >> 3) == nt) v = (ep.hb & 1) ? dd[nt][1] : dd[nt][0];
+                    args.mom_int[size_t(item.part) * args.e_total + ep.col] = v;
+                }
             }
             __syncwarp();
             // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact);
@@ -935,6 +953,10 @@ struct QuadArgs {
     uint32_t* fix_count; // entries appended by this launch (zeroed before it)
     uint32_t* queue;     // work-queue head of this launch (zeroed before it)
     int32_t n_items;
+    // moment-functional batches: quad_scan_kernel lists the items that hold a site quad_kernel has to integrate;
+    // quad_kernel then takes its items from the list (list == nullptr: every item, rate statistics included)
+    uint32_t* list;
+    uint32_t* list_count;
 };
 
 // GK21 on one epoch with the exponentials factored as e^{-c(centre -/+ h x_j)} = E0 * e^{+/- c h x_j}:
@@ -1151,7 +1173,10 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
 
     for (;;) {
         int it = 0;
-        if (lane == 0) it = int(atomicAdd(args.queue, 1u));
+        if (lane == 0) {
+            it = int(atomicAdd(args.queue, 1u));
+            if (args.list) it = (uint32_t(it) < *args.list_count) ? int(args.list[it]) : args.n_items;
+        }
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= args.n_items) break;
         const QuadItem item = args.items[it];
@@ -1282,7 +1307,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
             for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
             if (lane == 0) out[2 * eb.col[k >> 1] + (k & 1)] = v;
         }
-        if (eb.first) {
+        if (eb.first && !args.list) {  // (listed items: quad_scan_kernel has written the statistics)
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 rs += __shfl_down_sync(0xffffffffu, rs, off);
@@ -1311,6 +1336,66 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
             }
         }
         __syncwarp();
+    }
+}
+
+// Moment-functional batches: almost every site is served by the locus' moments (mom_epoch.h), so what is left of
+// the per-site path is a streaming pass over the rates that (i) writes the rate statistics of every item (the same
+// per-lane sums and shuffle tree as quad_kernel, bit for bit), (ii) zeroes the item's epoch cells and (iii) lists the
+// items holding at least one site quad_kernel must integrate.  The test is the conservative form of quad_kernel's
+// need_mask on the high words of the rates (a listed item is then filtered exactly by quad_kernel itself), integer
+// pipe only; the eight rounds of an item are loaded up front so that a warp keeps 2 KB in flight.
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads) quad_scan_kernel(const QuadArgs args, const EpochBatch eb)
+{
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int row = 2 * eb.e_total + 4;
+    for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < args.n_items; it += n_warps) {
+        const QuadItem item = args.items[it];
+        const double* rp = args.rates + item.site_begin;
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        double v[kQuadBlock / 32];
+#pragma unroll
+        for (int k = 0; k < kQuadBlock / 32; ++k) v[k] = (32 * k + lane < item.count) ? __ldg(rp + 32 * k + lane) : qnan;
+        double rs = 0.0;
+        int nn = 0, nf = 0;
+        uint32_t rare = 0;
+#pragma unroll
+        for (int k = 0; k < kQuadBlock / 32; ++k) {
+            const uint32_t hs = uint32_t(__double2hiint(v[k])), hi = hs & 0x7fffffffu, lo = uint32_t(__double2loint(v[k]));
+            const bool fin = hi < 0x7ff00000u;
+            const bool notnan = fin || (hi == 0x7ff00000u && lo == 0u);
+            rs += notnan ? v[k] : 0.0;
+            nn += __popc(__ballot_sync(0xffffffffu, notnan));
+            nf += __popc(__ballot_sync(0xffffffffu, fin));
+            // quad_kernel's `act`: finite and 16 r^2 != 0 (|r| above 0x1e56a09e667f3bcc, see rate_is_active)
+            const bool act = fin && (hi > 0x1e56a09eu || (hi == 0x1e56a09eu && lo > 0x667f3bccu));
+            const bool cls = hs < 0x3F940000u && hi <= 0x5fcfffffu;   // rate_is_slow (positive, below the class bound)
+            bool served = cls;
+#pragma unroll
+            for (int e = 0; e < kEpochsPerLaunch; ++e)
+                if (e < eb.n) {
+                    const uint32_t a0 = uint32_t(eb.rmin_bits[e] >> 32), a1 = uint32_t(eb.rmax_bits[e] >> 32);
+                    const uint32_t w0 = uint32_t(eb.wlo_bits[e] >> 32), w1 = uint32_t(eb.whi_bits[e] >> 32);
+                    served = served && eb.mom[e] && hs > a0 && hs < a1 && !(hs >= w0 && hs <= w1);
+                }
+            rare |= __ballot_sync(0xffffffffu, act && !served);
+        }
+        double* out = args.qpart + size_t(it) * row;
+        if (lane < 2 * eb.n) out[2 * eb.col[lane >> 1] + (lane & 1)] = 0.0;
+        if (eb.first) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) rs += __shfl_down_sync(0xffffffffu, rs, off);
+            if (lane == 0) {
+                out[2 * eb.e_total + 0] = rs;
+                out[2 * eb.e_total + 1] = double(nn);
+                out[2 * eb.e_total + 2] = double(nf);
+                out[2 * eb.e_total + 3] = 0.0;
+            }
+        }
+        if (rare != 0u && lane == 0) args.list[atomicAdd(args.list_count, 1u)] = uint32_t(it);
     }
 }
 

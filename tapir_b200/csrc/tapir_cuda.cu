@@ -120,7 +120,7 @@ struct Lane {
     DevBuf d_rates, d_work, d_counter;
     DevView d_prof_items, d_quad_items, d_nsplit, d_ws_base, d_qitem_begin, d_time_idx, d_part_base, d_mom_epochs, d_mom_p;
     // intermediates
-    DevBuf d_ws, d_tile_max, d_tile_arg, d_qpart, d_fix, d_mom_int;
+    DevBuf d_ws, d_tile_max, d_tile_arg, d_qpart, d_fix, d_mom_int, d_rare_list;
     // results: the profile, and ONE buffer holding every small per-locus vector (a single D2H copy per batch)
     DevBuf d_pi_net, d_small;
     DevView d_pi_times, d_integral, d_abserr, d_max_pi, d_argmax_t, d_argmax_epoch, d_mean_rate, d_n_finite, d_n_multi;
@@ -129,8 +129,8 @@ struct Lane {
     tapir_results pending_out = {};
     int64_t pending_row0 = 0;
     bool pending = false;
-    DevBuf* all_bufs[11] = {&d_rates, &d_work, &d_counter, &d_ws, &d_tile_max, &d_tile_arg, &d_qpart, &d_fix, &d_pi_net, &d_small,
-                            &d_mom_int};
+    DevBuf* all_bufs[12] = {&d_rates, &d_work, &d_counter, &d_ws, &d_tile_max, &d_tile_arg, &d_qpart, &d_fix, &d_pi_net, &d_small,
+                            &d_mom_int, &d_rare_list};
 };
 
 constexpr int kLanes = 8;  // upper bound; ctx->n_lanes of them rotate (TAPIR_CUDA_LANES)
@@ -150,6 +150,10 @@ struct tapir_cuda_ctx {
     int last_rh = 0, last_mom_form = 0, last_n_mom = 0;  // what the last tapir_cuda_compute launched (tapir_timing)
     // per-device launch configuration, filled once in tapir_cuda_create (index: log2(RH))
     int prof_per_sm[4] = {0, 0, 0, 0}, mom_per_sm[4] = {0, 0, 0, 0};
+    // plans of the moment-functional epochs seen so far (they depend on the epoch and the tile geometry only; a
+    // chunked run would otherwise recompute them for every chunk)
+    struct MomCacheEntry { double a, b; int64_t n_tiles; int32_t TT; MomEpochPlan plan; };
+    std::vector<MomCacheEntry> mom_cache;
     int prof_ctas_cap = 0, quad_ctas_cap = 0;  // TAPIR_PROF_CTAS_PER_SM / TAPIR_QUAD_CTAS_PER_SM (co-residency experiments)
     int force_rh = 0;                          // TAPIR_CUDA_RH
     int trace = 0;           // TAPIR_CUDA_TRACE=1: tapir_cuda_run prints the timeline of its chunks to stderr
@@ -210,26 +214,23 @@ int bind(tapir_cuda_ctx* ctx)
     return TAPIR_OK;
 }
 
-// Tile-size model.  Cost of one locus' profile in FP64 lane-operations per site, for the direct form
-// (profile_kernel<RH>: TT = 256 RH points per tile, one FMA per (site, point) plus the power tables) and for the
-// moment form (profile_mom_kernel<RH>, RH >= 4: a quarter of the FMAs, cheaper tables, plus a per-item moments ->
-// times product of 128 TT/1024 DMMAs that is shared by the item's sites).  `sites` = mean sites per locus.
-// Calibrated against profiles/r02_tile_sweep.txt.
+// Tile-size model: time of one locus' profile per site (ps), a + b / sites per time tile, for the direct form
+// (profile_kernel<RH>: TT = 256 RH points per tile) and the moment form (profile_mom_kernel<RH>, RH >= 4: a quarter of
+// the FMAs and cheaper tables, but a moments -> times product per item that its sites share).  `sites` = mean sites
+// per locus.  The constants are fitted to the many-tile rows of profiles/r02_tile_sweep.txt (B200, loci of 100 / 500 /
+// 2,000 sites, grids of 200 .. 5,000 points; one-tile rows carry the same ~20 % tail of a 2-round launch in every variant).
 double tile_cost(int rh, bool mom, int64_t T, double sites)
 {
+    static const double a_dir[4] = {19.8, 29.4, 52.0, 99.0}, b_dir[4] = {116.0, 630.0, 1010.0, 2160.0};
+    static const double a_mom[4] = {0.0, 0.0, 24.0, 44.7}, b_mom[4] = {0.0, 0.0, 4500.0, 10480.0};
     const int64_t TT = 32 * 8 * rh;
     const int64_t nt = (T + TT - 1) / TT;
+    const int i = rh == 1 ? 0 : rh == 2 ? 1 : rh == 4 ? 2 : 3;
     const double s = std::max(sites, 1.0);
-    if (!mom) {
-        const double gen = 45.0 + 32.0 + 8.0 * rh + (nt > 1 ? 28.0 : 0.0);
-        return double(nt) * (double(TT) + gen + double(TT) / s);
-    }
-    const double gen = 75.0 + 2.0 * double(TT / 128) + (nt > 1 ? 28.0 : 0.0);
-    const double per_item = 32768.0 * double(TT / 1024) + double(TT);   // moments -> times, epilogue
-    return double(nt) * (0.25 * double(TT) + gen + per_item / s);
+    return double(nt) * (mom ? a_mom[i] + b_mom[i] / s : a_dir[i] + b_dir[i] / s);
 }
 
-void choose_tile(const tapir_cuda_ctx* ctx, int64_t T, double sites, int& rh_out, bool& mom_out);
+void choose_tile(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t T, double sites, int& rh_out, bool& mom_out);
 
 template <int RH>
 cudaError_t configure_profile(tapir_cuda_ctx* ctx, int idx)
@@ -280,19 +281,25 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
     return cudaGetLastError();
 }
 
-void choose_tile(const tapir_cuda_ctx* ctx, int64_t T, double sites, int& rh_out, bool& mom_out)
+// Epoch integrals ride along: with the moment form the epochs mom_epoch.h serves cost a streaming scan of the rates
+// (~6 ps per site), every other (site, epoch) ~10 ps in quad_kernel.
+void choose_tile(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t T, double sites, int& rh_out, bool& mom_out)
 {
     rh_out = 1;
     mom_out = false;
-    double best = tile_cost(1, false, T, sites);
-    for (int rh : {2, 4, 8}) {
-        const double c = tile_cost(rh, false, T, sites);
-        if (c < best) { best = c; rh_out = rh; mom_out = false; }
-    }
-    if (ctx->prof_mom)
-        for (int rh : {4, 8}) {
-            const double c = tile_cost(rh, true, T, sites);
-            if (c < best) { best = c; rh_out = rh; mom_out = true; }
+    double best = 1e300;
+    for (int mom = 0; mom <= (ctx->prof_mom ? 1 : 0); ++mom)
+        for (int rh : {1, 2, 4, 8}) {
+            if (mom && rh < 4) continue;
+            const int64_t TT = 256 * rh, span = ((T + TT - 1) / TT) * TT;
+            int served = 0;
+            if (mom && ctx->mom_int)
+                for (int e = 0; e < p->n_epochs; ++e) {
+                    const double a = p->epoch_ab[2 * e], b = p->epoch_ab[2 * e + 1], h = 0.5 * (b - a);
+                    if (a >= 0.0 && h >= 0.5 && h <= 32.0 && 0.5 * (a + b) < double(span)) ++served;
+                }
+            const double c = tile_cost(rh, mom != 0, T, sites) + 10.3 * (p->n_epochs - served) + (served ? 6.0 : 0.0);
+            if (c < best) { best = c; rh_out = rh; mom_out = mom != 0; }
         }
     if (ctx->force_rh) {  // TAPIR_CUDA_RH: 1, 2, 4 or 8
         rh_out = ctx->force_rh;
@@ -580,7 +587,7 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     plan.E = p->n_epochs;
     plan.flags = p->flags;
     plan.nnz = plan.L ? off[plan.L] - base : 0;
-    choose_tile(ctx, std::max<int64_t>(plan.T, 1), plan.L ? double(plan.nnz) / double(plan.L) : 1.0, plan.rh, plan.mom_form);
+    choose_tile(ctx, p, std::max<int64_t>(plan.T, 1), plan.L ? double(plan.nnz) / double(plan.L) : 1.0, plan.rh, plan.mom_form);
     plan.TT = 32 * 8 * plan.rh;
     plan.n_tiles = int32_t(std::max<int64_t>(1, (plan.T + plan.TT - 1) / plan.TT));
     // epochs whose sums come out of the profile's moments (mom_epoch.h); the others, and the sites outside an
@@ -590,7 +597,18 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     plan.mom_mask = 0;
     if (ctx->mom_int && plan.mom_form && plan.T > 0 && plan.L > 0)
         for (int e = 0; e < plan.E; ++e) {
-            mom_epoch_plan(p->epoch_ab[2 * e], p->epoch_ab[2 * e + 1], plan.n_tiles, plan.TT, &plan.mom[size_t(e)]);
+            const double ea = p->epoch_ab[2 * e], eb_ = p->epoch_ab[2 * e + 1];
+            const tapir_cuda_ctx::MomCacheEntry* hit = nullptr;
+            for (const auto& ce : ctx->mom_cache)
+                if (ce.a == ea && ce.b == eb_ && ce.n_tiles == plan.n_tiles && ce.TT == plan.TT) { hit = &ce; break; }
+            if (!hit) {
+                if (ctx->mom_cache.size() >= 4096) ctx->mom_cache.clear();
+                tapir_cuda_ctx::MomCacheEntry ce{ea, eb_, plan.n_tiles, plan.TT, MomEpochPlan()};
+                mom_epoch_plan(ea, eb_, plan.n_tiles, plan.TT, &ce.plan);
+                ctx->mom_cache.push_back(ce);
+                hit = &ctx->mom_cache.back();
+            }
+            plan.mom[size_t(e)] = hit->plan;
             if (plan.mom[size_t(e)].eligible) {
                 ++plan.n_mom;
                 plan.mom_mask |= uint64_t(1) << e;
@@ -720,6 +738,7 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     CU(ctx, ln.d_qpart.ensure(size_t(n_quad) * qrow * 8 + 8));
     CU(ctx, ln.d_fix.ensure(size_t(n_quad) * kEpochsPerLaunch * sizeof(FixEntry) + 8));
     CU(ctx, ln.d_mom_int.ensure(size_t(n_parts) * size_t(plan.E) * 8 + 8));
+    CU(ctx, ln.d_rare_list.ensure(plan.n_mom ? size_t(n_quad) * plan.batches.size() * 4 + 8 : 8));
     CU(ctx, ln.d_pi_net.ensure(size_t(L) * plan.T * 8 + 16));
     CU(ctx, ln.d_small.ensure(plan.small_bytes + 8));
     CU(ctx, ln.h_small.ensure(plan.small_bytes + 8));
@@ -810,6 +829,18 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
                 qa.fix_count = ln.d_counter.as<uint32_t>() + 1 + 2 * k;
                 qa.queue = ln.d_counter.as<uint32_t>() + 2 + 2 * k;
                 ++k;
+                // two counters per batch in d_counter[1..16], the batch's rare-item count in d_counter[17 + k]
+                qa.list = nullptr;
+                qa.list_count = nullptr;
+                if (eb.mom_any) {
+                    qa.list = ln.d_rare_list.as<uint32_t>() + size_t(k - 1) * size_t(plan.n_quad_items);
+                    qa.list_count = ln.d_counter.as<uint32_t>() + 17 + (k - 1);
+                    const int64_t warps = kScanThreads / 32;
+                    const unsigned sgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>((plan.n_quad_items + warps - 1) / warps, int64_t(ctx->sm_count) * 8)));
+                    quad_scan_kernel<<<sgrid, kScanThreads, 0, sq>>>(qa, eb);
+                    CU(ctx, cudaGetLastError());
+                    ++launches;
+                }
                 const int64_t want = (plan.n_quad_items + kQuadWarps - 1) / kQuadWarps;
                 int q_per_sm = 12 / kQuadWarps;  // 12 warps per SM (168 registers)
                 if (ctx->quad_ctas_cap >= 1 && ctx->quad_ctas_cap <= q_per_sm) q_per_sm = ctx->quad_ctas_cap;

@@ -226,7 +226,8 @@ def test_staged_api_matches_run(eng):
     a = eng.run(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
     eng.upload(off, rates, T, synthetic.TIMES, synthetic.EPOCHS)
     tm = eng.compute()
-    assert tm.launches == 4 and tm.total_ms > 0       # profile, quad, quad_fix, finalize
+    # profile, [quad_scan when the moments serve some epoch], quad, quad_fix, finalize
+    assert tm.launches == (5 if tm.moment_epochs else 4) and tm.total_ms > 0
     b = eng.download()
     for name in ("pi_net", "pi_times", "integral", "abserr", "max_pi", "argmax_t", "argmax_epoch"):
         assert np.array_equal(getattr(a, name), getattr(b, name))
@@ -505,14 +506,14 @@ def test_cfg4_path_moment_form_2048_tiles_with_split_sites(eng):
     from tapir_b200 import synthetic
     from tapir_b200.engine import pack_csr
     rng = np.random.default_rng(44)
-    T = 5000
+    T = 6000                                              # three 2,048-point tiles: the model's choice for this grid
     loci = [synthetic.uce_rates(rng, n, T, nan_frac=0.01) for n in (260000, 200003, 20000)]
     loci[1][:40] = rng.uniform(0.02, 0.6, 40)             # more than 32 fast sites: second stream of the item
     loci[2][:5] = [0.05, 0.0195, 0.019531, 0.3, 1.5]
     off, rates = pack_csr(loci, pinned=False)
     eng.upload(off, rates, T, [5, -1, 2047, 2048], synthetic.EPOCHS, want_profile=True)
     tm = eng.compute()
-    assert tm.profile_moment_form == 1 and tm.profile_tile_points == 2048
+    assert tm.profile_moment_form == 1 and tm.profile_tile_points == 2048, (tm.profile_moment_form, tm.profile_tile_points)
     res = eng.download()
     tiles = (T + 2047) // 2048
     ts = sorted(set([0, 1, T - 1] + [2048 * k for k in range(tiles)] + [min(T, 2048 * (k + 1)) - 1 for k in range(tiles)]
@@ -607,3 +608,31 @@ def test_moment_functional_agrees_with_per_site_path(eng, monkeypatch):
     assert np.array_equal(a.pi_net, b.pi_net) and np.array_equal(a.n_multi_panel, b.n_multi_panel)
     assert np.array_equal(a.argmax_epoch, b.argmax_epoch) and np.array_equal(a.n_finite, b.n_finite)
     np.testing.assert_array_equal(a.mean_rate, b.mean_rate)
+
+
+@pytest.mark.parametrize("rh,mom", [(1, 0), (2, 0), (4, 0), (8, 0), (4, 1), (8, 1)])
+def test_every_profile_kernel_variant(monkeypatch, rh, mom):
+    """The tile-size model only ever picks some of the six profile kernels for a given shape; here each one is forced
+    (TAPIR_CUDA_RH / TAPIR_PROF_MOM, read when the context is created) on the same ragged batch and grid."""
+    from oracle import capi
+    from tapir_b200 import synthetic
+    from tapir_b200.engine import Engine, pack_csr
+    monkeypatch.setenv("TAPIR_CUDA_RH", str(rh))
+    monkeypatch.setenv("TAPIR_PROF_MOM", str(mom))
+    rng = np.random.default_rng(rh * 10 + mom)
+    T = 2500
+    loci = [synthetic.uce_rates(rng, n, T, nan_frac=0.05) for n in (1, 33, 257, 700, 1500)]
+    loci[3][:40] = rng.uniform(0.02, 1.0, 40)
+    off, rates = pack_csr(loci, pinned=False)
+    e = Engine(0)
+    try:
+        e.upload(off, rates, T, [0, -1, 1024], synthetic.EPOCHS)
+        tm = e.compute()
+        assert (tm.profile_tile_points, tm.profile_moment_form) == (256 * rh, mom)
+        res = e.download()
+    finally:
+        e.close()
+    pi_net, si, se = capi.batch(off, rates, T, synthetic.EPOCHS)
+    assert rel(res.pi_net, pi_net) < RTOL and rel(res.integral, si) < RTOL
+    np.testing.assert_allclose(res.abserr, se, rtol=ERR_RTOL, atol=1e-300)
+    assert np.array_equal(res.argmax_t, np.argmax(pi_net, axis=1)) and np.array_equal(res.argmax_epoch, np.argmax(si, axis=1))
