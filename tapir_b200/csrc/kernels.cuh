@@ -80,7 +80,13 @@ struct EpochBatch {
     unsigned long long rmin_bits[kEpochsPerLaunch], rmax_bits[kEpochsPerLaunch];
     unsigned long long wlo_bits[kEpochsPerLaunch], whi_bits[kEpochsPerLaunch];
     double tb[kEpochsPerLaunch];         // centre of the anchor block (absolute time)
-    const double* mom_p;                 // device [e_total][32]: coefficients of the functional, row = output column
+    // quad_scan_kernel's conservative form on the high words of the rates: a site is served for every epoch of the
+    // launch when mom_all is set, scan_lo < hi(rate) < scan_hi (the tightest range of the launch) and hi(rate) lies in
+    // none of the n_win windows [win_lo, win_hi]
+    int32_t mom_all, n_win;
+    uint32_t scan_lo, scan_hi;
+    uint32_t win_lo[kEpochsPerLaunch], win_hi[kEpochsPerLaunch];
+    const double* mom_p;                // device [e_total][32]: coefficients of the functional, row = output column
 };
 
 struct ProfArgs {
@@ -1361,28 +1367,26 @@ __global__ void __launch_bounds__(kScanThreads) quad_scan_kernel(const QuadArgs 
         for (int k = 0; k < kQuadBlock / 32; ++k) v[k] = (32 * k + lane < item.count) ? __ldg(rp + 32 * k + lane) : qnan;
         double rs = 0.0;
         int nn = 0, nf = 0;
-        uint32_t rare = 0;
+        bool rare = false;
 #pragma unroll
         for (int k = 0; k < kQuadBlock / 32; ++k) {
             const uint32_t hs = uint32_t(__double2hiint(v[k])), hi = hs & 0x7fffffffu, lo = uint32_t(__double2loint(v[k]));
             const bool fin = hi < 0x7ff00000u;
             const bool notnan = fin || (hi == 0x7ff00000u && lo == 0u);
             rs += notnan ? v[k] : 0.0;
-            nn += __popc(__ballot_sync(0xffffffffu, notnan));
-            nf += __popc(__ballot_sync(0xffffffffu, fin));
+            nn += notnan ? 1 : 0;
+            nf += fin ? 1 : 0;
             // quad_kernel's `act`: finite and 16 r^2 != 0 (|r| above 0x1e56a09e667f3bcc, see rate_is_active)
             const bool act = fin && (hi > 0x1e56a09eu || (hi == 0x1e56a09eu && lo > 0x667f3bccu));
-            const bool cls = hs < 0x3F940000u && hi <= 0x5fcfffffu;   // rate_is_slow (positive, below the class bound)
-            bool served = cls;
-#pragma unroll
-            for (int e = 0; e < kEpochsPerLaunch; ++e)
-                if (e < eb.n) {
-                    const uint32_t a0 = uint32_t(eb.rmin_bits[e] >> 32), a1 = uint32_t(eb.rmax_bits[e] >> 32);
-                    const uint32_t w0 = uint32_t(eb.wlo_bits[e] >> 32), w1 = uint32_t(eb.whi_bits[e] >> 32);
-                    served = served && eb.mom[e] && hs > a0 && hs < a1 && !(hs >= w0 && hs <= w1);
-                }
-            rare |= __ballot_sync(0xffffffffu, act && !served);
+            // inside the launch's common range (positive, in the moment class): one unsigned comparison
+            bool served = eb.mom_all && (hs - eb.scan_lo - 1u) < (eb.scan_hi - eb.scan_lo - 1u);
+#pragma unroll 1
+            for (int w = 0; w < eb.n_win; ++w) served = served && (hs - eb.win_lo[w]) > (eb.win_hi[w] - eb.win_lo[w]);
+            rare = rare || (act && !served);
         }
+        nn = __reduce_add_sync(0xffffffffu, nn);
+        nf = __reduce_add_sync(0xffffffffu, nf);
+        const bool any_rare = __any_sync(0xffffffffu, rare);
         double* out = args.qpart + size_t(it) * row;
         if (lane < 2 * eb.n) out[2 * eb.col[lane >> 1] + (lane & 1)] = 0.0;
         if (eb.first) {
@@ -1395,7 +1399,7 @@ __global__ void __launch_bounds__(kScanThreads) quad_scan_kernel(const QuadArgs 
                 out[2 * eb.e_total + 3] = 0.0;
             }
         }
-        if (rare != 0u && lane == 0) args.list[atomicAdd(args.list_count, 1u)] = uint32_t(it);
+        if (any_rare && lane == 0) args.list[atomicAdd(args.list_count, 1u)] = uint32_t(it);
     }
 }
 

@@ -22,12 +22,15 @@
 // rates:  with e0 <= 32 eps resk (y <= 1: Kronrod and Gauss agree to < 1e-19, what dqk21 sees is rounding noise)
 // the floor wins and resasc > floor whenever  resasc / resk >= 2.33e-8, and
 //
-//     resasc/resk >= sum_{j=4,5} wgk_j (|f1_j - m| + |f2_j - m|) / resk >= (2 h / resk_rel) sum_j wgk_j x_j |phi_j(c)|,
+//     resasc/resk >= sum_j wgk_j (|f1_j - m| + |f2_j - m|) / resk >= (2 h / resk_rel) sum_j wgk_j x_j |phi_j(c)|,
 //     phi_j(c) = c C sinhc(c h x_j) - cosh(c h x_j),     resk_rel = C Ak(y) - h y Bk(y) <= 3.1 C   (y <= 1),
 //
-// which only fails in a narrow window of rates around c = 1/C (the site whose PI curve peaks at the epoch centre).
-// The plan returns that window (with a 40x margin on the threshold); sites inside it, above r_max or below r_min
-// take the per-site path of quad_kernel for this epoch, and their polynomial value is subtracted there.
+// (f1_j - f2_j = 2 h x_j phi_j(c); all ten node pairs).  Every phi_j vanishes near c = 1/C -- the site whose PI curve
+// peaks at the epoch centre -- but at ten different rates, c_j ~ (1 + (h x_j / C)^2 / 3) / C, so the sum stays above the
+// threshold unless the epoch is very narrow against its distance from 0 (h/C below ~0.02); when it does dip, the plan
+// returns the window of rates around the dip (threshold taken with a 10x margin).  Sites inside the window, above
+// r_max or below r_min take the per-site path of quad_kernel for this epoch, and their polynomial value is subtracted
+// there.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -59,7 +62,7 @@ static const long double kW[11] = {
     0.123491976262065851077958109585166L, 0.134709217311473325928054001771707L, 0.142775938577060080797094273138717L,
     0.147739104901338491374841515972068L, 0.149445554002916905664936468389821L};
 
-// S(c) = sum_{j=4,5} wgk_j x_j |phi_j(c)|
+// S(c) = sum_j wgk_j x_j |phi_j(c)|: (resasc / resk) >= 2 h S(c) / (3.1 C)
 inline long double phi(int j, long double c, long double C, long double h)
 {
     const long double u = c * h * kX[j];
@@ -68,7 +71,9 @@ inline long double phi(int j, long double c, long double C, long double h)
 }
 inline long double S(long double c, long double C, long double h)
 {
-    return kW[4] * kX[4] * fabsl(phi(4, c, C, h)) + kW[5] * kX[5] * fabsl(phi(5, c, C, h));
+    long double s = 0.0L;
+    for (int j = 0; j < 10; ++j) s += kW[j] * kX[j] * fabsl(phi(j, c, C, h));
+    return s;
 }
 }  // namespace momdetail
 
@@ -96,49 +101,64 @@ inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, MomEpoch
     const long double r_min = 2.5e-16L;                       // a = 16 r^2 >= 1e-30: result > uflow / (50 eps)
     if (!(r_max > 1e-12L)) return;
     // ---- window of rates where the floor proof may fail ----
-    const long double tau = 1e-6L * 3.1L * C / (2.0L * h);    // S(c) >= tau  =>  resasc / resk >= 1e-6 >= 40 x 2.33e-8
+    // S(c) >= tau  =>  resasc / resk >= 2.5e-7, more than 10 x the 2.33e-8 the proof needs
+    const long double tau = 2.5e-7L * 3.1L * C / (2.0L * h);
     const long double c_max = 4.0L * r_max;
-    if (!(S(0.0L, C, h) > 2.0L * tau)) return;                // the whole range would be window (C/h ~ 1e5)
-    long double root[2];
-    for (int k = 0; k < 2; ++k) {
-        const int j = 4 + k;
-        if (phi(j, c_max, C, h) <= 0.0L) { root[k] = HUGE_VALL; continue; }
-        long double lo = 0.0L, hi = c_max;                    // phi(0+) = -1 < 0 < phi(c_max); phi_j increases (C >= h)
-        for (int it = 0; it < 200; ++it) {
-            const long double mid = 0.5L * (lo + hi);
-            if (phi(j, mid, C, h) <= 0.0L) lo = mid; else hi = mid;
-        }
-        root[k] = 0.5L * (lo + hi);
-    }
-    const long double c_first = fminl(root[0], root[1]), c_last = fmaxl(root[0], root[1]);
-    long double c_lo, c_hi;
-    {   // below the first root S decreases from S(0): last point with S >= tau
-        const long double cA = fminl(c_first, c_max);
-        if (S(cA, C, h) >= tau) c_lo = cA;
-        else {
-            long double lo = 0.0L, hi = cA;
-            for (int it = 0; it < 200; ++it) {
-                const long double mid = 0.5L * (lo + hi);
-                if (S(mid, C, h) >= tau) lo = mid; else hi = mid;
-            }
-            c_lo = lo;
-        }
-    }
-    if (c_last >= c_max) c_hi = (c_first > c_max && S(c_max, C, h) >= tau) ? -1.0L : c_max;
-    else if (S(c_max, C, h) < tau) c_hi = c_max;
-    else {  // above the last root S increases: first point with S >= tau
-        long double lo = c_last, hi = c_max;
-        for (int it = 0; it < 200; ++it) {
-            const long double mid = 0.5L * (lo + hi);
-            if (S(mid, C, h) >= tau) hi = mid; else lo = mid;
-        }
-        c_hi = hi;
-    }
     double w_lo = 1.0, w_hi = 0.0;
-    if (c_hi >= c_lo) {
-        w_lo = double(c_lo / 4.0L * (1.0L - 1e-9L));
-        w_hi = double(c_hi / 4.0L * (1.0L + 1e-9L));
-        if (w_lo <= double(r_min) && w_hi >= double(r_max)) return;   // nothing left
+    {
+        // coarse look at the whole range (S is smooth away from the roots of the phi_j, which all lie in a span of
+        // relative width (h/C)^2 / 3 around 1/C)
+        const int N = 2048;
+        long double s_min = S(0.0L, C, h);
+        for (int i = 1; i <= N; ++i) s_min = fminl(s_min, S(c_max * i / N, C, h));
+        // roots of the phi_j inside the range: phi_j(0+) = -1; beyond y = 1 they are out of range
+        long double root[10];
+        int n_root = 0;
+        for (int j = 0; j < 10; ++j) {
+            if (phi(j, c_max, C, h) <= 0.0L) continue;
+            long double lo = 0.0L, hi = c_max;
+            for (int it = 0; it < 100; ++it) {
+                const long double mid = 0.5L * (lo + hi);
+                if (phi(j, mid, C, h) <= 0.0L) lo = mid; else hi = mid;
+            }
+            root[n_root++] = 0.5L * (lo + hi);
+        }
+        // between its breakpoints S is a sum of smooth, nearly linear terms: the dip is at a root
+        long double c_dip = -1.0L;
+        for (int k = 0; k < n_root; ++k) {
+            const long double v = S(root[k], C, h);
+            if (v < s_min) s_min = v;
+            if (c_dip < 0.0L || v < S(c_dip, C, h)) c_dip = root[k];
+        }
+        if (n_root == 0 && s_min < 4.0L * tau) return;   // no sign change, yet close to the threshold: leave the epoch per site
+        if (s_min < 2.0L * tau) {
+            if (n_root == 0) return;
+            // sub-level set {S < 2 tau} around the dip, found outwards from it (twice the threshold: the set is taken
+            // generously, and what lies outside is verified below)
+            long double lo = 0.0L, hi = c_dip;
+            for (int it = 0; it < 100; ++it) {
+                const long double mid = 0.5L * (lo + hi);
+                if (S(mid, C, h) >= 2.0L * tau) lo = mid; else hi = mid;
+            }
+            const long double c_lo = lo;
+            lo = c_dip; hi = c_max;
+            if (S(c_max, C, h) < 2.0L * tau) lo = c_max;
+            else
+                for (int it = 0; it < 100; ++it) {
+                    const long double mid = 0.5L * (lo + hi);
+                    if (S(mid, C, h) >= 2.0L * tau) hi = mid; else lo = mid;
+                }
+            const long double c_hi = (lo == c_max) ? c_max : hi;
+            // verify: outside [c_lo, c_hi] S stays above the threshold proper
+            for (int i = 1; i <= 512; ++i) {
+                const long double below = c_lo * (1.0L - 0.25L * i / 512.0L), above = c_hi + (c_max - c_hi) * i / 512.0L;
+                const long double near_above = c_hi * (1.0L + 0.25L * i / 512.0L);
+                if (S(below, C, h) < tau || S(above, C, h) < tau || (near_above < c_max && S(near_above, C, h) < tau)) return;
+            }
+            w_lo = double(c_lo / 4.0L * (1.0L - 1e-9L));
+            w_hi = double(c_hi / 4.0L * (1.0L + 1e-9L));
+            if (w_lo <= double(r_min) && w_hi >= double(r_max)) return;   // nothing left
+        }
     }
     // ---- the functional ----
     long double E[kMomTerms], G[kMomTerms], fact = 1.0L, dk = 1.0L;

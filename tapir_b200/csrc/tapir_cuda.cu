@@ -340,6 +340,8 @@ void fill_batches(Plan& plan, const double* epoch_ab)
                 eb.tp[k][j] = eb.center[k] + absc;
             }
             eb.new_half[k] = (k == 0) || (eb.half[k] != eb.half[k - 1]);
+            if (k == 0) { eb.mom_all = 1; eb.n_win = 0; eb.scan_lo = 0u; eb.scan_hi = 0x3F940000u; }
+            if (!(size_t(e) < plan.mom.size() && plan.mom[e].eligible)) eb.mom_all = 0;
             if (size_t(e) < plan.mom.size() && plan.mom[e].eligible) {
                 const MomEpochPlan& mp = plan.mom[e];
                 auto bits = [](double v) { unsigned long long u; memcpy(&u, &v, 8); return u; };
@@ -350,10 +352,19 @@ void fill_batches(Plan& plan, const double* epoch_ab)
                 eb.wlo_bits[k] = bits(mp.w_lo);
                 eb.whi_bits[k] = bits(mp.w_hi);
                 eb.tb[k] = mp.tb;
+                // high words for the scan: strictly inside the range, windows widened to whole high words
+                eb.scan_lo = std::max(eb.scan_lo, uint32_t(eb.rmin_bits[k] >> 32));
+                eb.scan_hi = std::min(eb.scan_hi, uint32_t(eb.rmax_bits[k] >> 32));
+                if (mp.w_lo <= mp.w_hi) {
+                    eb.win_lo[eb.n_win] = uint32_t(eb.wlo_bits[k] >> 32);
+                    eb.win_hi[eb.n_win] = uint32_t(eb.whi_bits[k] >> 32);
+                    ++eb.n_win;
+                }
             }
             if (a < 0.0) eb.nonneg = 0;
             eb.bmax = std::max(eb.bmax, std::max(std::fabs(a), std::fabs(b)));
         }
+        if (eb.scan_hi <= eb.scan_lo + 1u) eb.mom_all = 0;   // empty common range: nothing is served for every epoch
         plan.batches.push_back(eb);
     }
     if (E == 0) {  // still need the rate statistics

@@ -554,17 +554,19 @@ def test_moment_functional_epoch_sums(eng, T):
     from tapir_b200.engine import pack_csr
     rng = np.random.default_rng(T)
     epochs = [[32, 42], [88, 98], [164, 174], [0, 64], [120, 136], [1, 2], [0, 200], [-3, 5], [60, 68], [127, 129],
-              [T - 30, T - 20], [T + 50, T + 60], [3 * T // 4, 3 * T // 4 + 11]]
+              [T - 30, T - 20], [T + 50, T + 60], [3 * T // 4, 3 * T // 4 + 11], [T - 3, T - 1], [500, 502]]
     tile_points = 1024 if T <= 1024 else 2048
     n_tiles = (T + tile_points - 1) // tile_points
     plans = [_mom_plan(a, b, n_tiles, tile_points) for a, b in epochs]
-    assert sum(p.eligible for p in plans) >= 9 and not plans[6].eligible and not plans[7].eligible
+    assert sum(p.eligible for p in plans) >= 11 and not plans[6].eligible and not plans[7].eligible
+    assert sum(p.eligible and p.w_lo <= p.w_hi for p in plans) >= 2      # narrow far epochs: an excluded window exists
     special = [1e-20, 1e-100, 2.4e-16, 2.6e-16, 0.0195, 0.019531, 0.01953125, 0.0196, 0.3]
     for p in plans:
         if p.eligible:
             for edge in (p.w_lo, p.w_hi, p.r_max):
                 special += [edge, np.nextafter(edge, 0.0), np.nextafter(edge, 1.0), edge * (1 - 1e-6), edge * (1 + 1e-6)]
-            special += list(rng.uniform(p.w_lo, p.w_hi, 6))
+            if p.w_lo <= p.w_hi:
+                special += list(rng.uniform(p.w_lo, p.w_hi, 6))
     loci = [np.concatenate([rng.gamma(0.5, 4.0 / T, 500), special]),                 # UCE-like + every boundary
             np.array(special * 3),                                                   # boundary sites only
             rng.permutation(np.concatenate([rng.gamma(0.5, 0.004, 300), rng.uniform(0.02, 2.0, 50), special])),
