@@ -598,6 +598,16 @@ __device__ __forceinline__ void prof_epilogue(const ProfArgs& args, const double
 // from profile_kernel's by the series remainder, the cancellation noted above and a different association of the
 // same sums (observed <= 1e-12 relative; the parity gate is 1e-9).
 constexpr int kMomStride = 34;  // doubles per moment row (32 + 2: rows 272 bytes apart, conflict-free 16-byte fragments)
+constexpr int kLinBlock = 130;  // doubles per 128-point block of the moments -> times scratch (128 + 2: the four row groups
+                                // of a store land 8 banks apart instead of on the same banks)
+// 1/k!, k = 0..31
+__device__ __constant__ double c_inv_fact[32] = {
+    1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333, 0.001388888888888889,
+    0.0001984126984126984, 2.48015873015873e-05, 2.7557319223985893e-06, 2.755731922398589e-07, 2.505210838544172e-08,
+    2.08767569878681e-09, 1.6059043836821613e-10, 1.1470745597729725e-11, 7.647163731819816e-13, 4.779477332387385e-14,
+    2.8114572543455206e-15, 1.5619206968586225e-16, 8.22063524662433e-18, 4.110317623312165e-19, 1.9572941063391263e-20,
+    8.896791392450574e-22, 3.8681701706306835e-23, 1.6117375710961184e-24, 6.446950284384474e-26, 2.4795962632247972e-27,
+    9.183689863795546e-29, 3.279889237069838e-30, 1.1309962886447718e-31, 3.7699876288159054e-33, 1.2161250415535181e-34};
 
 // Shared memory of one warp of profile_mom_kernel: the moment tables U' [32][34] + W' [32][WA]; later, over them, the
 // scratch of the moments -> times step ([32][NB+4] moments, then [TT] times) and the 16-site power tables of the
@@ -607,13 +617,15 @@ template <int RH>
 struct MomCfg {
     static constexpr int TT = ProfCfg<RH>::TT, NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
     static constexpr int Tables = 32 * kMomStride + 32 * WA;
-    static constexpr int FastOff = Tables > TT ? Tables : TT;
+    static constexpr int Lin = kLinBlock * NB;   // moments -> times scratch, one padded row per 128-point block
+    static constexpr int FastOff = Tables > Lin ? Tables : Lin;
     static constexpr int QueueOff = FastOff + 32;
     static constexpr int WarpDoubles = QueueOff + 64;
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
     static constexpr int MinBlocks = (RH == 4 ? 14 : 8) / kProfWarps;  // 144 / 255 registers
     static_assert(16 * (kUStride + ProfCfg<RH>::WStride) <= FastOff, "16-site power tables fit below the fast-site list");
     static_assert(32 * (NB + 4) <= FastOff, "moment scratch fits");
+    static_assert((kLinBlock * 8) % 16 == 0, "16-byte reads of the scratch stay aligned");
 };
 
 // a slow site: 64 c = 256 r <= 5, i.e. r < 0x3F94000000000000 (0.01953125), r >= 0 -- on the bit pattern
@@ -838,8 +850,16 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                     args.mom_int[size_t(item.part) * args.e_total + ep.col] = v;
                 }
             }
+            // the 1/k! of the Taylor terms goes onto the moments (8 NT multiplies per lane), so that the A fragments
+            // below are pure powers of x
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const double f = c_inv_fact[4 * ks + fk];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bf[ks][nt] *= f;
+            }
             __syncwarp();
-            // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact);
+            // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact), one multiply per step;
             // eight row tiles at a time, so that the eight DMMAs of a tile are not one dependent chain
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -849,19 +869,17 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                     const double x = double(8 * (8 * half + m) + fg - 64) * 0.015625;
                     const double xx = x * x;
                     x4[m] = xx * xx;
-                    pw[m] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx * 0.5 : (xx * x) * (1.0 / 6.0);  // x^fk / fk!
+                    pw[m] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;  // x^fk
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) d[m][nt][0] = d[m][nt][1] = 0.0;
                 }
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
-                    const double kk = double(4 * ks + fk);
-                    const double rk = 1.0 / ((kk + 1.0) * (kk + 2.0) * (kk + 3.0) * (kk + 4.0));
 #pragma unroll
                     for (int m = 0; m < 8; ++m) {
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) dmma884(d[m][nt][0], d[m][nt][1], pw[m], bf[ks][nt]);
-                        pw[m] *= x4[m] * rk;  // -> x^(k+4) / (k+4)!, k = 4 ks + fk
+                        pw[m] *= x4[m];  // -> x^(k+4), k = 4 ks + fk
                     }
                 }
 #pragma unroll
@@ -869,7 +887,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) lin[128 * (8 * nt + 2 * fk + c) + 8 * (8 * half + m) + fg] = d[m][nt][c];
+                        for (int c = 0; c < 2; ++c) lin[kLinBlock * (8 * nt + 2 * fk + c) + 8 * (8 * half + m) + fg] = d[m][nt][c];
             }
             __syncwarp();
 #pragma unroll
@@ -877,7 +895,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
-                    const double* src = lin + 32 * hi + 4 * chunk_pair(fg);
+                    const double* src = lin + kLinBlock * (hi >> 2) + 32 * (hi & 3) + 4 * chunk_pair(fg);
                     const double2 v01 = *reinterpret_cast<const double2*>(src);
                     const double2 v23 = *reinterpret_cast<const double2*>(src + 2);
                     acc[0][j][c] = v01.x; acc[1][j][c] = v01.y; acc[2][j][c] = v23.x; acc[3][j][c] = v23.y;

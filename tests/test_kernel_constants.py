@@ -156,3 +156,12 @@ def test_collapsed_panel_against_quadpack():
                 else:
                     n_unproved += 1
     assert n_proved > 2000 and n_unproved > 100, (n_proved, n_unproved)
+
+
+def test_inverse_factorial_table():
+    """c_inv_fact of kernels.cuh (the 1/k! that profile_mom_kernel puts onto the moments) is 1/k! correctly rounded."""
+    text = open(os.path.join(ROOT, "tapir_b200", "csrc", "kernels.cuh")).read()
+    vals = _array("inv_fact", text)
+    assert len(vals) == 32
+    for k, v in enumerate(vals):
+        assert v == float(D(1) / D(factorial(k))), k
