@@ -57,28 +57,52 @@ def pack_csr(loci: Sequence[np.ndarray], pinned: bool = True):
     offsets[0] = 0
     np.cumsum(lens, out=offsets[1:])
     rates = alloc(int(offsets[-1]), np.float64)
-    for l, x in enumerate(loci):
-        rates[offsets[l]:offsets[l + 1]] = x
+    if len(loci):
+        np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in loci], out=rates)
     return offsets, rates
+
+
+def shard_csr(offsets, rates, index, pinned: bool = False):
+    """CSR slice holding the loci `index` (ascending) -> (offsets_p, rates_p), without a Python loop over loci: a run
+    of consecutive loci is one slice copy, anything else one gather through a site index."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    index = np.asarray(index, dtype=np.int64)
+    alloc = pinned_empty if pinned else np.empty
+    lens = offsets[index + 1] - offsets[index]
+    off_p = alloc(index.size + 1, np.int64)
+    off_p[0] = 0
+    np.cumsum(lens, out=off_p[1:])
+    rates_p = alloc(int(off_p[-1]), np.float64)
+    if index.size and int(index[-1]) - int(index[0]) + 1 == index.size:        # contiguous block of loci
+        rates_p[:] = rates[offsets[index[0]]:offsets[index[-1] + 1]]
+    elif index.size:
+        src = np.repeat(offsets[index] - off_p[:-1], lens) + np.arange(int(off_p[-1]), dtype=np.int64)
+        np.take(rates, src, out=rates_p)
+    return off_p, rates_p
 
 
 def partition_loci(site_counts: np.ndarray, n_parts: int):
     """Size-balanced locus partition (longest-processing-time greedy, ties by index): returns a
     list of index arrays, one per part, each sorted ascending so a part's CSR slice keeps the
     original locus order."""
+    import heapq
     site_counts = np.asarray(site_counts, dtype=np.int64)
-    order = np.argsort(-site_counts, kind="stable")
-    loads = np.zeros(n_parts, dtype=np.int64)
-    parts = [[] for _ in range(n_parts)]
-    if len(site_counts) and (site_counts == site_counts[0]).all():
+    n = len(site_counts)
+    if n and (site_counts == site_counts[0]).all():
         # uniform loci: contiguous blocks, no need for the greedy pass
-        bounds = np.linspace(0, len(site_counts), n_parts + 1).astype(np.int64)
+        bounds = np.linspace(0, n, n_parts + 1).astype(np.int64)
         return [np.arange(bounds[i], bounds[i + 1], dtype=np.int64) for i in range(n_parts)]
-    for idx in order:
-        p = int(np.argmin(loads))
-        parts[p].append(int(idx))
-        loads[p] += site_counts[idx] + 1
-    return [np.array(sorted(p), dtype=np.int64) for p in parts]
+    order = np.argsort(-site_counts, kind="stable")
+    owner = np.empty(n, dtype=np.int64)
+    heap = [(0, p) for p in range(n_parts)]          # (load, part): the least loaded part, lowest index on ties
+    costs = (site_counts[order] + 1).tolist()
+    for k, cost in enumerate(costs):
+        load, p = heap[0]
+        owner[k] = p
+        heapq.heapreplace(heap, (load + cost, p))
+    part_of = np.empty(n, dtype=np.int64)
+    part_of[order] = owner
+    return [np.nonzero(part_of == p)[0].astype(np.int64) for p in range(n_parts)]
 
 
 class Engine:

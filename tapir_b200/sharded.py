@@ -7,22 +7,10 @@ arithmetic is whatever ``compute_fn`` does -- Engine.run in the product; the glo
 """
 import numpy as np
 
-from .engine import BatchResult, partition_loci
+from .engine import BatchResult, partition_loci, shard_csr  # noqa: F401 (shard_csr re-exported)
 
 SMALL_FIELDS = ("pi_times", "integral", "abserr", "max_pi", "argmax_t", "argmax_epoch", "mean_rate", "n_finite",
                 "n_multi_panel")
-
-
-def shard_csr(offsets, rates, index):
-    """CSR slice holding the loci `index` (ascending) -> (offsets_p, rates_p)."""
-    offsets = np.asarray(offsets, dtype=np.int64)
-    lens = offsets[index + 1] - offsets[index]
-    off_p = np.zeros(index.size + 1, dtype=np.int64)
-    np.cumsum(lens, out=off_p[1:])
-    rates_p = np.empty(int(off_p[-1]), dtype=np.float64)
-    for j, l in enumerate(index):
-        rates_p[off_p[j]:off_p[j + 1]] = rates[offsets[l]:offsets[l + 1]]
-    return off_p, rates_p
 
 
 def pack_small(res: BatchResult):

@@ -579,10 +579,17 @@ def test_moment_functional_epoch_sums(eng, T):
     assert tm.profile_moment_form == 1 and tm.moment_epochs == sum(p.eligible for p in plans)
     res = eng.download()
     for l, lam in enumerate(loci):
-        si, se, nm = capi.epochs(lam[np.isfinite(lam)], epochs)
+        ok = lam[np.isfinite(lam)]
+        si, se, nm = capi.epochs(ok, epochs)
         assert rel(res.integral[l], si) < RTOL, l
         np.testing.assert_allclose(res.abserr[l], se, rtol=ERR_RTOL, atol=1e-300)
-        assert res.n_multi_panel[l] == int(nm.sum())
+        # panel counts are compared outside the denormal range: a site whose integral underflows (|I| < 1e-300, a fast
+        # site over a late epoch) is bisected or not on the last bits of denormal node values, which the device's and
+        # the C library's exp do not share -- far below the 1e-290 floor of the value comparison
+        slack = sum(int(np.sum((np.abs(capi.epoch_sites(ok, a, b)[0]) < 1e-300) & (ok != 0.0))) for a, b in epochs)
+        assert abs(int(res.n_multi_panel[l]) - int(nm.sum())) <= slack, (l, res.n_multi_panel[l], nm.sum(), slack)
+        if slack == 0:
+            assert res.n_multi_panel[l] == int(nm.sum())
         assert res.argmax_epoch[l] == int(np.argmax(si))
     again = eng.run(off, rates, T, [1], epochs, want_profile=False)
     assert np.array_equal(res.integral, again.integral) and np.array_equal(res.abserr, again.abserr)
