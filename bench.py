@@ -1,25 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- Townsend-PI hot path on B200: site*timepoint PI evals/s and loci/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" is one pass of the whole hot path (PI profile + --times picks + GK21/QAGS epoch
-integrals + per-locus maxima) over one batch of synthetic loci.  At N = 1 the batch is
-BASELINE.json configs[1] (5,000 loci x 500 sites, 1,000-point grid, 4 epochs); at N > 1 every
-rank owns one such shard (weak scaling; loci are independent, bin/tapir_compute.py:159-164) and
-the small per-locus result vectors are gathered to rank 0 over NCCL.
+One "step" is one pass of the whole hot path (PI profile + --times picks + QUADPACK epoch integrals + per-locus
+maxima) over one batch of synthetic loci.  The batch is BASELINE.json configs[4] -- 500,000 loci x 800 sites on a
+2,048-point grid, the configuration the metric ("... at 1/2/4/8 B200") is quoted on -- at every N: ONE batch, split
+over the ranks by the size-balanced locus partition (strong scaling; loci are independent,
+bin/tapir_compute.py:159-164), per-locus result vectors gathered to rank 0 over NVLink and put back into the original
+locus order there.  configs[1] and configs[2] ride along as `other_configs` (N = 1); at N > 1 configs[2] goes through
+the LPT partition and configs[1] runs as one shard per rank (the round-1 weak-scaling number).
 
 Printed keys (one JSON line, rank 0):
-  value    evals/s with inputs resident in HBM, kernels timed by CUDA events on the library's stream
-  e2e      the same metric through the C-ABI call with HOST buffers: pinned H2D + kernels + D2H
-  roofline FP64-pipe roofline of the dominant kernel (profile_kernel), see DESIGN.md
-  cpu_baseline  the reference's CPU path (numpy + scipy quad port, Pool(cpu_count-1)) on a bounded sample
+  value         evals/s with inputs resident in HBM, kernels timed by CUDA events on the library's stream, max over ranks
+  e2e           the same metric through the C-ABI call with HOST buffers: pinned H2D + kernels + D2H (+ gather, un-permute)
+  roofline      FP64-pipe roofline of the dominant kernel: executed lane-operations, and the direct formulation's beside it
+  parity        sampled loci of the timed batch against the CPU oracle, outside the timed region
+  cpu_baseline  the reference's CPU path (Pool(cpu_count-1)) on a bounded sample of the same batch
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -32,33 +34,72 @@ if ROOT not in sys.path:
 
 METRIC = "site*timepoint PI evals/sec"
 UNIT = "evals/s"
+DEFAULT_WORKLOAD = "cfg5"
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm: the reference's own algorithm (oracle port: numpy ufuncs + scipy.integrate.quad),
-# mapped over loci with multiprocessing.Pool(cpu_count()-1) as bin/tapir_compute.py:162-164 does.
+# CPU arm: the reference's own algorithm mapped over loci with multiprocessing.Pool(cpu_count()-1) as
+# bin/tapir_compute.py:162-164 does.  When build() has placed the reference's unmodified tapir/compute.py under
+# baseline/_ref/ (git-ignored; it travels to the GPU box) the arithmetic is THAT file's functions, imported with the
+# three-line shim of SURVEY.md 8c (kind "reference"); otherwise the bit-exact port oracle/townsend_port.py (kind "port").
 # --------------------------------------------------------------------------------------------
 _CPU_STATE = {}
+REF_COMPUTE = os.path.join(ROOT, "baseline", "_ref", "tapir", "compute.py")
+
+
+def load_reference_compute():
+    """The reference's tapir/compute.py, unmodified, or None."""
+    if not os.path.exists(REF_COMPUTE):
+        return None
+    import importlib.util
+    import types
+    import numpy
+    import scipy
+    sys.modules.setdefault("dendropy", types.ModuleType("dendropy"))   # only correct_branch_lengths needs it
+    if not hasattr(scipy, "vectorize"):
+        scipy.vectorize = numpy.vectorize                               # removed from modern scipy (compute.py:20)
+    spec = importlib.util.spec_from_file_location("tapir_ref_compute", REF_COMPUTE)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_kind():
+    return "reference" if os.path.exists(REF_COMPUTE) else "port"
 
 
 def _cpu_init(T, times, epochs):
-    from oracle import townsend_port as tp
-    _CPU_STATE["tp"] = tp
-    _CPU_STATE["tcol"] = tp.time_column(0, T)
+    ref = load_reference_compute()
+    _CPU_STATE["ref"] = ref
+    if ref is None:
+        from oracle import townsend_port as tp
+        _CPU_STATE["tp"] = tp
+        _CPU_STATE["tcol"] = tp.time_column(0, T)
+    else:
+        _CPU_STATE["tcol"] = ref.get_time(0, T)
     _CPU_STATE["times"] = times
     _CPU_STATE["epochs"] = epochs
 
 
 def _cpu_worker(lam):
     import warnings
-    tp = _CPU_STATE["tp"]
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        # returns the full (T,S) matrix through the pool pipe, as the reference's worker does
-        return tp.locus_worker(_CPU_STATE["tcol"], lam, _CPU_STATE["times"], _CPU_STATE["epochs"], keep_matrix=True)
+        ref = _CPU_STATE["ref"]
+        tcol, times, epochs = _CPU_STATE["tcol"], _CPU_STATE["times"], _CPU_STATE["epochs"]
+        if ref is None:
+            # returns the full (T,S) matrix through the pool pipe, as the reference's worker does
+            return _CPU_STATE["tp"].locus_worker(tcol, lam, times, epochs, keep_matrix=True)
+        # worker() of bin/tapir_compute.py:110-123 on the reference's own functions
+        mean_rate = np.mean(np.ma.masked_array(lam, np.isnan(lam)))
+        pi = ref.get_townsend_pi(tcol, lam)
+        pi_net = np.nansum(pi, axis=1)
+        pi_times = ref.get_net_pi_for_periods(pi, times)
+        pi_epochs = ref.get_net_integral_for_epochs(lam[np.isfinite(lam)], epochs)
+        return lam, mean_rate, pi, pi_net, pi_times, pi_epochs
 
 
-def cpu_reference_pass(offsets, rates, T, times, epochs, n_loci, pool):
+def cpu_reference_pass(offsets, rates, T, n_loci, pool):
     loci = [rates[offsets[l]:offsets[l + 1]] for l in range(n_loci)]
     t0 = time.perf_counter()
     out = pool.map(_cpu_worker, loci)
@@ -74,26 +115,27 @@ def make_pool(T, times, epochs):
     return ctx.Pool(processes=workers, initializer=_cpu_init, initargs=(T, times, epochs)), workers
 
 
+def cpu_how():
+    return ("the reference's unmodified tapir/compute.py (baseline/_ref, dendropy stubbed)" if cpu_kind() == "reference"
+            else "numpy+scipy.quad port of tapir/compute.py (oracle/townsend_port.py)")
+
+
 def cpu_baseline(offsets, rates, T, times, epochs, budget_s=15.0):
     """Bounded sample: calibrate on one pool round, then size the sample for ~budget_s seconds."""
     pool, workers = make_pool(T, times, epochs)
     try:
         L = offsets.size - 1
         n0 = min(L, 4 * workers)
-        cpu_reference_pass(offsets, rates, T, times, epochs, min(L, workers), pool)      # fork + import warm-up
-        dt0, _, _ = cpu_reference_pass(offsets, rates, T, times, epochs, n0, pool)
+        cpu_reference_pass(offsets, rates, T, min(L, workers), pool)      # fork + import warm-up
+        dt0, _, _ = cpu_reference_pass(offsets, rates, T, n0, pool)
         n = int(min(L, max(n0, n0 * budget_s / max(dt0, 1e-3))))
-        dt, evals, _ = cpu_reference_pass(offsets, rates, T, times, epochs, n, pool)
+        dt, evals, _ = cpu_reference_pass(offsets, rates, T, n, pool)
     finally:
         pool.close()
         pool.join()
-    return {
-        "value": evals / dt, "unit": UNIT, "cores": workers, "kind": "port",
-        "loci_per_s": n / dt,
-        "sample": "first %d of %d loci of the same batch, %.1f s wall, Pool(%d) over numpy+scipy.quad port "
-                  "(oracle/townsend_port.py), full (T,S) matrix returned through the pool pipe as the reference does"
-                  % (n, L, dt, workers),
-    }
+    return {"value": evals / dt, "unit": UNIT, "cores": workers, "kind": cpu_kind(), "loci_per_s": n / dt,
+            "sample": "first %d of %d loci of the same batch, %.1f s wall, Pool(%d) over %s, full (T,S) matrix returned "
+                      "through the pool pipe as the reference does" % (n, L, dt, workers, cpu_how())}
 
 
 # --------------------------------------------------------------------------------------------
@@ -101,7 +143,7 @@ def cpu_baseline(offsets, rates, T, times, epochs, budget_s=15.0):
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
     """SM clock + throttle reasons sampled through NVML every few ms on a host thread while the timed
-    region runs (a step is well under a millisecond, far below nvidia-smi's polling period)."""
+    region runs (a step is milliseconds, far below nvidia-smi's polling period)."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index=0, period_s=0.002):
@@ -150,22 +192,24 @@ class ClockSampler:
         load = [x for x in self.sm if x >= 0.6 * hi]    # "under load": within 60 % of the busiest clock seen
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": self.smax,
                 "reasons": sorted(k for k, bit in self.REASONS.items() if self.mask & bit),
-                "samples": len(self.sm), "source": "NVML, %.0f ms period, sampled over the attribution, timed and end-to-end loops" % (self.period * 1e3)}
+                "samples": len(self.sm),
+                "source": "NVML, %.0f ms period, sampled over the attribution, timed and end-to-end loops" % (self.period * 1e3)}
 
 
 def profile_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of one profile-kernel launch from the committed ncu --set full
-    capture of this workload (profiles/*_ncu_full_<workload>.txt), or None."""
+    capture of this workload (profiles/*_ncu_full_<workload>.txt, latest round), or None."""
     import glob
     import re
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_%s.txt" % workload)))
     if not files:
         return None
-    total, inside = 0.0, False
+    total, inside, seen = 0.0, False, 0
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for line in open(files[-1]):
         if line.startswith("== "):
-            inside = "profile_kernel" in line or "profile_mom_kernel" in line
+            inside = ("profile_kernel" in line or "profile_mom_kernel" in line) and seen == 0
+            seen += 1 if inside else 0
         m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
         if inside and m:
             total += float(m.group(2)) * scale.get(m.group(3), 1.0)
@@ -181,26 +225,109 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------------------------
+# What the profile kernel EXECUTES on the FP64 pipe (profile_mom_kernel / profile_kernel, kernels.cuh), counted from
+# the batch itself: DMMA.8x8x4 instructions (256 FMA lanes each) and scalar FP64 warp instructions (32 lanes each).
+# The DMMA count follows the kernels' loop structure exactly; the scalar counts per group / per item are read off the
+# kernel source.  tests/test_bench_model.py checks both against the opcode counts of the committed ncu capture.
+# --------------------------------------------------------------------------------------------
+def site_classes(offsets, rates, moment_form, chunk=1 << 26):
+    """Per locus: (# sites of profile_mom_kernel's moment class, # other sites with a non-zero finite rate)."""
+    off = np.asarray(offsets, dtype=np.int64)
+    L = off.size - 1
+    n_slow, n_fast = np.zeros(L, dtype=np.int64), np.zeros(L, dtype=np.int64)
+    if L == 0 or rates.size == 0:
+        return n_slow, n_fast
+    l0 = 0
+    while l0 < L:                                           # whole loci per chunk of at most ~`chunk` sites
+        l1 = int(np.searchsorted(off, off[l0] + chunk, side="right")) - 1
+        l1 = min(L, max(l1, l0 + 1))
+        r = np.asarray(rates[off[l0]:off[l1]])
+        mag = np.abs(r)
+        active = (mag > 1.5717277847026288e-162) & (mag <= 3.3519519824856493e+153)   # 16 r^2 neither 0 nor Inf (rate_is_active)
+        slow = active & (r > 0.0) & (r < 0.01953125) if moment_form else np.zeros_like(active)
+        seg = off[l0:l1] - off[l0]
+        lens = off[l0 + 1:l1 + 1] - off[l0:l1]
+        full = np.nonzero(lens > 0)[0]                       # reduceat over the non-empty loci only (their segments tile r)
+        for mask, dst in ((slow, n_slow), (active & ~slow, n_fast)):
+            if full.size:
+                dst[l0 + full] = np.add.reduceat(mask, seg[full], dtype=np.int64)
+        l0 = l1
+    return n_slow, n_fast
+
+
+def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=0):
+    """-> dict(dmma, scalar, lane_ops, n_active) of one profile launch over the batch."""
+    TT = int(tile_points)
+    n_tiles = max(1, (int(T) + TT - 1) // TT)
+    RH, NB = TT // 256, TT // 128
+    NT = max(1, NB // 8)
+    n_slow, n_fast = site_classes(offsets, rates, bool(moment_form))
+
+    def ksteps(cnt, group):
+        """k-steps (4 sites each, issued in pairs) summed over the groups of `group` sites of every item."""
+        full, last = cnt // group, cnt % group
+        ks_last = 2 * ((((last + 3) // 4) + 1) // 2)
+        return full * (group // 4) + np.where(last > 0, ks_last, 0)
+
+    if moment_form:
+        groups, fgroups = (n_slow + 31) // 32, (n_fast + 15) // 16
+        dmma = 4 * NT * ksteps(n_slow, 32) + 128 * NT + 8 * NT * ((n_mom_epochs + 7) // 8) + 4 * RH * ksteps(n_fast, 16)
+        # scalar FP64 warp instructions.  Per group of the moment pass: c, a (3), z, bounded exp (18), q^128, q^256,
+        # z^2, z^4, three moment seeds, 32 chain multiplies, NB column multiplies (+ a full exp and a multiply for tiles
+        # after the first).  Per item: two accumulator sets added (8 NT), 1/k! onto the moments (8 NT), A fragments of
+        # the moments -> times step (2 x 8 x (5 + 8)), epilogue (16 RH).  Per group of 16 fast sites: two exps + tables.
+        per_group = 61 + NB
+        per_item = 16 * NT + 208 + 16 * RH
+        scalar0 = groups * per_group + per_item + fgroups * 110
+        scalar1 = groups * (per_group + 27) + per_item + fgroups * 136
+    else:
+        n_all = n_slow + n_fast
+        groups = (n_all + 31) // 32
+        dmma = 4 * RH * ksteps(n_all, 32)
+        per_group = 45 + 32 + 8 * RH
+        scalar0 = groups * per_group + 16 * RH
+        scalar1 = groups * (per_group + 28) + 16 * RH
+    dmma_total = int(dmma.sum()) * n_tiles
+    scalar_total = int(scalar0.sum()) + int(scalar1.sum()) * (n_tiles - 1)
+    return {"dmma": dmma_total, "scalar": scalar_total, "lane_ops": 256 * dmma_total + 32 * scalar_total,
+            "n_active": int(n_slow.sum() + n_fast.sum())}
+
+
+# --------------------------------------------------------------------------------------------
+def workload_name(w):
+    from tapir_b200 import synthetic
+    c = synthetic.CONFIGS[w]
+    if c["kind"] == "uniform":
+        return "%s: synthetic %d loci x %d sites, %d-point grid, 4 epochs, 4 times" % (w, c["n_loci"], c["n_sites"], c["T"])
+    return "%s: synthetic %d loci x ~%d sites (ragged %d-%d), %d-point grid, 4 epochs, 4 times" % (
+        w, c["n_loci"], c["mean_sites"], c["smin"], c["smax"], c["T"])
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU path alone, rank 0 only."""
     if rank != 0:
         return
     from tapir_b200 import synthetic
-    off, rates, T = synthetic.build(args.workload)
+    cfg = synthetic.CONFIGS[args.workload]
+    # a bounded prefix of the batch is all this arm ever touches (block-seeded generation: the same loci as the full batch)
+    if cfg["kind"] == "uniform" and cfg["n_loci"] * cfg["n_sites"] > synthetic.BLOCKED_ABOVE:
+        off, rates, T = synthetic.build(args.workload, loci=(0, min(cfg["n_loci"], 16384)))
+    else:
+        off, rates, T = synthetic.build(args.workload)
     times, epochs = synthetic.TIMES, synthetic.EPOCHS
     pool, workers = make_pool(T, times, epochs)
     L = off.size - 1
     try:
         # size one step for ~8 s so that steps + warmup finish within a few minutes
-        cpu_reference_pass(off, rates, T, times, epochs, min(L, workers), pool)           # fork + import warm-up
+        cpu_reference_pass(off, rates, T, min(L, workers), pool)           # fork + import warm-up
         n0 = min(L, 4 * workers)
-        dt0, _, _ = cpu_reference_pass(off, rates, T, times, epochs, n0, pool)
+        dt0, _, _ = cpu_reference_pass(off, rates, T, n0, pool)
         n = int(min(L, max(n0, n0 * 8.0 / max(dt0, 1e-3))))
         for _ in range(args.warmup):
-            cpu_reference_pass(off, rates, T, times, epochs, min(n, workers), pool)
+            cpu_reference_pass(off, rates, T, min(n, workers), pool)
         tot_t = tot_e = 0.0
         for _ in range(args.steps):
-            dt, evals, _ = cpu_reference_pass(off, rates, T, times, epochs, n, pool)
+            dt, evals, _ = cpu_reference_pass(off, rates, T, n, pool)
             tot_t += dt
             tot_e += evals
     finally:
@@ -209,24 +336,15 @@ def run_reference(args, rank, world):
     value = tot_e / tot_t
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "sample_loci_per_step": n, "timing": "host wall clock"},
         "loci_per_s": n * args.steps / tot_t,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
-                         "sample": "%d of %d loci per step, Pool(%d), numpy+scipy.quad port of tapir/compute.py" % (n, L, workers)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": cpu_kind(),
+                         "sample": "%d of %d loci per step, Pool(%d), %s" % (n, cfg["n_loci"], workers, cpu_how())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-def workload_name(w):
-    from tapir_b200 import synthetic
-    c = synthetic.CONFIGS[w]
-    if c["kind"] == "uniform":
-        return "%s: synthetic %d loci x %d sites, %d-point grid, 4 epochs, 4 times" % (w, c["n_loci"], c["n_sites"], c["T"])
-    return "%s: synthetic %d loci x ~%d sites (ragged %d-%d), %d-point grid, 4 epochs, 4 times" % (
-        w, c["n_loci"], c["mean_sites"], c["smin"], c["smax"], c["T"])
 
 
 def host_side_rates(rates_np, off_np, T, times, epochs, out, n_files=512, n_db=256):
@@ -240,8 +358,7 @@ def host_side_rates(rates_np, off_np, T, times, epochs, out, n_files=512, n_db=2
     from tapir_b200.engine import BatchResult
     d = tempfile.mkdtemp(prefix="tapir_bench_")
     try:
-        # bounded by content, not only by count: at most ~1M sites of rate files and ~1M sqlite rows (the genome-scale
-        # shape has 1e6 sites per locus and a 10,000-point grid; 512 such files would take minutes to write and parse)
+        # bounded by content, not only by count: at most ~1M sites of rate files and ~1M sqlite rows
         n_files = min(n_files, off_np.size - 1)
         while n_files > 1 and off_np[n_files] > 1_000_000:
             n_files //= 2
@@ -267,47 +384,189 @@ def host_side_rates(rates_np, off_np, T, times, epochs, out, n_files=512, n_db=2
         sub = BatchResult(pi_net=np.array(out.pi_net[:n_db]), pi_times=np.array(out.pi_times[:n_db]),
                           integral=np.array(out.integral[:n_db]), abserr=np.array(out.abserr[:n_db]), max_pi=None,
                           argmax_t=None, argmax_epoch=None, mean_rate=None, n_finite=None, n_multi_panel=None)
-        conn, c = db.create_probe_db(os.path.join(d, "pi.sqlite"))
-        t0 = time.perf_counter()
-        db.insert_batch(conn, c, ["locus-%d.rates" % l for l in range(n_db)], sub, times, epochs)
-        conn.commit()
-        t_db = time.perf_counter() - t0
-        conn.close()
+        names = ["locus-%d.rates" % l for l in range(n_db)]
+        t_db = {}
+        for with_net in (True, False):
+            conn, c = db.create_probe_db(os.path.join(d, "pi_%d.sqlite" % with_net))
+            t0 = time.perf_counter()
+            db.insert_batch(conn, c, names, sub, times, epochs, with_net=with_net)
+            conn.commit()
+            t_db[with_net] = time.perf_counter() - t0
+            conn.close()
         rows = n_db * (1 + T + len(times) + len(epochs))
         return {"ingest_files": n_files, "ingest_native_files_per_s": n_files / t_native, "ingest_native_matches": ok,
-                "ingest_json_load_files_per_s": n_files / t_py, "sqlite_loci": n_db, "sqlite_rows_per_s": rows / t_db,
-                "sqlite_loci_per_s": n_db / t_db,
+                "ingest_json_load_files_per_s": n_files / t_py, "sqlite_loci": n_db, "sqlite_rows_per_s": rows / t_db[True],
+                "sqlite_loci_per_s": n_db / t_db[True], "sqlite_loci_per_s_without_net_table": n_db / t_db[False],
                 "note": "host side of the drop-in, outside the timed region: tapir_ingest_rates (C++ threads) vs json.load "
-                        "per file; bulk executemany writer with the reference's schema incl. the T-rows-per-locus net table"}
+                        "per file; bulk executemany writer with the reference's schema, with and without the "
+                        "T-rows-per-locus net table (--no-net-table)"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
 
+# --------------------------------------------------------------------------------------------
+# parity gate: sampled loci of the timed batch against the CPU oracle (outside the timed region)
+# --------------------------------------------------------------------------------------------
+def parity_sample(L, n=32, seed=12345):
+    rng = np.random.default_rng(seed)
+    idx = np.unique(np.concatenate([[0, L - 1], rng.integers(0, L, size=max(0, n - 2))]))
+    return idx.astype(np.int64)
+
+
+def oracle_for(offsets, rates, idx, T, epochs):
+    """CPU oracle (QUADPACK port) of the loci `idx`: (pi_net [n,T], integral [n,E], abserr [n,E])."""
+    from oracle import capi
+    from tapir_b200.engine import shard_csr
+    off_s, rates_s = shard_csr(offsets, rates, idx)
+    return capi.batch(off_s, rates_s, T, epochs)
+
+
+def rel_err(a, b, floor=1e-290):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / (np.abs(b) + floor))) if a.size else 0.0
+
+
+def parity_check(want, pi_net_rows, small_rows):
+    """want = oracle tuple for the sampled loci; the device's rows for the same loci."""
+    pi_net, si, se = want
+    out = {"n": int(si.shape[0]),
+           "max_rel_pi_net": rel_err(pi_net_rows, pi_net),
+           "max_rel_integral": rel_err(small_rows["integral"], si),
+           "max_rel_abserr": rel_err(small_rows["abserr"], se),
+           "argmax_epoch_identical": bool(np.array_equal(small_rows["argmax_epoch"], np.argmax(si, axis=1))),
+           "argmax_t_identical": bool(np.array_equal(small_rows["argmax_t"], np.argmax(pi_net, axis=1)))}
+    out["ok"] = bool(max(out["max_rel_integral"], out["max_rel_pi_net"]) <= 1e-9 and out["argmax_epoch_identical"]
+                     and out["argmax_t_identical"])
+    out["gate"] = ("sampled loci of the timed batch vs oracle/quadpack_port.c: pi_net, integral <= 1e-9 relative "
+                   "(FP64 mode), identical argmax epoch and argmax t")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+def timed_steps(eng, sb, steps, warmup, barrier):
+    """Attribution pass (kernels serialised on one stream: exact per-kernel times) and the timed steps proper."""
+    eng.set_serial_kernels(True)
+    for _ in range(max(warmup, 3)):
+        sb.step()
+    k = {"profile": 0.0, "quad": 0.0, "finalize": 0.0, "serialised_step": 0.0}
+    for _ in range(steps):
+        eng.flush_l2()
+        tm = sb.step()
+        k["profile"] += tm.profile_ms
+        k["quad"] += tm.quad_ms
+        k["finalize"] += tm.finalize_ms
+        k["serialised_step"] += tm.total_ms
+    eng.set_serial_kernels(False)
+    for _ in range(max(warmup, 3)):
+        sb.step()
+        sb.gather_step()
+    barrier()
+    dev_ms, gather_ms, launches = 0.0, 0.0, 0
+    for _ in range(steps):
+        eng.flush_l2()                      # untimed: the step starts with a cold L2
+        tm = sb.step()                      # CUDA events on the library stream, synchronised on both sides
+        dev_ms += tm.total_ms
+        launches += tm.launches
+        if sb.mode == "nccl":
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sb.gather_step()
+            e1.record()
+            torch.cuda.synchronize()
+            gather_ms += e0.elapsed_time(e1)
+    barrier()
+    k = {n: v / steps for n, v in k.items()}
+    k["gather"] = gather_ms / steps
+    return (dev_ms + gather_ms) / steps, k, launches, tm
+
+
+class SoloBatch:
+    """A whole batch on this rank's GPU, no gather (N = 1, and the one-shard-per-rank weak-scaling side config)."""
+    mode = "none"
+
+    def __init__(self, eng, off, rates, T, times, epochs):
+        from tapir_b200.engine import pinned_empty
+        self.eng, self.T, self.times, self.epochs = eng, T, times, epochs
+        self.offsets = pinned_empty(off.shape, np.int64)
+        self.offsets[:] = off
+        self.rates = pinned_empty(rates.shape, np.float64)
+        self.rates[:] = rates
+        eng.upload(self.offsets, self.rates, T, times, epochs, want_profile=True)
+        self.loads = np.array([rates.size])
+        self.parts = [np.arange(off.size - 1)]
+
+    def step(self):
+        return self.eng.compute()
+
+    def gather_step(self):
+        pass
+
+    def run_host(self, out=None, pinned_results=True):
+        return self.eng.run(self.offsets, self.rates, self.T, self.times, self.epochs, want_profile=True, out=out,
+                            pinned_results=pinned_results)
+
+    def close(self):
+        pass
+
+
+def side_config(eng, name, steps, e2e_steps, dist_state, gather):
+    """A secondary workload, device-timed (and optionally end to end), reported under other_configs."""
+    from tapir_b200 import sharded, synthetic
+    rank, world, barrier, allmax = dist_state
+    times, epochs = synthetic.TIMES, synthetic.EPOCHS
+    if name == "cfg2_weak":
+        cfg = dict(synthetic.CONFIGS["cfg2"])
+        cfg["seed"] = cfg["seed"] * 1000 + rank
+        synthetic.CONFIGS["_shard"] = cfg
+        off, rates, T = synthetic.build("_shard")
+        label = workload_name("cfg2") + " per GPU (weak scaling: one such shard per rank, as in round 1)"
+        sb = SoloBatch(eng, off, rates, T, times, epochs)
+        total_sites, total_loci = rates.size * world, (off.size - 1) * world
+    else:
+        off, rates, T = synthetic.build(name)
+        label = workload_name(name)
+        sb = sharded.ShardedBatch(eng, off, rates, T, times, epochs, gather=gather, want_profile=True)
+        total_sites, total_loci = rates.size, off.size - 1
+    step_ms, k, _, tm = timed_steps(eng, sb, steps, 3, barrier)
+    step_ms = allmax(step_ms)
+    rec = {"workload": label, "ms_per_step": step_ms, "value": total_sites * T / (step_ms * 1e-3), "unit": UNIT,
+           "loci_per_s": total_loci / (step_ms * 1e-3), "steps": steps, "kernel_ms": k,
+           "kernel": "%s<%d>" % ("profile_mom_kernel" if tm.profile_moment_form else "profile_kernel", tm.profile_tile_points // 256),
+           "epochs_from_moments": tm.moment_epochs}
+    if world > 1 and name != "cfg2_weak":
+        rec["partition"] = {"sites_per_rank_max_over_mean": float(sb.loads.max() / sb.loads.mean()),
+                            "loci_per_rank": [int(len(p)) for p in sb.parts], "how": "partition_loci: longest-processing-time greedy"}
+    if e2e_steps:
+        out = sb.run_host()
+        sb.run_host(out=out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sb.run_host(out=out)
+        dt = allmax((time.perf_counter() - t0) / e2e_steps)
+        rec["e2e"] = {"value": total_sites * T / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": e2e_steps}
+        del out
+    sb.close()
+    return rec
+
+
 def run_ours(args, rank, world, local_rank):
-    from tapir_b200 import synthetic
-    from tapir_b200 import sharded
-    from tapir_b200.engine import Engine, bind_host_thread_near, pinned_empty
+    from tapir_b200 import sharded, synthetic
+    from tapir_b200.engine import Engine, bind_host_thread_near
 
     times, epochs = synthetic.TIMES, synthetic.EPOCHS
-    # every rank owns one shard of the global batch (same shape, different seed)
-    cfg = dict(synthetic.CONFIGS[args.workload])
-    cfg["seed"] = cfg["seed"] * 1000 + rank
-    synthetic.CONFIGS["_shard"] = cfg
-    off_np, rates_np, T = synthetic.build("_shard")
+    t_build = time.perf_counter()
+    off_np, rates_np, T = synthetic.build(args.workload)          # every rank builds the SAME full batch
+    t_build = time.perf_counter() - t_build
     L, nnz = off_np.size - 1, rates_np.size
-    evals_rank = nnz * T
-    # sites that contribute: a zero rate (invariant site) or a culled (NaN/Inf) site adds exactly 0 everywhere; the
-    # kernels drop them after the load.  `value` counts every site*timepoint (BASELINE.json's metric); the roofline
-    # counts only the FMAs that are algorithmically required, i.e. those of the active sites.
-    with np.errstate(over="ignore", invalid="ignore"):
-        a_np = 16.0 * rates_np * rates_np
-    n_active = int(np.count_nonzero(np.isfinite(a_np) & (a_np != 0.0)))
-    n_slow = int(np.count_nonzero(np.isfinite(a_np) & (a_np != 0.0) & (rates_np >= 0.0) & (rates_np < 0.01953125)))
-    evals_active = n_active * T
 
+    # parity sample and its oracle, and the CPU arm, before any CUDA call (fork safety)
+    sample = parity_sample(L)
+    want = oracle_for(off_np, rates_np, sample, T, epochs) if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(off_np, rates_np, T, times, epochs)   # before any CUDA call (fork safety)
+        cpu = cpu_baseline(off_np, rates_np, T, times, epochs)
 
     dist = torch = None
     if world > 1:
@@ -316,215 +575,194 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    numa_bound = bind_host_thread_near(local_rank) if world > 1 else False   # after the CPU pool (N = 1 keeps all cores)
-    eng = Engine(local_rank)
-    offsets = pinned_empty(off_np.shape, np.int64); offsets[:] = off_np
-    rates = pinned_empty(rates_np.shape, np.float64); rates[:] = rates_np
-
     def barrier():
         if dist is not None:
             dist.barrier()
 
-    # ---- small-result gather (N > 1).  The library keeps every per-locus vector of a batch in ONE device block.
-    #  "push" (default): rank 0 owns a buffer with one slot per rank, exported through CUDA IPC; every rank's
-    #      tapir_cuda_compute ends with a device-to-device copy of its block into its slot over NVLink, on the
-    #      same stream as finalize -- no collective launch inside a step.
-    #  "nccl": one dist.gather of the block per step (fallback if IPC peer memory is unavailable, or --gather nccl)
-    gather = None
-    gather_mode = "none"
-    if dist is not None:
-        eng.upload(offsets, rates, T, times, epochs, want_profile=True)
-        _, slot_bytes, sections = eng.device_small_block()
-        gather_mode = args.gather
-        if gather_mode == "push":
-            try:
-                obj = [eng.gather_create(slot_bytes, world) if rank == 0 else None]
-                dist.broadcast_object_list(obj, src=0)
-                eng.gather_attach(None if rank == 0 else obj[0], slot_bytes, rank)
-                ok = torch.tensor([1], device="cuda")
-            except Exception as err:                      # noqa: BLE001 - any failure means: use NCCL
-                sys.stderr.write("rank %d: push gather unavailable (%s); falling back to NCCL\n" % (rank, err))
-                ok = torch.tensor([0], device="cuda")
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok.item()) == 0:
-                eng.gather_detach()
-                gather_mode = "nccl"
-        if gather_mode == "nccl":
-            class _Dev:
-                def __init__(self, ptr, n):
-                    self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+    def allmax(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
-            state = {}
+    numa_bound = bind_host_thread_near(local_rank) if world > 1 else False   # after the CPU pool (N = 1 keeps all cores)
+    eng = Engine(local_rank)
 
-            def gather():
-                ptr, nbytes, _ = eng.device_small_block()
-                if state.get("ptr") != (ptr, nbytes):
-                    state["ptr"] = (ptr, nbytes)
-                    state["src"] = torch.as_tensor(_Dev(ptr, nbytes // 8), device="cuda")
-                    state["dst"] = [torch.empty_like(state["src"]) for _ in range(world)] if rank == 0 else None
-                dist.gather(state["src"], state["dst"], dst=0)
-                return state["dst"]
+    # ---- ONE batch, split over the ranks by the size-balanced locus partition ----
+    t_shard = time.perf_counter()
+    sb = sharded.ShardedBatch(eng, off_np, rates_np, T, times, epochs, gather=args.gather, want_profile=True)
+    t_shard = time.perf_counter() - t_shard
+    my_sites = int(sb.rates.size)
+    hs_prefix = None
+    if rank == 0 and world == 1 and not args.no_host_side:
+        n_hs = min(L, 512)
+        hs_prefix = (np.array(off_np[:n_hs + 1]), np.array(rates_np[:off_np[n_hs]]))
+    del rates_np                                               # the partition lives in pinned memory now
 
-    # ---- device-resident timing ----
-    eng.upload(offsets, rates, T, times, epochs, want_profile=True)
-    # clocks and throttle reasons are sampled (NVML, 1 ms period) from here to the end of the end-to-end loop: the
-    # attribution pass, the timed steps and the e2e steps all run the same kernels under load
     sampler = ClockSampler(local_rank, period_s=0.001)
     if rank == 0:
         sampler.start()
-    # (1) attribution pass: kernels serialised on one stream so that per-kernel CUDA-event times are exact
-    eng.set_serial_kernels(True)
-    for _ in range(max(args.warmup, 3)):
-        eng.compute()
-    prof_ms = quad_ms = fin_ms = serial_ms = 0.0
-    for _ in range(args.steps):
-        eng.flush_l2()
-        tm = eng.compute()
-        prof_ms += tm.profile_ms; quad_ms += tm.quad_ms; fin_ms += tm.finalize_ms; serial_ms += tm.total_ms
-    # (2) the timed steps proper: the shipped configuration (profile and integral kernels on two streams)
-    eng.set_serial_kernels(False)
-    for _ in range(max(args.warmup, 3)):
-        eng.compute()
-        if gather:
-            gather()
-    barrier()
-    dev_ms, gather_ms, launches = 0.0, 0.0, 0
-    for _ in range(args.steps):
-        eng.flush_l2()                      # untimed: the step starts with a cold L2
-        tm = eng.compute()                  # CUDA events on the library stream, synchronised on both sides
-        dev_ms += tm.total_ms
-        launches += tm.launches
-        if gather:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); gather(); e1.record(); torch.cuda.synchronize()
-            gather_ms += e0.elapsed_time(e1)
-    barrier()
-    step_ms = (dev_ms + gather_ms) / args.steps
-    gather_check = None
-    if dist is not None:
-        # every rank's integral checksum, to compare with what arrived at rank 0
-        mine = eng.download()
-        sums = [None] * world
-        dist.all_gather_object(sums, float(mine.integral.sum()))
-        if rank == 0:
-            E = len(epochs)
-            if gather_mode == "push":
-                raw = eng.gather_read(slot_bytes * world)
-                blocks = [raw[r * slot_bytes:(r + 1) * slot_bytes] for r in range(world)]
-            else:
-                blocks = [d.cpu().numpy().view(np.uint8) for d in gather()]
-            got = [float(b[sections["integral"]:sections["integral"] + L * E * 8].view(np.float64).sum()) for b in blocks]
-            gather_check = "ok" if np.allclose(got, sums, rtol=1e-12) else "MISMATCH %r vs %r" % (got, sums)
-        elif gather_mode == "nccl":
-            gather()
+    step_ms, kernel_ms, launches, tm = timed_steps(eng, sb, args.steps, args.warmup, barrier)
+    step_ms = allmax(step_ms)
 
-    # ---- end to end through the public call: pinned host in, pinned host out ----
-    out = eng.run(offsets, rates, T, times, epochs, want_profile=True, pinned_results=True)   # allocates + warms
+    # ---- correctness of exactly what was timed: the resident batch's results ----
+    out = eng.download(pinned_results=True)                    # this rank's rows (profile included), pinned: reused below
+    gathered = sb.collect(local=out)                           # rank 0: every locus, original order (barrier inside)
+    where = np.empty(L, dtype=np.int64)
+    for r, idx in enumerate(sb.parts):
+        where[idx] = r
+    rows = {int(l): np.array(out.pi_net[int(np.searchsorted(sb.mine, l))]) for l in sample if where[l] == rank}
+    my_sum = float(np.sum(out.integral))
+    if dist is not None:
+        allrows, sums = [None] * world, [None] * world
+        dist.all_gather_object(allrows, rows)
+        dist.all_gather_object(sums, my_sum)
+    else:
+        allrows, sums = [rows], [my_sum]
+    parity = gather_check = checksum = None
+    if rank == 0:
+        merged = {}
+        for d in allrows:
+            merged.update(d)
+        pi_rows = np.stack([merged[int(l)] for l in sample])
+        parity = parity_check(want, pi_rows, {n: gathered[n][sample] for n in ("integral", "abserr", "argmax_epoch", "argmax_t")})
+        checksum = float(np.sum(gathered["integral"]))         # original locus order: the same number at every N
+        if world > 1:
+            ok = np.isclose(checksum, float(np.sum(sums)), rtol=1e-12)
+            gather_check = "ok" if ok else "MISMATCH %r vs %r" % (checksum, float(np.sum(sums)))
+    del gathered
+
+    # ---- end to end through the public call: pinned host in, pinned host out, per-locus vectors at rank 0 ----
     for _ in range(2):
-        eng.run(offsets, rates, T, times, epochs, want_profile=True, out=out)
+        sb.run_host(out=out)
+        if world > 1:
+            sb.collect()
     h0, d0 = eng.transfer_bytes()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.run(offsets, rates, T, times, epochs, want_profile=True, out=out)
-        if gather_mode == "nccl":
-            # the step's results are on the host already (tapir_cuda_run); the per-locus vectors go through NCCL
-            packed = torch.from_numpy(sharded.pack_small(out)).cuda()
-            dst = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
-            dist.gather(packed, dst, dst=0)
-            if rank == 0:
-                _ = [d.cpu() for d in dst]
-            torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+        sb.run_host(out=out)
+        if world > 1:
+            sb.collect()                                       # barrier + rank 0 reads the gather buffer, un-permutes
+    e2e_s = allmax((time.perf_counter() - t0) / args.steps)
     h1, d1 = eng.transfer_bytes()
     clocks = sampler.stop() if rank == 0 else None
-    # PCIe context for the e2e number: the D2H copy of one step's results on its own (pinned destination)
-    eng.upload(offsets, rates, T, times, epochs, want_profile=True)
+    e2e_checksum = float(np.sum(out.integral))
+    # PCIe context for the e2e number: the D2H copy of this rank's results on its own (pinned destination)
+    eng.upload(sb.offsets, sb.rates, T, times, epochs, want_profile=True)
     eng.compute()
     eng.download(out=out)
     _, dd0 = eng.transfer_bytes()
     t0 = time.perf_counter()
-    for _ in range(5):
+    for _ in range(3):
         eng.download(out=out)
-    d2h_s = (time.perf_counter() - t0) / 5
+    d2h_s = (time.perf_counter() - t0) / 3
     _, dd1 = eng.transfer_bytes()
-    d2h_gbs = (dd1 - dd0) / 5 / d2h_s / 1e9
-    checksum = float(out.integral.sum())
-
+    d2h_gbs = (dd1 - dd0) / 3 / d2h_s / 1e9
     peak_tf, _ = eng.fp64_peak()
+    hs_out = None
+    if hs_prefix is not None:
+        hs_out = eng.run(hs_prefix[0], hs_prefix[1], T, times, epochs, want_profile=True)
+    del out
+
+    # executed FP64 work of rank 0's profile launch (counted from its own partition)
+    ex = executed_fp64_ops(sb.offsets, sb.rates, T, tm.profile_tile_points, tm.profile_moment_form, tm.moment_epochs) if rank == 0 else None
+    mode, loads, parts_len = sb.mode, sb.loads, [int(len(p)) for p in sb.parts]
+    sb.close()
+    del sb
+
+    # ---- secondary workloads (device-timed, few steps) ----
+    others = {}
+    if not args.no_other_configs:
+        dist_state = (rank, world, barrier, allmax)
+        if world == 1:
+            others["cfg2"] = side_config(eng, "cfg2", max(3, min(args.steps, 10)), 5, dist_state, args.gather)
+            others["cfg3"] = side_config(eng, "cfg3", 3, 0, dist_state, args.gather)
+        else:
+            others["cfg3"] = side_config(eng, "cfg3", 3, 0, dist_state, args.gather)
+            others["cfg2_weak"] = side_config(eng, "cfg2_weak", max(3, min(args.steps, 10)), 0, dist_state, args.gather)
 
     if dist is not None:
-        t = torch.tensor([step_ms, e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, e2e_s = float(t[0]), float(t[1])
+        dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
 
-    total_evals = evals_rank * world
-    total_loci = L * world
+    total_evals = nnz * T
     peaks, peak_src = measured_peaks()
-    prof_s = prof_ms / args.steps * 1e-3
-    # what tapir_cuda_compute reports it launched (tapir_timing), not a guess from the grid size
+    prof_s = kernel_ms["profile"] * 1e-3
     kernel_name = "%s<%d>" % ("profile_mom_kernel" if tm.profile_moment_form else "profile_kernel", tm.profile_tile_points // 256)
-    achieved_tf = 2.0 * evals_active / prof_s / 1e12      # one FP64 FMA per (active site, timepoint): DESIGN.md
+    direct_tf = 2.0 * ex["n_active"] * T / prof_s / 1e12        # one FP64 FMA per (active site, timepoint): the direct formulation
+    exec_tf = 2.0 * ex["lane_ops"] / prof_s / 1e12             # what the kernel issues to the FP64 pipe
     line = {
         "metric": METRIC, "value": total_evals / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload) + (" per GPU" if world > 1 else ""),
-                   "loci_per_gpu": L, "grid": T, "epochs": epochs, "times": times,
+        "config": {"workload": workload_name(args.workload), "loci": L, "loci_per_gpu": parts_len,
+                   "grid": T, "epochs": epochs, "times": times,
                    "cache": "L2 flushed (256 MB memset) before every timed step",
                    "timing": "CUDA events on the launching stream per step, max over ranks",
-                   "parallelism": ("locus-sharded x%d, per-locus vectors gathered to rank 0 by %s" % (
-                       world, "NVLink peer-memory push fused after finalize (CUDA IPC)" if gather_mode == "push"
-                       else "one NCCL gather per step")) if world > 1 else "single GPU"},
-        "loci_per_s": total_loci / (step_ms * 1e-3),
-        # the same step counted over the sites that need arithmetic only (non-zero finite rate): `value` follows the
-        # metric's definition (every site*timepoint of the input), this one is what the FP64 pipe actually evaluates
-        "active_evals_per_s": evals_active * world / (step_ms * 1e-3),
-        "kernel_ms": {"profile": prof_ms / args.steps, "quad": quad_ms / args.steps, "finalize": fin_ms / args.steps,
-                      "serialised_step": serial_ms / args.steps, "gather": gather_ms / args.steps,
-                      "note": "per-kernel times from a separate pass with the kernels serialised on one stream; "
-                              "ms_per_step is the shipped two-stream configuration"},
+                   "parallelism": ("ONE batch split over %d GPUs by partition_loci (size-balanced LPT) + shard_csr; per-locus "
+                                   "vectors gathered to rank 0 by %s and un-permuted to the original locus order there" % (
+                                       world, "NVLink peer-memory push fused after finalize (CUDA IPC)" if mode == "push"
+                                       else "one NCCL gather per step")) if world > 1 else "single GPU",
+                   "partition": {"sites_per_rank_max_over_mean": float(loads.max() / loads.mean())}},
+        "loci_per_s": L / (step_ms * 1e-3),
+        "kernel_ms": dict(kernel_ms, note="per-kernel times from a separate pass with the kernels serialised on one stream "
+                                          "(rank 0); ms_per_step is the shipped two-stream configuration"),
         "roofline": {
             "bound": "tensor", "pipe": "FP64 (DMMA sub-pipe of the tensor pipe; shared with DFMA on B200)",
-            "kernel": kernel_name, "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": profile_traffic(args.workload),
+            "kernel": kernel_name, "epochs_from_moments": tm.moment_epochs,
+            # executed: DMMA.8x8x4 (256 FMA lanes) and scalar FP64 warp instructions (32 lanes) the launch issues, counted
+            # from the batch by the kernel's own loop structure (checked against ncu's opcode counts in the tests)
+            "achieved": exec_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": exec_tf / peak_tf if peak_tf else None,
+            "executed": {"dmma_instructions": ex["dmma"], "scalar_fp64_warp_instructions": ex["scalar"],
+                         "fma_lane_ops": ex["lane_ops"], "launch": "rank 0's partition, %d sites" % my_sites},
+            "direct_form_equivalent": {
+                "achieved": direct_tf, "frac": direct_tf / peak_tf if peak_tf else None,
+                "note": "2 flop per (site with a non-zero finite rate, grid point) -- the work of the reference's "
+                        "formulation -- over the same kernel time; the moment form executes about a quarter of it, so "
+                        "this ratio is an algebra speed-up and may exceed 1, not a pipe utilisation"},
+            "traffic": profile_traffic(args.workload),
             "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has HBM and bf16 entries only; "
                            "tools/microbench/fp64_pipes.cu: DMMA 37.0, DFMA 36.6 TFLOP/s, one shared pipe)",
-            "algorithmic": "2 flop (1 FP64 FMA) per site*timepoint eval of a site with a non-zero finite rate: "
-                           "%d of the launch's %d evals (zero-rate and culled sites add exactly 0 and are dropped after "
-                           "the load).  profile_mom_kernel EXECUTES about a quarter of them: a site with rate < 0.0195 "
-                           "enters the contraction as 32 Taylor moments per 128-point block of the time tile instead of 32 "
-                           "powers per 32-point block (DESIGN.md 3.1), so this fraction measures the direct formulation's "
-                           "work against the FP64 peak and may exceed 1" % (evals_active, evals_rank),
-            "executed_over_algorithmic": None if T < 1000 else round(
-                (0.25 * n_slow + (n_active - n_slow)) / max(n_active, 1), 4),
-            "active_site_fraction": n_active / max(nnz, 1),
-            "quad_kernel": {"ms": quad_ms / args.steps, "site_epochs_per_s": nnz * len(epochs) / (quad_ms / args.steps * 1e-3)},
+            "active_site_fraction": ex["n_active"] / max(my_sites, 1),
+            "quad": {"ms": kernel_ms["quad"], "note": "quad_scan_kernel + quad_kernel + quad_fix_kernel: rate statistics and "
+                                                      "the sites the moment functional does not serve"},
             # the same evals/s against the ceiling of the reference's formulation, one FP64 exp per
             # (site, timepoint): ~17 pipe operations for a branch-free exp + 3 for a*t*e, on the same measured pipe
-            "naive_one_exp_per_eval": {"ops_per_eval": 20, "ceiling_evals_per_s": peak_tf * 1e12 / 2.0 / 20.0,
-                                       "value_over_ceiling": (evals_rank / (step_ms * 1e-3)) / (peak_tf * 1e12 / 2.0 / 20.0)
+            "naive_one_exp_per_eval": {"ops_per_eval": 20, "ceiling_evals_per_s": peak_tf * 1e12 / 2.0 / 20.0 * world,
+                                       "value_over_ceiling": (total_evals / (step_ms * 1e-3)) / (peak_tf * 1e12 / 2.0 / 20.0 * world)
                                        if peak_tf else None},
-            "hbm": {"achieved_gbs": 8.0 * nnz / prof_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src,
-                    "note": "rate stream, 8 B per site per time tile"},
+            "hbm": {"achieved_gbs": 8.0 * my_sites * max(1, -(-T // tm.profile_tile_points)) / prof_s / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src,
+                    "note": "rate stream of the profile kernel, 8 B per site per time tile"},
         },
         "e2e": {"value": total_evals / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": (h1 - h0) // args.steps, "d2h_bytes_per_step": (d1 - d0) // args.steps,
-                "loci_per_s": total_loci / e2e_s, "timing": "host wall clock around tapir_cuda_run, pinned buffers",
+                "bytes_are": "rank 0's (its partition's rates + work lists in, its profile rows + per-locus vectors out%s)" % (
+                    "; plus the gathered vectors of all ranks" if world > 1 else ""),
+                "loci_per_s": L / e2e_s, "timing": "host wall clock around tapir_cuda_run, pinned buffers, max over ranks",
                 "d2h_alone_ms": d2h_s * 1e3, "d2h_gbs": d2h_gbs, "host_thread_bound_to_gpu_numa_node": numa_bound,
-                "note": "chunks of loci (13 MB of traffic each, a quarter- and a half-size one first) rotate over up to eight lanes (H2D / kernels / D2H of consecutive chunks overlap); bounded below by the D2H copy of the profile"},
-        "gpu_launches": launches, "gather": {"mode": gather_mode, "check": gather_check},
-        "clocks": clocks,
-        "checksum": checksum,
+                "note": "chunks of loci (13 MB of traffic each, a quarter- and a half-size one first) rotate over up to eight "
+                        "lanes (H2D / kernels / D2H of consecutive chunks overlap); bounded below by the D2H copy of the profile"},
+        "parity": parity,
+        "gpu_launches": launches, "gather": {"mode": mode, "check": gather_check},
+        "clocks": clocks, "checksum": checksum, "e2e_checksum_rank0": e2e_checksum,
+        "host_prep": {"build_batch_s": t_build, "partition_shard_upload_s": t_shard,
+                      "note": "untimed: synthetic batch generation; partition_loci + shard_csr into pinned memory + first upload"},
+        "other_configs": others,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    if world == 1 and not args.no_host_side:
-        line["host_side"] = host_side_rates(rates_np, off_np, T, times, epochs, out)
+    if hs_out is not None:
+        line["host_side"] = host_side_rates(hs_prefix[1], hs_prefix[0], T, times, epochs, hs_out)
+    if parity is not None and not parity["ok"]:
+        sys.stderr.write("PARITY GATE FAILED: %r\n" % (parity,))
     print(json.dumps(line))
+    if parity is not None and not parity["ok"]:
+        sys.exit(3)
 
 
 def main():
@@ -533,9 +771,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-side", action="store_true", help="skip the (untimed) ingest / sqlite sample")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--gather", default="push", choices=["push", "nccl"], help="N > 1: how per-locus vectors reach rank 0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
