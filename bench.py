@@ -272,11 +272,11 @@ def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=
     if moment_form:
         groups, fgroups = (n_slow + 31) // 32, (n_fast + 15) // 16
         dmma = 4 * NT * ksteps(n_slow, 32) + 128 * NT + 8 * NT * ((n_mom_epochs + 7) // 8) + 4 * RH * ksteps(n_fast, 16)
-        # scalar FP64 warp instructions.  Per group of the moment pass: c, a (3), z, bounded exp (18), q^128, q^256,
-        # z^2, z^4, three moment seeds, 32 chain multiplies, NB column multiplies (+ a full exp and a multiply for tiles
+        # scalar FP64 warp instructions.  Per group of the moment pass: c, a, z (4 after folding), bounded exp (18),
+        # q^128, q^256, z^2, z^4, three moment seeds, 32 chain multiplies, NB column multiplies (+ a full exp and a multiply for tiles
         # after the first).  Per item: two accumulator sets added (8 NT), 1/k! onto the moments (8 NT), A fragments of
         # the moments -> times step (2 x 8 x (5 + 8)), epilogue (16 RH).  Per group of 16 fast sites: two exps + tables.
-        per_group = 61 + NB
+        per_group = 57 + NB
         per_item = 16 * NT + 208 + 16 * RH
         scalar0 = groups * per_group + per_item + fgroups * 110
         scalar1 = groups * (per_group + 27) + per_item + fgroups * 136

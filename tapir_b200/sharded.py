@@ -263,5 +263,15 @@ class ShardedBatch:
         return full
 
     def close(self):
-        if self.dist is not None and self.mode == "push":
+        """Release the gather buffer: the importing ranks unmap it before its owner frees it."""
+        if self.dist is None or self.mode != "push":
+            return
+        import torch
+        torch.cuda.synchronize()
+        self.dist.barrier()
+        if self.rank != 0:
             self.eng.gather_detach()
+        self.dist.barrier()
+        if self.rank == 0:
+            self.eng.gather_detach()
+        self.mode = "closed"
