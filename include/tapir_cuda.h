@@ -179,6 +179,15 @@ int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_point
  * modified.  Returns TAPIR_E_INVALID on an unreadable or malformed file (tapir_ingest_last_error()). */
 int tapir_ingest_rates(const char *const *paths, int64_t n_files, int n_threads, double correction, int64_t *offsets,
                        double *rates, int64_t capacity, int64_t *needed);
+/* The same in three steps, so that every file is read and parsed once: open parses all files and keeps the rates
+ * (offsets[n_files + 1] and *needed are filled), copy writes rates / correction into a buffer of >= *needed doubles
+ * (e.g. pinned memory sized from *needed), close releases the handle.  A file json.load would reject (truncated,
+ * trailing data) is an error. */
+typedef struct tapir_ingest tapir_ingest;
+int tapir_ingest_open(const char *const *paths, int64_t n_files, int n_threads, tapir_ingest **handle, int64_t *offsets,
+                      int64_t *needed);
+int tapir_ingest_copy(const tapir_ingest *handle, double correction, double *rates, int64_t capacity);
+int tapir_ingest_close(tapir_ingest *handle);
 const char *tapir_ingest_last_error(void);
 
 /* --- measurement helpers used by bench.py --- */

@@ -97,6 +97,10 @@ SYMBOLS = {
     "tapir_mom_epoch_plan": (ctypes.c_int, [_dbl, _dbl, _i64, ctypes.c_int32, ctypes.POINTER(MomEpoch)]),
     "tapir_ingest_rates": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), _i64, ctypes.c_int, _dbl, _vp, _vp, _i64,
                                           ctypes.POINTER(_i64)]),
+    "tapir_ingest_open": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), _i64, ctypes.c_int, ctypes.POINTER(_vp), _vp,
+                                         ctypes.POINTER(_i64)]),
+    "tapir_ingest_copy": (ctypes.c_int, [_vp, _dbl, _vp, _i64]),
+    "tapir_ingest_close": (ctypes.c_int, [_vp]),
     "tapir_ingest_last_error": (ctypes.c_char_p, []),
     "tapir_cuda_fp64_peak": (ctypes.c_int, [_vp, ctypes.POINTER(_dbl), ctypes.POINTER(ctypes.c_float)]),
     "tapir_cuda_flush_l2": (ctypes.c_int, [_vp]),

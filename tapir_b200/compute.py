@@ -108,6 +108,12 @@ def get_net_integral_for_epochs(rates, epochs):
     rates = numpy.ascontiguousarray(rates, dtype=numpy.float64).reshape(-1)
     for span in epochs:
         assert span[0] < span[1], "Start time [{0}] is sooner than end time [{1}]".format(span[0], span[1])
+    if not numpy.isfinite(rates).all():
+        # the reference integrates whatever it is given: a NaN rate makes sum(integral) NaN, an infinite one makes quad
+        # fail.  worker() always filters first (bin/tapir_compute.py:122); the batched engine treats non-finite rates
+        # as culled sites, so an unfiltered vector is refused here rather than silently summed without them.
+        raise ValueError("get_net_integral_for_epochs expects finite rates: filter with rates[numpy.isfinite(rates)] "
+                         "as worker() does (bin/tapir_compute.py:122)")
     if rates.size == 0:
         # numpy.vectorize on an empty vector raises in the reference
         raise ValueError("cannot integrate over an empty rate vector")
@@ -170,45 +176,59 @@ def cull_uninformative_rates(rates, inform):
     return rates * inform
 
 
-def compute_loci(rate_vectors, time_vector, times, epochs, names=None, keep_matrix=False, engine=None, devices=None):
-    """The body of worker() (bin/tapir_compute.py:104-123) for MANY loci in one device pass.
+def compute_batch(offsets, rates, time_vector, times, epochs, engine=None, devices=None, want_profile=True):
+    """The body of worker() (bin/tapir_compute.py:104-123) for MANY loci in one device pass, array in / array out.
 
-    rate_vectors: sequence of 1-D rate arrays (NaN = culled site), already corrected/subset.
-    Returns a list of 7-tuples (name, rates, mean_rate, pi, pi_net, pi_times, pi_epochs) in input order,
-    exactly what insert_pi_data (tapir/db.py:44-61) consumes; `pi` (the (T,S) matrix the reference
-    pickles back to the parent) is None unless keep_matrix is set.  `devices`: list of CUDA device indices to
+    (offsets, rates): CSR pack of the loci's corrected rates (NaN = culled site).  Returns an engine.BatchResult
+    whose row l is locus l: pi_net (T values, the `net` table), pi_times (`discrete`), integral / abserr
+    (`interval`), mean_rate, ... -- no per-locus Python object is built.  `devices`: list of CUDA device indices to
     spread the loci over (one host thread and one context per device); default: the process-wide engine."""
-    eng = engine or (get_engine() if not (devices and len(devices) > 1) else None)
-    n = len(rate_vectors)
-    names = list(names) if names is not None else [None] * n
     time_vector = numpy.asarray(time_vector)
     T = int(time_vector.reshape(-1).size)
     if T and not numpy.array_equal(time_vector.reshape(-1), numpy.arange(T)):
         raise ValueError("the batched path expects the grid get_time(0, T) (bin/tapir_compute.py:135)")
     for span in epochs:
         assert span[0] < span[1], "Start time [{0}] is sooner than end time [{1}]".format(span[0], span[1])
-    vectors = [numpy.ascontiguousarray(v, dtype=numpy.float64).reshape(-1) for v in rate_vectors]
-    for name, v in zip(names, vectors):
-        if not numpy.isfinite(v).any():
-            # the reference dies inside numpy.vectorize on an empty finite-rate vector (SURVEY.md A.2-3)
-            raise ValueError("locus {0!r} has no finite site rate".format(name))
     if times:
         numpy.empty(T)[list(times)]                     # numpy's IndexError for an out-of-range time (compute.py:78)
     span_list = [[s[0], s[1]] for s in epochs]
     if devices is not None and len(devices) > 1:
         from . import sharded
-        offsets, rates = _engine_mod.pack_csr(vectors, pinned=False)
-        res = sharded.run_threaded(offsets, rates, T, list(times), span_list, devices)
-    else:
-        offsets, rates = _engine_mod.pack_csr(vectors, pinned=True)
-        res = eng.run(offsets, rates, T, list(times), span_list, want_profile=True)
+        return sharded.run_threaded(offsets, rates, T, list(times), span_list, devices, want_profile=want_profile)
+    eng = engine or get_engine()
+    return eng.run(offsets, rates, T, list(times), span_list, want_profile=want_profile)
+
+
+def loci_without_finite_rate(offsets, rates):
+    """Indices of the loci that have no finite site rate at all (empty, or every site culled)."""
+    offsets = numpy.asarray(offsets, dtype=numpy.int64)
+    fin = numpy.concatenate([[0], numpy.cumsum(numpy.isfinite(rates), dtype=numpy.int64)])
+    return numpy.nonzero(fin[offsets[1:]] == fin[offsets[:-1]])[0]
+
+
+def compute_loci(rate_vectors, time_vector, times, epochs, names=None, keep_matrix=False, engine=None, devices=None):
+    """compute_batch in the reference's own result format: a list of worker() 7-tuples
+    (name, rates, mean_rate, pi, pi_net, pi_times, pi_epochs) in input order, exactly what insert_pi_data
+    (tapir/db.py:44-61) consumes; `pi` (the (T,S) matrix the reference pickles back to the parent) is None unless
+    keep_matrix is set.  A locus without any finite rate raises ValueError, as the reference dies on it inside
+    numpy.vectorize; the batched driver (driver.run_batch) skips and reports such loci instead."""
+    n = len(rate_vectors)
+    names = list(names) if names is not None else [None] * n
+    vectors = [numpy.ascontiguousarray(v, dtype=numpy.float64).reshape(-1) for v in rate_vectors]
+    offsets, rates = _engine_mod.pack_csr(vectors, pinned=not (devices and len(devices) > 1))
+    bad = loci_without_finite_rate(offsets, rates)
+    if bad.size:
+        raise ValueError("locus {0!r} has no finite site rate".format(names[int(bad[0])]))
+    res = compute_batch(offsets, rates, time_vector, times, epochs, engine=engine, devices=devices)
     labels = ["{0}-{1}".format(s[0], s[1]) for s in epochs]
+    tcol = numpy.asarray(time_vector).reshape(-1, 1)
+    pi_times, integral, abserr = res.pi_times.tolist(), res.integral.tolist(), res.abserr.tolist()
+    mean_rate = res.mean_rate.tolist()
+    pi_net = numpy.array(res.pi_net)                      # one copy out of the (possibly pinned) result buffer
+    times = list(times)
     out = []
-    tcol = time_vector.reshape(-1, 1)
     for l in range(n):
         pi = get_townsend_pi(tcol, vectors[l]) if keep_matrix else None
-        pi_times = dict(zip(times, res.pi_times[l].tolist()))
-        pi_epochs = {lab: {"sum(integral)": float(res.integral[l, k]), "sum(error)": float(res.abserr[l, k])}
-                     for k, lab in enumerate(labels)}
-        out.append((names[l], vectors[l], float(res.mean_rate[l]), pi, numpy.array(res.pi_net[l]), pi_times, pi_epochs))
+        pi_epochs = {lab: {"sum(integral)": integral[l][k], "sum(error)": abserr[l][k]} for k, lab in enumerate(labels)}
+        out.append((names[l], vectors[l], mean_rate[l], pi, pi_net[l], dict(zip(times, pi_times[l])), pi_epochs))
     return out

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -51,7 +52,10 @@ struct Cursor {
         ++p;
         const char* s = p;
         while (p < end && *p != '"') {
-            if (*p == '\\') ++p;
+            if (*p == '\\') {
+                if (p + 1 >= end) return fail("unterminated string");
+                ++p;
+            }
             ++p;
         }
         if (p >= end) return fail("unterminated string");
@@ -122,6 +126,22 @@ struct Cursor {
         double d;
         return num(&d);
     }
+    // after a member's value: consume the remaining members of the enclosing object up to and including its '}'
+    bool finish_object()
+    {
+        for (;;) {
+            ws();
+            if (p < end && *p == '}') { ++p; return true; }
+            if (p >= end || *p != ',') return fail("expected ',' or '}'");
+            ++p;
+            ws();
+            if (!str(nullptr)) return false;
+            ws();
+            if (p >= end || *p != ':') return fail("expected ':'");
+            ++p;
+            if (!skip()) return false;
+        }
+    }
     // enter an object and position the cursor on the value of `key`; false (no error) if the key is absent
     bool find_key(const char* key, bool* found)
     {
@@ -161,7 +181,15 @@ bool parse_rates(const std::string& text, std::vector<double>& out, std::string&
     if (c.p >= c.end || *c.p != '[') { err = "\"rates\" is not a list"; return false; }
     ++c.p;
     c.ws();
-    if (c.p < c.end && *c.p == ']') return true;
+    // the rest of the document is walked to its end as json.load does: a truncated or corrupt file is an error
+    auto rest = [&]() {
+        ++c.p;                                             // the ']' that closes the list
+        if (!c.finish_object() || !c.finish_object()) { err = c.err; return false; }   // "sites", then the document
+        c.ws();
+        if (c.p != c.end) { err = "trailing data after the JSON document"; return false; }
+        return true;
+    };
+    if (c.p < c.end && *c.p == ']') return rest();
     for (;;) {
         // one {"site":..,"subst":..,"rate":..,"ll":..} record; the record must be consumed to its end
         c.ws();
@@ -198,7 +226,7 @@ bool parse_rates(const std::string& text, std::vector<double>& out, std::string&
         out.push_back(rate);
         c.ws();
         if (c.p < c.end && *c.p == ',') { ++c.p; continue; }
-        if (c.p < c.end && *c.p == ']') return true;
+        if (c.p < c.end && *c.p == ']') return rest();
         err = "expected ',' or ']'";
         return false;
     }
@@ -224,16 +252,31 @@ extern "C" {
 
 const char* tapir_ingest_last_error(void) { return g_ingest_error.c_str(); }
 
-int tapir_ingest_rates(const char* const* paths, int64_t n_files, int n_threads, double correction, int64_t* offsets,
-                       double* rates, int64_t capacity, int64_t* needed)
+}  // extern "C" (reopened below)
+
+struct tapir_ingest {
+    std::vector<std::vector<double>> per_file;
+};
+
+extern "C" {
+
+int tapir_ingest_open(const char* const* paths, int64_t n_files, int n_threads, tapir_ingest** handle, int64_t* offsets,
+                      int64_t* needed)
 {
-    if (n_files < 0 || (n_files > 0 && !paths) || !offsets || !needed) {
+    if (handle) *handle = nullptr;
+    if (n_files < 0 || (n_files > 0 && !paths) || !offsets || !needed || !handle) {
         g_ingest_error = "bad argument";
         return TAPIR_E_INVALID;
     }
     if (n_threads < 1) n_threads = 1;
     if (int64_t(n_threads) > n_files) n_threads = int(std::max<int64_t>(1, n_files));
-    std::vector<std::vector<double>> per_file(static_cast<size_t>(n_files));
+    tapir_ingest* h = new (std::nothrow) tapir_ingest();
+    if (!h) {
+        g_ingest_error = "out of host memory";
+        return TAPIR_E_NOMEM;
+    }
+    std::vector<std::vector<double>>& per_file = h->per_file;
+    per_file.resize(static_cast<size_t>(n_files));
     std::atomic<int64_t> next{0};
     std::atomic<int64_t> bad{-1};
     std::vector<std::string> errors(static_cast<size_t>(n_threads));
@@ -261,6 +304,7 @@ int tapir_ingest_rates(const char* const* paths, int64_t n_files, int n_threads,
     if (bad.load() >= 0) {
         for (const std::string& e : errors)
             if (!e.empty()) { g_ingest_error = e; break; }
+        delete h;
         return TAPIR_E_INVALID;
     }
     int64_t total = 0;
@@ -270,13 +314,45 @@ int tapir_ingest_rates(const char* const* paths, int64_t n_files, int n_threads,
         offsets[i + 1] = total;
     }
     *needed = total;
-    if (total > capacity || (total > 0 && !rates)) return TAPIR_OK;  // caller re-calls with a buffer of *needed doubles
-    for (int64_t i = 0; i < n_files; ++i) {
-        const std::vector<double>& v = per_file[size_t(i)];
-        double* dst = rates + offsets[i];
+    *handle = h;
+    return TAPIR_OK;
+}
+
+int tapir_ingest_copy(const tapir_ingest* h, double correction, double* rates, int64_t capacity)
+{
+    if (!h) {
+        g_ingest_error = "null handle";
+        return TAPIR_E_INVALID;
+    }
+    int64_t total = 0;
+    for (const auto& v : h->per_file) total += int64_t(v.size());
+    if (total > capacity || (total > 0 && !rates)) {
+        g_ingest_error = "rates buffer too small";
+        return TAPIR_E_INVALID;
+    }
+    double* dst = rates;
+    for (const auto& v : h->per_file) {
         for (size_t k = 0; k < v.size(); ++k) dst[k] = v[k] / correction;
+        dst += v.size();
     }
     return TAPIR_OK;
+}
+
+int tapir_ingest_close(tapir_ingest* h)
+{
+    delete h;
+    return TAPIR_OK;
+}
+
+int tapir_ingest_rates(const char* const* paths, int64_t n_files, int n_threads, double correction, int64_t* offsets,
+                       double* rates, int64_t capacity, int64_t* needed)
+{
+    tapir_ingest* h = nullptr;
+    int rc = tapir_ingest_open(paths, n_files, n_threads, &h, offsets, needed);
+    if (rc != TAPIR_OK) return rc;
+    if (*needed <= capacity && (*needed == 0 || rates)) rc = tapir_ingest_copy(h, correction, rates, capacity);
+    tapir_ingest_close(h);
+    return rc;   // *needed > capacity: the caller re-calls with a buffer of *needed doubles (or uses open / copy / close)
 }
 
 }  // extern "C"

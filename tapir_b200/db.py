@@ -68,25 +68,36 @@ def insert_pi_data(conn, c, pis):
     return
 
 
-def insert_batch(conn, c, names, result, times, epochs, with_net=True):
+def insert_batch(conn, c, names, result, times, epochs, with_net=True, block=4096):
     """Bulk form of insert_pi_data straight from an engine.BatchResult (row l = locus l): same rows, same
-    order, one executemany per table.  `with_net=False` skips the T-rows-per-locus `net` table."""
+    order, one executemany per table and block of loci, rows built from whole-array tolist() calls (no per-value
+    Python arithmetic).  `with_net=False` skips the T-rows-per-locus `net` table."""
     labels = ["{0}-{1}".format(s[0], s[1]) for s in epochs]
-    keys = []
-    for name in names:
-        c.execute("INSERT INTO loci(locus) VALUES (?)", (locus_name(name),))
-        keys.append(c.lastrowid)
-    if with_net and result.pi_net is not None:
+    n = len(names)
+    c.executemany("INSERT INTO loci(locus) VALUES (?)", ((locus_name(name),) for name in names))
+    # AUTOINCREMENT ids of one executemany are consecutive: the last one is the table's maximum
+    last = c.execute("SELECT MAX(id) FROM loci").fetchone()[0] if n else 0
+    keys = list(range(last - n + 1, last + 1))
+    import numpy
+    if with_net and result.pi_net is not None and n:
         T = result.pi_net.shape[1]
-        c.executemany("INSERT INTO net VALUES (?,?,?)",
-                      ((keys[l], k, v) for l in range(len(keys)) for k, v in zip(range(T), result.pi_net[l].tolist())))
-    if times:
+        tt = list(range(T))
+        for l0 in range(0, n, max(1, block)):
+            l1 = min(n, l0 + block)
+            vals = numpy.asarray(result.pi_net[l0:l1]).reshape(-1).tolist()
+            ids = numpy.repeat(numpy.asarray(keys[l0:l1]), T).tolist()
+            c.executemany("INSERT INTO net VALUES (?,?,?)", zip(ids, tt * (l1 - l0), vals))
+    if times and n:
+        K = len(times)
+        ids = numpy.repeat(numpy.asarray(keys), K).tolist()
         c.executemany("INSERT INTO discrete VALUES (?,?,?)",
-                      ((keys[l], int(t), v) for l in range(len(keys)) for t, v in zip(times, result.pi_times[l].tolist())))
-    if labels:
+                      zip(ids, [int(t) for t in times] * n, numpy.asarray(result.pi_times).reshape(-1).tolist()))
+    if labels and n:
+        E = len(labels)
+        ids = numpy.repeat(numpy.asarray(keys), E).tolist()
         c.executemany("INSERT INTO interval VALUES (?,?,?,?)",
-                      ((keys[l], lab, i, e) for l in range(len(keys))
-                       for lab, i, e in zip(labels, result.integral[l].tolist(), result.abserr[l].tolist())))
+                      zip(ids, labels * n, numpy.asarray(result.integral).reshape(-1).tolist(),
+                          numpy.asarray(result.abserr).reshape(-1).tolist()))
     return keys
 
 

@@ -9,12 +9,16 @@ context per device); without it one GPU is used.  The arithmetic always runs on 
 import argparse
 import os
 import sys
+import time
 from subprocess import PIPE, Popen
 
 import numpy
 
 from . import base, compute, db
 from .engine import device_count
+
+# wall-clock split of the last main(): loci, skipped, ingest_s, gpu_s, sqlite_s (tools/cli_walltime.py)
+LAST_TIMING = {}
 
 
 def get_args(argv=None):
@@ -50,6 +54,10 @@ def get_args(argv=None):
     # leave them untouched, instead of json.load + rewrite-with-corrected_rates per file (compute.py:30-43)
     parser.add_argument('--no-rate-rewrite', default=False, action='store_true',
                         help="With --site-rates: do not rewrite the *.rates files with corrected rates (fast batched ingest)")
+    # extension: the `net` table holds one row per locus and grid point (10^9 rows for 500,000 loci on a 2,048-point
+    # grid); the plotting scripts that read it (tapir_plot.py, tapir_matplot.py) are optional consumers
+    parser.add_argument('--no-net-table', default=False, action='store_true',
+                        help="Do not fill the per-time-point `net` table (loci, discrete and interval are written as usual)")
     return parser.parse_args(argv)
 
 
@@ -102,37 +110,83 @@ def worker(params):
     return compute.compute_loci([rates], time_vector, times, epochs, names=[alignment], keep_matrix=True)[0]
 
 
-def run_batch(params, threads=1, native_ingest=False, devices=None):
-    """All loci of a run: host-side ingest (optionally threaded), then ONE device pass.
+def load_batch(params, threads=1, native_ingest=False):
+    """Host half of every worker() of a run -> (names, offsets, rates): the loci's rate vectors as one CSR pack.
 
-    native_ingest (only for --site-rates parameters): the rate files are parsed by tapir_ingest_rates on
-    `threads` C++ threads straight into one CSR pack and are not rewritten."""
-    if not params:
-        return []
+    native_ingest (only for --site-rates parameters): the rate files are parsed by tapir_ingest_rates on `threads`
+    C++ threads straight into the pack and are not rewritten; otherwise load_rates() per file (optionally on a thread
+    pool), which keeps the reference's rewrite of every *.rates file."""
+    from .engine import pack_csr
+    names = [p[6] for p in params]
+    subsets = params[0][10] if params else {}
     if native_ingest and all(p[3] is None for p in params):
         from . import ingest
         sys.stdout.write("." * len(params))
         sys.stdout.flush()
-        offsets, rates = ingest.read_rate_files([p[4] for p in params], correction=params[0][5], threads=threads, pinned=False)
-        subsets = params[0][10]
+        offsets, rates = ingest.read_rate_files([p[4] for p in params], correction=params[0][5], threads=threads,
+                                                pinned=not subsets)
+        if not subsets:
+            return names, offsets, rates
         vectors = []
-        for l, p in enumerate(params):
+        for l, name in enumerate(names):
             v = rates[offsets[l]:offsets[l + 1]]
-            name = os.path.basename(p[6])
-            if name in subsets:
-                v = v[subsets[name][0]:subsets[name][1]]
+            base_name = os.path.basename(name)
+            if base_name in subsets:
+                v = v[subsets[base_name][0]:subsets[base_name][1]]
             vectors.append(v)
-        time_vector, times, epochs = params[0][0], params[0][7], params[0][8]
-        return compute.compute_loci(vectors, time_vector, times, epochs, names=[p[6] for p in params], devices=devices)
-    if threads > 1:
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(max_workers=threads) as pool:
-            loaded = list(pool.map(load_rates, params))
     else:
-        loaded = [load_rates(p) for p in params]
+        if threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                loaded = list(pool.map(load_rates, params))
+        else:
+            loaded = [load_rates(p) for p in params]
+        names = [a for a, _ in loaded]
+        vectors = [r for _, r in loaded]
+    offsets, rates = pack_csr(vectors, pinned=True)
+    return names, offsets, rates
+
+
+def run_batch_arrays(params, threads=1, native_ingest=False, devices=None, want_profile=True):
+    """All loci of a run: host-side ingest, then ONE device pass -> (names, BatchResult, skipped).
+
+    A locus without any finite site rate (the reference crashes on it inside numpy.vectorize and takes the whole
+    run down) is left out of the pass and returned in `skipped`; names / result rows cover the remaining loci in
+    glob order."""
+    if not params:
+        return [], None, []
+    t0 = time.perf_counter()
+    names, offsets, rates = load_batch(params, threads=threads, native_ingest=native_ingest)
+    LAST_TIMING["ingest_s"] = time.perf_counter() - t0
+    bad = compute.loci_without_finite_rate(offsets, rates)
+    skipped = [names[int(l)] for l in bad]
+    if bad.size:
+        from .engine import shard_csr
+        keep = numpy.setdiff1d(numpy.arange(len(names)), bad)
+        offsets, rates = shard_csr(offsets, rates, keep, pinned=True)
+        names = [names[int(l)] for l in keep]
     time_vector, times, epochs = params[0][0], params[0][7], params[0][8]
-    return compute.compute_loci([r for _, r in loaded], time_vector, times, epochs, names=[a for a, _ in loaded],
-                                devices=devices)
+    t0 = time.perf_counter()
+    res = compute.compute_batch(offsets, rates, time_vector, times, epochs, devices=devices, want_profile=want_profile)
+    LAST_TIMING["gpu_s"] = time.perf_counter() - t0
+    return names, res, skipped
+
+
+def run_batch(params, threads=1, native_ingest=False, devices=None):
+    """run_batch_arrays in the reference's result format: one worker() 7-tuple per locus (what map(worker, params)
+    returns, bin/tapir_compute.py:160), loci without a finite rate left out."""
+    names, res, _ = run_batch_arrays(params, threads=threads, native_ingest=native_ingest, devices=devices)
+    if res is None:
+        return []
+    times, epochs = params[0][7], params[0][8]
+    labels = ["{0}-{1}".format(s[0], s[1]) for s in epochs]
+    pi_times, integral, abserr = res.pi_times.tolist(), res.integral.tolist(), res.abserr.tolist()
+    mean_rate, pi_net = res.mean_rate.tolist(), numpy.array(res.pi_net)
+    out = []
+    for l, name in enumerate(names):
+        pi_epochs = {lab: {"sum(integral)": integral[l][k], "sum(error)": abserr[l][k]} for k, lab in enumerate(labels)}
+        out.append((name, None, mean_rate[l], None, pi_net[l], dict(zip(times, pi_times[l])), pi_epochs))
+    return out
 
 
 def get_hyphy_conf():
@@ -167,13 +221,22 @@ def main(argv=None):
     # --multiprocessing: all host cores for the ingest (as the reference's Pool) and every visible GPU for the math
     threads = max(1, (os.cpu_count() or 2) - 1) if args.multiprocessing else 1
     devices = list(range(max(1, device_count()))) if args.multiprocessing else None
-    pis = run_batch(params, threads=threads, native_ingest=args.site_rates and args.no_rate_rewrite, devices=devices)
+    t0 = time.perf_counter()
+    names, res, skipped = run_batch_arrays(params, threads=threads, native_ingest=args.site_rates and args.no_rate_rewrite,
+                                           devices=devices, want_profile=not args.no_net_table)
+    if skipped:
+        sys.stdout.write("\nSkipped {0} loci without any finite site rate: {1}{2}\n".format(
+            len(skipped), ", ".join(db.locus_name(s) for s in skipped[:10]), " ..." if len(skipped) > 10 else ""))
+    t2 = time.perf_counter()
     db_name = os.path.join(args.output, 'phylogenetic-informativeness.sqlite')
     sys.stdout.write("\nStoring results in {0}...".format(db_name))
     sys.stdout.flush()
     conn, c = db.create_probe_db(db_name)
-    db.insert_pi_data(conn, c, pis)
+    # the bulk writer: same rows, same order as insert_pi_data over worker() tuples (tapir/db.py:44-61)
+    db.insert_batch(conn, c, names, res, args.times, args.intervals, with_net=not args.no_net_table)
     conn.commit()
+    t3 = time.perf_counter()
+    LAST_TIMING.update(loci=len(names), skipped=len(skipped), ingest_and_gpu_s=t2 - t0, sqlite_s=t3 - t2)
     sys.stdout.write("DONE")
     sys.stdout.flush()
     print("\n")

@@ -22,16 +22,20 @@ def read_rate_files(paths, correction=1, threads=None, pinned=True):
     threads = int(threads or max(1, (os.cpu_count() or 2) - 1))
     offsets = np.zeros(n + 1, dtype=np.int64)
     needed = ctypes.c_int64(0)
+    handle = ctypes.c_void_p()
 
-    def call(buf, cap):
-        rc = lib.tapir_ingest_rates(arr, n, threads, float(correction), offsets.ctypes.data, buf, cap, ctypes.byref(needed))
+    def check(rc):
         if rc != 0:
             msg = (lib.tapir_ingest_last_error() or b"?").decode("utf-8", "replace")
             raise (IOError if msg.startswith("Cannot open") else ValueError)(msg)
 
-    call(None, 0)                                    # sizes only
-    alloc = pinned_empty if pinned else np.empty
-    rates = alloc(int(needed.value), np.float64)
-    if needed.value:
-        call(rates.ctypes.data, int(needed.value))
+    # every file is read and parsed once: open keeps the rates, the buffer is sized from `needed`, copy fills it
+    check(lib.tapir_ingest_open(arr, n, threads, ctypes.byref(handle), offsets.ctypes.data, ctypes.byref(needed)))
+    try:
+        alloc = pinned_empty if pinned else np.empty
+        rates = alloc(int(needed.value), np.float64)
+        if needed.value:
+            check(lib.tapir_ingest_copy(handle, float(correction), rates.ctypes.data, int(needed.value)))
+    finally:
+        lib.tapir_ingest_close(handle)
     return offsets, rates

@@ -52,3 +52,26 @@ def test_json_corner_cases_and_errors(tmp_path):
             ingest.read_rate_files([str(empty), str(bad)], pinned=False)
     with pytest.raises(IOError):
         ingest.read_rate_files([str(tmp_path / "missing.rates")], pinned=False)
+
+
+def test_truncated_and_trailing_documents_are_rejected(tmp_path):
+    """json.load rejects a document that stops early or carries trailing data; so does the batched reader (it walks
+    the document to its end instead of stopping when the rates list closes)."""
+    import json
+    import pytest
+    from tapir_b200 import ingest
+    good = {"sites": {"rates": [{"site": 1, "rate": 0.25, "ll": -1.0}, {"site": 2, "rate": 0.5}], "freqs": {"A": 0.25}},
+            "note": "x\\"}
+    text = json.dumps(good)
+    ok = tmp_path / "ok.rates"
+    ok.write_text(text)
+    off, r = ingest.read_rate_files([str(ok)], pinned=False)
+    assert list(off) == [0, 2] and list(r) == [0.25, 0.5]
+    cut = text.index("]") + 1
+    for k, bad_text in enumerate([text[:cut], text[:-1], text + " 1", text + "}", text[:cut] + "}", text[:-3]]):
+        path = tmp_path / ("bad%d.rates" % k)
+        path.write_text(bad_text)
+        with pytest.raises(ValueError):
+            json.loads(bad_text)
+        with pytest.raises(ValueError):
+            ingest.read_rate_files([str(ok), str(path)], pinned=False)
