@@ -230,8 +230,13 @@ def measured_peaks():
 # The DMMA count follows the kernels' loop structure exactly; the scalar counts per group / per item are read off the
 # kernel source.  tests/test_bench_model.py checks both against the opcode counts of the committed ncu capture.
 # --------------------------------------------------------------------------------------------
+MOM_BOUND = {32: 0.01953125, 16: 0.0048828125}     # moment classes of profile_mom_kernel<RH, KM> (mom_epoch.h)
+
+
 def site_classes(offsets, rates, moment_form, chunk=1 << 26):
-    """Per locus: (# sites of profile_mom_kernel's moment class, # other sites with a non-zero finite rate)."""
+    """Per locus: (# sites of profile_mom_kernel's moment class, # other sites with a non-zero finite rate).
+    moment_form: 0 (direct form: no moment class) or the number of moments per block, 32 or 16 (True = 32)."""
+    bound = MOM_BOUND[16 if moment_form == 16 else 32]
     off = np.asarray(offsets, dtype=np.int64)
     L = off.size - 1
     n_slow, n_fast = np.zeros(L, dtype=np.int64), np.zeros(L, dtype=np.int64)
@@ -244,7 +249,7 @@ def site_classes(offsets, rates, moment_form, chunk=1 << 26):
         r = np.asarray(rates[off[l0]:off[l1]])
         mag = np.abs(r)
         active = (mag > 1.5717277847026288e-162) & (mag <= 3.3519519824856493e+153)   # 16 r^2 neither 0 nor Inf (rate_is_active)
-        slow = active & (r > 0.0) & (r < 0.01953125) if moment_form else np.zeros_like(active)
+        slow = active & (r > 0.0) & (r < bound) if moment_form else np.zeros_like(active)
         seg = off[l0:l1] - off[l0]
         lens = off[l0 + 1:l1 + 1] - off[l0:l1]
         full = np.nonzero(lens > 0)[0]                       # reduceat over the non-empty loci only (their segments tile r)
@@ -261,7 +266,8 @@ def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=
     n_tiles = max(1, (int(T) + TT - 1) // TT)
     RH, NB = TT // 256, TT // 128
     NT = max(1, NB // 8)
-    n_slow, n_fast = site_classes(offsets, rates, bool(moment_form))
+    KM = 16 if moment_form == 16 else 32
+    n_slow, n_fast = site_classes(offsets, rates, moment_form)
 
     def ksteps(cnt, group):
         """k-steps (4 sites each, issued in pairs) summed over the groups of `group` sites of every item."""
@@ -271,13 +277,13 @@ def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=
 
     if moment_form:
         groups, fgroups = (n_slow + 31) // 32, (n_fast + 15) // 16
-        dmma = 4 * NT * ksteps(n_slow, 32) + 128 * NT + 8 * NT * ((n_mom_epochs + 7) // 8) + 4 * RH * ksteps(n_fast, 16)
+        dmma = (KM // 8) * NT * ksteps(n_slow, 32) + 4 * KM * NT + (KM // 4) * NT * ((n_mom_epochs + 7) // 8) + 4 * RH * ksteps(n_fast, 16)
         # scalar FP64 warp instructions.  Per group of the moment pass: c, a, z (4 after folding), bounded exp (18),
-        # q^128, q^256, z^2, z^4, three moment seeds, 32 chain multiplies, NB column multiplies (+ a full exp and a multiply for tiles
+        # q^128, q^256, z^2, z^4, three moment seeds, KM chain multiplies, NB column multiplies (+ a full exp and a multiply for tiles
         # after the first).  Per item: two accumulator sets added (8 NT), 1/k! onto the moments (8 NT), A fragments of
-        # the moments -> times step (2 x 8 x (5 + 8)), epilogue (16 RH).  Per group of 16 fast sites: two exps + tables.
-        per_group = 57 + NB
-        per_item = 16 * NT + 208 + 16 * RH
+        # the moments -> times step (2 x 8 x (5 + KM/4)), epilogue (16 RH).  Per group of 16 fast sites: two exps + tables.
+        per_group = 25 + KM + NB
+        per_item = 16 * NT + 16 * (5 + KM // 4) + 16 * RH
         scalar0 = groups * per_group + per_item + fgroups * 110
         scalar1 = groups * (per_group + 27) + per_item + fgroups * 136
     else:
@@ -532,7 +538,8 @@ def side_config(eng, name, steps, e2e_steps, dist_state, gather):
     step_ms = allmax(step_ms)
     rec = {"workload": label, "ms_per_step": step_ms, "value": total_sites * T / (step_ms * 1e-3), "unit": UNIT,
            "loci_per_s": total_loci / (step_ms * 1e-3), "steps": steps, "kernel_ms": k,
-           "kernel": "%s<%d>" % ("profile_mom_kernel" if tm.profile_moment_form else "profile_kernel", tm.profile_tile_points // 256),
+           "kernel": ("profile_mom_kernel<%d, %d moments>" % (tm.profile_tile_points // 256, tm.profile_moment_form)
+                      if tm.profile_moment_form else "profile_kernel<%d>" % (tm.profile_tile_points // 256)),
            "epochs_from_moments": tm.moment_epochs}
     if world > 1 and name != "cfg2_weak":
         rec["partition"] = {"sites_per_rank_max_over_mean": float(sb.loads.max() / sb.loads.mean()),
@@ -692,7 +699,8 @@ def run_ours(args, rank, world, local_rank):
     total_evals = nnz * T
     peaks, peak_src = measured_peaks()
     prof_s = kernel_ms["profile"] * 1e-3
-    kernel_name = "%s<%d>" % ("profile_mom_kernel" if tm.profile_moment_form else "profile_kernel", tm.profile_tile_points // 256)
+    kernel_name = ("profile_mom_kernel<%d, %d moments>" % (tm.profile_tile_points // 256, tm.profile_moment_form)
+                   if tm.profile_moment_form else "profile_kernel<%d>" % (tm.profile_tile_points // 256))
     direct_tf = 2.0 * ex["n_active"] * T / prof_s / 1e12        # one FP64 FMA per (active site, timepoint): the direct formulation
     exec_tf = 2.0 * ex["lane_ops"] / prof_s / 1e12             # what the kernel issues to the FP64 pipe
     line = {

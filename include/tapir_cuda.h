@@ -160,8 +160,9 @@ int tapir_cuda_site_integrals(tapir_cuda_ctx *ctx, double a, double b, const dou
  * per epoch when the profile runs in moment form, exported so that tests can pin it against QUADPACK) ---
  * For the epoch [a, b] on a grid of n_tiles tiles of tile_points points: eligible != 0 when the sum over a locus'
  * slowly decaying sites of scipy.integrate.quad's value (tapir/compute.py:50-52, 81-94) is taken as
- * sum_j p[j] M[j][hb] from the 32 moments of block hb of tile `tile` (block centre tb); only sites with
- * r_min <= rate <= r_max outside [w_lo, w_hi] (and below the moment class bound 0.01953125) are served that way. */
+ * sum_j p[j] M[j][hb] from the n_moments (32 or 16) moments of block hb of tile `tile` (block centre tb); only sites
+ * with r_min <= rate <= r_max outside [w_lo, w_hi] (and below the moment class bound, 0.01953125 for 32 moments,
+ * 0.0048828125 for 16) are served that way. */
 typedef struct tapir_mom_epoch {
     int32_t eligible;
     int32_t tile, hb;
@@ -170,7 +171,7 @@ typedef struct tapir_mom_epoch {
     double r_min, r_max;
     double w_lo, w_hi;
 } tapir_mom_epoch;
-int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, tapir_mom_epoch *out);
+int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, int32_t n_moments, tapir_mom_epoch *out);
 
 /* --- batched rate ingest (host only, no device needed): parse_site_rates' read half (compute.py:30-39) for
  * n_files HyPhy site-rate JSON files on n_threads threads into one CSR pack.  offsets[n_files + 1] is always

@@ -94,7 +94,7 @@ SYMBOLS = {
     "tapir_cuda_pi_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "tapir_cuda_nansum_rows": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "tapir_cuda_site_integrals": (ctypes.c_int, [_vp, _dbl, _dbl, _vp, _i64, _vp, _vp, _vp]),
-    "tapir_mom_epoch_plan": (ctypes.c_int, [_dbl, _dbl, _i64, ctypes.c_int32, ctypes.POINTER(MomEpoch)]),
+    "tapir_mom_epoch_plan": (ctypes.c_int, [_dbl, _dbl, _i64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(MomEpoch)]),
     "tapir_ingest_rates": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), _i64, ctypes.c_int, _dbl, _vp, _vp, _i64,
                                           ctypes.POINTER(_i64)]),
     "tapir_ingest_open": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), _i64, ctypes.c_int, ctypes.POINTER(_vp), _vp,

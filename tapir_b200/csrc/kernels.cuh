@@ -84,6 +84,8 @@ struct EpochBatch {
     // launch when mom_all is set, scan_lo < hi(rate) < scan_hi (the tightest range of the launch) and hi(rate) lies in
     // none of the n_win windows [win_lo, win_hi]
     int32_t mom_all, n_win;
+    int32_t mom_terms;                   // moments per block the profile kernel runs with (32 or 16)
+    uint32_t class_hi;                   // high word of the moment class bound (rate_is_slow)
     uint32_t scan_lo, scan_hi;
     uint32_t win_lo[kEpochsPerLaunch], win_hi[kEpochsPerLaunch];
     const double* mom_p;                // device [e_total][32]: coefficients of the functional, row = output column
@@ -597,7 +599,9 @@ __device__ __forceinline__ void prof_epilogue(const ProfArgs& args, const double
 // skipped when there is none) and the epilogue is profile_kernel's.  All arithmetic is IEEE double; the result differs
 // from profile_kernel's by the series remainder, the cancellation noted above and a different association of the
 // same sums (observed <= 1e-12 relative; the parity gate is 1e-9).
-constexpr int kMomStride = 34;  // doubles per moment row (32 + 2: rows 272 bytes apart, conflict-free 16-byte fragments)
+// (KM = 16: sites with 64 c <= 1.25, rate < 0.0048828125, need only 16 moments for the same remainder -- half the
+// DMMAs, multiplies and shared-memory traffic of the moment pass and of the moments -> times step; the host picks KM
+// per batch from a sample of the rates, tapir_cuda.cu choose_tile)
 constexpr int kLinBlock = 130;  // doubles per 128-point block of the moments -> times scratch (128 + 2: the four row groups
                                 // of a store land 8 banks apart instead of on the same banks)
 // 1/k!, k = 0..31
@@ -615,33 +619,42 @@ __device__ __constant__ double c_inv_fact[32] = {
 // scratch of the moments -> times step ([32][NB+4] moments, then [TT] times) and the 16-site power tables of the
 // fast-site pass; behind all of them the list of up to 32 fast rates (filled during the moment pass, read after the
 // scratch has been used) and the 64-entry compaction queue.  12.25 KB for RH = 4: sixteen warps per SM.
-template <int RH>
+template <int RH, int KM = 32>
 struct MomCfg {
     static constexpr int TT = ProfCfg<RH>::TT, NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
-    static constexpr int Tables = 32 * kMomStride + 32 * WA;
+    static constexpr int MS = KM + 2;  // doubles per moment row (+ 2: rows 16 bytes off a multiple of 128, conflict-free 16-byte fragments)
+    static constexpr int Tables = 32 * MS + 32 * WA;
     static constexpr int Lin = kLinBlock * NB;   // moments -> times scratch, one padded row per 128-point block
-    static constexpr int FastOff = Tables > Lin ? Tables : Lin;
+    static constexpr int Pow = 16 * (kUStride + ProfCfg<RH>::WStride);   // 16-site power tables of the fast-site pass
+    static constexpr int FastOff = (Tables > Lin ? Tables : Lin) > Pow ? (Tables > Lin ? Tables : Lin) : Pow;
     static constexpr int QueueOff = FastOff + 32;
     static constexpr int WarpDoubles = QueueOff + 64;
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
     static constexpr int MinBlocks = (RH == 4 ? 14 : 8) / kProfWarps;  // 144 / 255 registers
     static_assert(16 * (kUStride + ProfCfg<RH>::WStride) <= FastOff, "16-site power tables fit below the fast-site list");
-    static_assert(32 * (NB + 4) <= FastOff, "moment scratch fits");
+    static_assert(KM * (NB + 4) <= FastOff, "moment scratch fits");
+    static_assert(KM == 16 || KM == 32, "16 or 32 moments per block");
     static_assert((kLinBlock * 8) % 16 == 0, "16-byte reads of the scratch stay aligned");
 };
 
-// a slow site: 64 c = 256 r <= 5, i.e. r < 0x3F94000000000000 (0.01953125), r >= 0 -- on the bit pattern
-__device__ __forceinline__ bool rate_is_slow(double r) { return uint32_t(__double2hiint(r)) < 0x3F940000u; }
+// a slow site: 64 c = 256 r <= 5 (KM = 32: r < 0x3F94000000000000 = 0.01953125) or <= 1.25 (KM = 16: r <
+// 0x3F74000000000000 = 0.0048828125), r >= 0 -- on the bit pattern; `bound_hi` is the high word of the bound
+__device__ __forceinline__ bool rate_is_slow(double r, uint32_t bound_hi) { return uint32_t(__double2hiint(r)) < bound_hi; }
+template <int KM>
+__device__ __forceinline__ constexpr uint32_t mom_bound_hi() { return KM == 16 ? 0x3F740000u : 0x3F940000u; }
 
 // TRACE (measurement only): [0] SM id, [1] entry, [12] exit, [13] items done; for the warp's second item
 // [16] claimed, [17] moment pass done, [18] moments -> times done, [19] fast-site pass done, [20] epilogue done,
 // [22] groups of the moment pass, [24] n_fast
-template <int RH, bool TRACE = false>
-__global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profile_mom_kernel(const ProfArgs args)
+template <int RH, bool TRACE = false, int KM = 32>
+__global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) profile_mom_kernel(const ProfArgs args)
 {
     using Cfg = ProfCfg<RH>;
-    using Mom = MomCfg<RH>;
-    constexpr int TT = Cfg::TT, WS = Cfg::WStride, US = kUStride, MS = kMomStride;
+    using Mom = MomCfg<RH, KM>;
+    constexpr int TT = Cfg::TT, WS = Cfg::WStride, US = kUStride, MS = Mom::MS;
+    constexpr int MI = KM / 8;   // moments per fragment row (moment = MI * mrow(fg) + i)
+    constexpr int KS = KM / 4;   // k-steps of the moments -> times product
+    constexpr uint32_t kBound = mom_bound_hi<KM>();
     static_assert(RH >= 4, "moment form: tiles of 1024 points or more");
     constexpr int NB = Mom::NB, NT = Mom::NT, WA = Mom::WA;
     extern __shared__ __align__(16) double smem[];
@@ -660,7 +673,8 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
     double* myM = Us + lane * MS;
     double* WAs = Us + 32 * MS;
     double* myWA = WAs + lane * WA;
-    const double* fragM = Us + fk * MS + 4 * chunk_pair(fg);
+    const int mrow = (MI == 4) ? chunk_pair(fg) : fg;   // 16-byte chunks of a row: MI = 2 needs no permutation
+    const double* fragM = Us + fk * MS + MI * mrow;
     const double* fragWA = WAs + fk * WA + NT * w_chunk<NT>(fg);
     double* Fs = Us + Mom::FastOff;  // up to 32 fast rates of the item, behind everything that is written before they are read
     long long* tr = nullptr;
@@ -694,11 +708,11 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
         n_groups = 0;
 
         // ---------------- moment pass: slow sites ----------------
-        // accA[i][j][c]: moment = 4 chunk_pair(fg) + i, hb = NT w_chunk<NT>(2 fk + c) + j
+        // accA[i][j][c]: moment = MI mrow + i, hb = NT w_chunk<NT>(2 fk + c) + j
         // (two sets, for the even and the odd k-steps: with NT = 1 a single set is a dependent chain of four DMMAs)
-        double accA[4][NT][2], accB[4][NT][2];
+        double accA[MI][NT][2], accB[MI][NT][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
             for (int j = 0; j < NT; ++j) accA[i][j][0] = accA[i][j][1] = accB[i][j][0] = accB[i][j][1] = 0.0;
         int n_fast = 0;
@@ -720,7 +734,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                         lam_q[kAhead - 1] = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
                     }
                     const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
-                    const bool slow = act && rate_is_slow(lam_new);
+                    const bool slow = act && rate_is_slow(lam_new, kBound);
                     const unsigned ballot = __ballot_sync(0xffffffffu, slow);
                     {   // the first 32 fast sites are kept aside, so that their pass need not stream the item again
                         const unsigned bf = __ballot_sync(0xffffffffu, act && !slow);
@@ -749,7 +763,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                         const double z2 = z * z, z4 = z2 * z2;
                         double m0 = u0, m1 = u0 * z, m2 = u0 * z2, m3 = m1 * z2;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
+                        for (int k = 0; k < KM / 4; ++k) {
                             st_shared_v2(myM + 4 * k, m0, m1);
                             st_shared_v2(myM + 4 * k + 2, m2, m3);
                             m0 *= z4; m1 *= z4; m2 *= z4; m3 *= z4;
@@ -765,11 +779,14 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                     ++n_groups;
                     __syncwarp();
                     {
-                        auto fetch = [&](double (&a)[4], double (&b)[NT], int step) {
+                        auto fetch = [&](double (&a)[MI], double (&b)[NT], int step) {
                             const double* mp = fragM + step * (4 * MS);
                             const double2 m01 = *reinterpret_cast<const double2*>(mp);
-                            const double2 m23 = *reinterpret_cast<const double2*>(mp + 2);
-                            a[0] = m01.x; a[1] = m01.y; a[2] = m23.x; a[3] = m23.y;
+                            a[0] = m01.x; a[1] = m01.y;
+                            if constexpr (MI == 4) {
+                                const double2 m23 = *reinterpret_cast<const double2*>(mp + 2);
+                                a[2] = m23.x; a[3] = m23.y;
+                            }
                             const double* wp = fragWA + step * (4 * WA);
                             if constexpr (NT == 1) {
                                 b[0] = wp[0];
@@ -781,14 +798,14 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                                 }
                             }
                         };
-                        auto mma_step = [&](double (&ac)[4][NT][2], const double (&a)[4], const double (&b)[NT]) {
+                        auto mma_step = [&](double (&ac)[MI][NT][2], const double (&a)[MI], const double (&b)[NT]) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
+                            for (int i = 0; i < MI; ++i)
 #pragma unroll
                                 for (int j = 0; j < NT; ++j) dmma884(ac[i][j][0], ac[i][j][1], a[i], b[j]);
                         };
                         const int nk = (cnt + 3) >> 2;  // rows past cnt are zero, so an odd count rounds up
-                        double a0[4], b0[NT], a1[4], b1[NT];
+                        double a0[MI], b0[NT], a1[MI], b1[NT];
                         fetch(a0, b0, 0);
                         for (int st = 0; st < nk; st += 2) {
                             fetch(a1, b1, st + 1);
@@ -808,19 +825,19 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
         double acc[4][RH][2];
         {
             constexpr int SA = NB + 4;
-            double* MA = Us;   // [32][SA]
+            double* MA = Us;   // [KM][SA]
             double* lin = Us;  // [TT], once the B fragments are in registers
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NT; ++j)
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
-                        MA[(4 * chunk_pair(fg) + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c] + accB[i][j][c];
+                        MA[(MI * mrow + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c] + accB[i][j][c];
             __syncwarp();
-            double bf[8][NT];  // B fragments: M[4 ks + fk][8 nt + fg]
+            double bf[KS][NT];  // B fragments: M[4 ks + fk][8 nt + fg]
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
+            for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) bf[ks][nt] = MA[(4 * ks + fk) * SA + 8 * nt + fg];
             // Epoch integrals of the item's slow sites: for every epoch whose centre lies in this tile the sum of the
@@ -834,14 +851,14 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                 ep.col = 0; ep.tile = -1; ep.hb = 0; ep.pad_ = 0;
                 if (valid) ep = args.mom_epochs[g0 + fg];
                 const double* pc = args.mom_p + 32 * ep.col + fk;
-                double pa[8];
+                double pa[KS];
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) pa[ks] = valid ? __ldg(pc + 4 * ks) : 0.0;
+                for (int ks = 0; ks < KS; ++ks) pa[ks] = valid ? __ldg(pc + 4 * ks) : 0.0;
                 double dd[NT][2];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) dd[nt][0] = dd[nt][1] = 0.0;
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
+                for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dmma884(dd[nt][0], dd[nt][1], pa[ks], bf[ks][nt]);
                 if (valid && ep.tile == item.tile && ((ep.hb & 7) >> 1) == fk) {
@@ -855,7 +872,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
             // the 1/k! of the Taylor terms goes onto the moments (8 NT multiplies per lane), so that the A fragments
             // below are pure powers of x
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {
                 const double f = c_inv_fact[4 * ks + fk];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) bf[ks][nt] *= f;
@@ -876,7 +893,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                     for (int nt = 0; nt < NT; ++nt) d[m][nt][0] = d[m][nt][1] = 0.0;
                 }
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
+                for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
                     for (int m = 0; m < 8; ++m) {
 #pragma unroll
@@ -928,7 +945,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH>::MinBlocks) profil
                         const int nb = base + 64 + lane;
                         lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
                     }
-                    const bool fast = rate_is_active(lam_new) && !rate_is_slow(lam_new);
+                    const bool fast = rate_is_active(lam_new) && !rate_is_slow(lam_new, kBound);
                     const unsigned ballot = __ballot_sync(0xffffffffu, fast);
                     if (fast) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
                     qn += __popc(ballot);
@@ -1185,7 +1202,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
     auto need_mask = [&](double lam) -> uint32_t {
         const uint32_t all = (NE > 0) ? ((1u << NE) - 1u) : 1u;
         if (!eb.mom_any) return all;
-        if (!(rate_is_active(lam) && rate_is_slow(lam))) return all;
+        if (!(rate_is_active(lam) && rate_is_slow(lam, eb.class_hi))) return all;
         const unsigned long long rb = (unsigned long long)__double_as_longlong(lam);
         uint32_t need = 0;
 #pragma unroll 1
@@ -1256,7 +1273,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
                     const bool fast = on && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
                     const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps idle lanes' arithmetic finite
                     const uint32_t need = on ? need_mask(lam2) : 0u;
-                    const bool in_moments = on && eb.mom_any && rate_is_active(lam2) && rate_is_slow(lam2);
+                    const bool in_moments = on && eb.mom_any && rate_is_active(lam2) && rate_is_slow(lam2, eb.class_hi);
                     PanelSums ps;
                     // one copy of the GK21 code, looped over the epochs: the fully unrolled form (4 x ~350
                     // instructions) thrashed the instruction cache once the warps ran out of step (18 % of the
@@ -1307,9 +1324,9 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
                             if (__any_sync(0xffffffffu, sub)) {
                                 const double* pc = eb.mom_p + 32 * eb.col[e];
                                 const double z = -64.0 * c;
-                                double hz = __ldg(pc + 31);
+                                double hz = __ldg(pc + eb.mom_terms - 1);
 #pragma unroll 1
-                                for (int k = 30; k >= 0; --k) hz = fma(hz, z, __ldg(pc + k));
+                                for (int k = eb.mom_terms - 2; k >= 0; --k) hz = fma(hz, z, __ldg(pc + k));
                                 const double pv = (a * exp(-(c * eb.tb[e]))) * hz;
                                 if (sub) { vi -= pv; ve -= (kEpmach * 50.0) * pv; }
                             }

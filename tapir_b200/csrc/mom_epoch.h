@@ -38,8 +38,15 @@
 
 namespace tapir {
 
-constexpr double kMomRateBound = 0.01953125;  // 64 c <= 5: the moment class of profile_mom_kernel (rate_is_slow)
-constexpr int kMomTerms = 32;
+// The moment class of profile_mom_kernel<RH, KM>: KM Taylor moments per 128-point block represent a site with
+// 64 c = 256 r <= x(KM) to ~1e-11 (remainder x^KM / KM! against e^{-x}):  KM = 32: x = 5 (r < 0.01953125),
+// KM = 16: x = 1.25 (r < 0.0048828125).  Both bounds are exact binary fractions, so the class test is one comparison of
+// the rate's high word.
+constexpr int kMomTerms = 32;                 // storage of a plan's coefficients (the largest KM)
+inline double mom_class_x(int km) { return km <= 16 ? 1.25 : 5.0; }
+inline double mom_rate_bound(int km) { return mom_class_x(km) / 256.0; }
+inline uint32_t mom_rate_bound_hi(int km) { return km <= 16 ? 0x3F740000u : 0x3F940000u; }
+constexpr double kMomRateBound = 0.01953125;  // KM = 32
 
 struct MomEpochPlan {
     int32_t eligible;    // 0: every site takes the per-site path for this epoch
@@ -77,8 +84,8 @@ inline long double S(long double c, long double C, long double h)
 }
 }  // namespace momdetail
 
-// Plan of the epoch [a, b] on a grid of n_tiles tiles of TT points (TT a multiple of 128).
-inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, MomEpochPlan* out)
+// Plan of the epoch [a, b] on a grid of n_tiles tiles of TT points (TT a multiple of 128) for the class of km moments.
+inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, int km, MomEpochPlan* out)
 {
     using namespace momdetail;
     std::memset(out, 0, sizeof *out);
@@ -94,9 +101,10 @@ inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, MomEpoch
     const int nb = TT / 128;
     const long double tb = 128.0L * gb + 64.0L, d = C - tb;
     // ---- rate range ----
-    long double r_max = kMomRateBound;                        // class bound (exclusive; applied by the class test)
+    const long double xk = mom_class_x(km);
+    long double r_max = mom_rate_bound(km);                   // class bound (exclusive; applied by the class test)
     r_max = fminl(r_max, 1.0L / (4.0L * h));                  // y = c h <= 1
-    r_max = fminl(r_max, 5.0L / (4.0L * (fabsl(d) + h)));     // series remainder as for the profile: (|d| + h) c <= 5
+    r_max = fminl(r_max, xk / (4.0L * (fabsl(d) + h)));       // series remainder as for the profile: (|d| + h) c <= x(km)
     r_max = fminl(r_max, 150.0L / (long double)b);            // c b <= 600: every exponential stays a normal number
     const long double r_min = 2.5e-16L;                       // a = 16 r^2 >= 1e-30: result > uflow / (50 eps)
     if (!(r_max > 1e-12L)) return;
@@ -183,7 +191,7 @@ inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, MomEpoch
     for (int j = 0; j < kMomTerms; ++j) {
         long double s = 0.0L;
         for (int k = 0; k <= j; ++k) s += E[k] * G[j - k];
-        out->p[j] = double(h * s);
+        out->p[j] = (j < km) ? double(h * s) : 0.0;          // P(z) mod z^km
     }
     out->eligible = 1;
     out->tile = int32_t(gb / nb);

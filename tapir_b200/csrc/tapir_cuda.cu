@@ -6,6 +6,7 @@
 #include "../../include/tapir_cuda.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -91,6 +92,7 @@ struct Plan {
     uint32_t flags = 0;
     int rh = 4;       // profile kernel variant
     bool mom_form = false;  // profile_mom_kernel<rh> (moment form) instead of profile_kernel<rh>
+    int mom_terms = 32;     // moments per 128-point block of the moment form (32 or 16, see choose_moments)
     int32_t TT = 1024, n_tiles = 1;
     int64_t n_prof_items = 0, n_quad_items = 0, ws_rows = 0, n_parts = 0;
     std::vector<EpochBatch> batches;
@@ -149,10 +151,11 @@ struct tapir_cuda_ctx {
     int mom_int = 1;         // epoch integrals of the moment class from the locus' moments (mom_epoch.h); TAPIR_MOM_INT=0: per site
     int last_rh = 0, last_mom_form = 0, last_n_mom = 0;  // what the last tapir_cuda_compute launched (tapir_timing)
     // per-device launch configuration, filled once in tapir_cuda_create (index: log2(RH))
-    int prof_per_sm[4] = {0, 0, 0, 0}, mom_per_sm[4] = {0, 0, 0, 0};
+    int prof_per_sm[4] = {0, 0, 0, 0}, mom_per_sm[4] = {0, 0, 0, 0}, mom16_per_sm[4] = {0, 0, 0, 0};
+    int force_terms = 0;                       // TAPIR_MOM_TERMS = 16 / 32
     // plans of the moment-functional epochs seen so far (they depend on the epoch and the tile geometry only; a
     // chunked run would otherwise recompute them for every chunk)
-    struct MomCacheEntry { double a, b; int64_t n_tiles; int32_t TT; MomEpochPlan plan; };
+    struct MomCacheEntry { double a, b; int64_t n_tiles; int32_t TT, km; MomEpochPlan plan; };
     std::vector<MomCacheEntry> mom_cache;
     int prof_ctas_cap = 0, quad_ctas_cap = 0;  // TAPIR_PROF_CTAS_PER_SM / TAPIR_QUAD_CTAS_PER_SM (co-residency experiments)
     int force_rh = 0;                          // TAPIR_CUDA_RH
@@ -249,6 +252,11 @@ cudaError_t configure_profile(tapir_cuda_ctx* ctx, int idx)
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->mom_per_sm[idx], profile_mom_kernel<RH>, kProfWarps * 32, Mom::SmemBytes);
         if (e == cudaSuccess && ctx->prof_trace)
             e = cudaFuncSetAttribute(profile_mom_kernel<RH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom::SmemBytes));
+        using Mom16 = MomCfg<RH, 16>;
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(profile_mom_kernel<RH, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom16::SmemBytes));
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->mom16_per_sm[idx], profile_mom_kernel<RH, false, 16>, kProfWarps * 32, Mom16::SmemBytes);
     }
     return e;
 }
@@ -256,15 +264,20 @@ cudaError_t configure_profile(tapir_cuda_ctx* ctx, int idx)
 int rh_index(int rh) { return rh == 1 ? 0 : rh == 2 ? 1 : rh == 4 ? 2 : 3; }
 
 template <int RH>
-cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, int64_t n_items, bool mom)
+cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, int64_t n_items, bool mom, int km)
 {
     using Cfg = ProfCfg<RH>;
     const int idx = rh_index(RH);
-    int per_sm = std::max(1, mom ? ctx->mom_per_sm[idx] : ctx->prof_per_sm[idx]);
+    int per_sm = std::max(1, mom ? (km == 16 ? ctx->mom16_per_sm[idx] : ctx->mom_per_sm[idx]) : ctx->prof_per_sm[idx]);
     if (ctx->prof_ctas_cap >= 1 && ctx->prof_ctas_cap < per_sm) per_sm = ctx->prof_ctas_cap;  // TAPIR_PROF_CTAS_PER_SM
     const int64_t need = (n_items + kProfWarps - 1) / kProfWarps;
     const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(need, int64_t(ctx->sm_count) * per_sm));
     if constexpr (RH >= 4) {
+        if (mom && km == 16 && !pa.trace) {
+            using Mom16 = MomCfg<RH, 16>;
+            profile_mom_kernel<RH, false, 16><<<unsigned(grid), kProfWarps * 32, Mom16::SmemBytes, ln.stream>>>(pa);
+            return cudaGetLastError();
+        }
         if (mom) {
             using Mom = MomCfg<RH>;
             if (pa.trace)
@@ -307,6 +320,40 @@ void choose_tile(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t T, d
     }
 }
 
+// Moments per 128-point block for the moment form: 32 (class 64 c <= 5) or 16 (class 64 c <= 1.25: half the work per
+// slow site and per item, but every site between the two bounds goes through the power-table pass of the fast
+// sites).  Decided per batch from a strided sample of its rates -- expected FP64-pipe cycles per item, the fast groups
+// weighted by what their exposed latency costs (profiles/r02_moments_sweep.txt).
+int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0, int64_t l1, int rh)
+{
+    if (ctx->force_terms) return ctx->force_terms;
+    const int64_t s0 = p->offsets[l0], s1 = p->offsets[l1];
+    const int64_t nnz = s1 - s0, L = l1 - l0;
+    if (nnz <= 0 || L <= 0) return 32;
+    const int64_t n_sample = std::min<int64_t>(nnz, 16384);
+    const double stride = double(nnz) / double(n_sample);
+    int64_t n_act = 0, n_ge16 = 0, n_ge32 = 0;
+    for (int64_t i = 0; i < n_sample; ++i) {
+        const double r = p->rates[s0 + int64_t(double(i) * stride)];
+        const double a = 16.0 * (r * r);
+        if (!(std::fabs(a) <= DBL_MAX) || a == 0.0) continue;
+        ++n_act;
+        if (!(r >= 0.0 && r < mom_rate_bound(16))) ++n_ge16;
+        if (!(r >= 0.0 && r < mom_rate_bound(32))) ++n_ge32;
+    }
+    if (n_act == 0) return 32;
+    const double per_item = double(nnz) / double(L) * double(n_act) / double(n_sample);   // active sites per item
+    const int NT = rh / 4, NB = 8 * NT;
+    auto cost = [&](int km, double frac_fast) {
+        const double n_fast = per_item * frac_fast, n_slow = per_item - n_fast;
+        const double groups16 = std::ceil((n_fast + std::sqrt(n_fast)) / 16.0);
+        const double fast = groups16 * 2.5 * (256.0 * rh + 220.0) * (n_fast > 24.0 ? 1.2 : 1.0);
+        return n_slow * (0.5 * km * NT + (33.0 + km + NB) / 16.0) + 64.0 * km * NT + fast;
+    };
+    const double c16 = cost(16, double(n_ge16) / double(n_act)), c32 = cost(32, double(n_ge32) / double(n_act));
+    return c16 < c32 ? 16 : 32;
+}
+
 void fill_batches(Plan& plan, const double* epoch_ab)
 {
     plan.batches.clear();
@@ -340,7 +387,14 @@ void fill_batches(Plan& plan, const double* epoch_ab)
                 eb.tp[k][j] = eb.center[k] + absc;
             }
             eb.new_half[k] = (k == 0) || (eb.half[k] != eb.half[k - 1]);
-            if (k == 0) { eb.mom_all = 1; eb.n_win = 0; eb.scan_lo = 0u; eb.scan_hi = 0x3F940000u; }
+            if (k == 0) {
+                eb.mom_all = 1;
+                eb.n_win = 0;
+                eb.scan_lo = 0u;
+                eb.mom_terms = plan.mom_terms;
+                eb.class_hi = mom_rate_bound_hi(plan.mom_terms);
+                eb.scan_hi = eb.class_hi;
+            }
             if (!(size_t(e) < plan.mom.size() && plan.mom[e].eligible)) eb.mom_all = 0;
             if (size_t(e) < plan.mom.size() && plan.mom[e].eligible) {
                 const MomEpochPlan& mp = plan.mom[e];
@@ -472,6 +526,10 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         if ((env = getenv("TAPIR_MOM_INT"))) ctx->mom_int = atoi(env) != 0;
         if ((env = getenv("TAPIR_PROF_CTAS_PER_SM"))) ctx->prof_ctas_cap = atoi(env);
         if ((env = getenv("TAPIR_QUAD_CTAS_PER_SM"))) ctx->quad_ctas_cap = atoi(env);
+        if ((env = getenv("TAPIR_MOM_TERMS"))) {
+            const int v = atoi(env);
+            if (v == 16 || v == 32) ctx->force_terms = v;
+        }
         if ((env = getenv("TAPIR_CUDA_RH"))) {
             const int v = atoi(env);
             if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_rh = v;
@@ -603,6 +661,8 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     plan.n_tiles = int32_t(std::max<int64_t>(1, (plan.T + plan.TT - 1) / plan.TT));
     // epochs whose sums come out of the profile's moments (mom_epoch.h); the others, and the sites outside an
     // epoch's rate range, are integrated per site by quad_kernel
+    plan.mom_terms = plan.mom_form ? choose_moments(ctx, p, l0, l1, plan.rh) : 32;
+    if (ctx->prof_trace) plan.mom_terms = 32;   // (the trace instantiation exists for 32 moments only)
     plan.mom.assign(size_t(plan.E), MomEpochPlan());
     plan.n_mom = 0;
     plan.mom_mask = 0;
@@ -611,11 +671,11 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
             const double ea = p->epoch_ab[2 * e], eb_ = p->epoch_ab[2 * e + 1];
             const tapir_cuda_ctx::MomCacheEntry* hit = nullptr;
             for (const auto& ce : ctx->mom_cache)
-                if (ce.a == ea && ce.b == eb_ && ce.n_tiles == plan.n_tiles && ce.TT == plan.TT) { hit = &ce; break; }
+                if (ce.a == ea && ce.b == eb_ && ce.n_tiles == plan.n_tiles && ce.TT == plan.TT && ce.km == plan.mom_terms) { hit = &ce; break; }
             if (!hit) {
                 if (ctx->mom_cache.size() >= 4096) ctx->mom_cache.clear();
-                tapir_cuda_ctx::MomCacheEntry ce{ea, eb_, plan.n_tiles, plan.TT, MomEpochPlan()};
-                mom_epoch_plan(ea, eb_, plan.n_tiles, plan.TT, &ce.plan);
+                tapir_cuda_ctx::MomCacheEntry ce{ea, eb_, plan.n_tiles, plan.TT, plan.mom_terms, MomEpochPlan()};
+                mom_epoch_plan(ea, eb_, plan.n_tiles, plan.TT, plan.mom_terms, &ce.plan);
                 ctx->mom_cache.push_back(ce);
                 hit = &ctx->mom_cache.back();
             }
@@ -818,10 +878,10 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
             pa.e_total = plan.E;
             cudaError_t e = cudaSuccess;
             switch (plan.rh) {
-                case 1: e = launch_profile<1>(ctx, ln, pa, plan.n_prof_items, false); break;
-                case 2: e = launch_profile<2>(ctx, ln, pa, plan.n_prof_items, false); break;
-                case 4: e = launch_profile<4>(ctx, ln, pa, plan.n_prof_items, plan.mom_form); break;
-                default: e = launch_profile<8>(ctx, ln, pa, plan.n_prof_items, plan.mom_form); break;
+                case 1: e = launch_profile<1>(ctx, ln, pa, plan.n_prof_items, false, 32); break;
+                case 2: e = launch_profile<2>(ctx, ln, pa, plan.n_prof_items, false, 32); break;
+                case 4: e = launch_profile<4>(ctx, ln, pa, plan.n_prof_items, plan.mom_form, plan.mom_terms); break;
+                default: e = launch_profile<8>(ctx, ln, pa, plan.n_prof_items, plan.mom_form, plan.mom_terms); break;
             }
             CU(ctx, e);
             ++launches;
@@ -991,7 +1051,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync,
         }
         timing->launches = launches;
         timing->profile_tile_points = plan.TT;
-        timing->profile_moment_form = plan.mom_form ? 1 : 0;
+        timing->profile_moment_form = plan.mom_form ? plan.mom_terms : 0;
         timing->moment_epochs = plan.mom_form ? plan.n_mom : 0;
     }
     return TAPIR_OK;
@@ -1426,12 +1486,13 @@ int tapir_cuda_fp64_peak(tapir_cuda_ctx* ctx, double* tflops, float* ms_out)
     return TAPIR_OK;
 }
 
-int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, tapir_mom_epoch* out)
+int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, int32_t n_moments, tapir_mom_epoch* out)
 {
     static_assert(sizeof(tapir_mom_epoch) == sizeof(MomEpochPlan), "public and internal plan structs agree");
-    if (!out || n_tiles < 1 || tile_points < 1024 || tile_points % 1024) return fail(nullptr, TAPIR_E_INVALID, "bad plan geometry");
+    if (!out || n_tiles < 1 || tile_points < 1024 || tile_points % 1024 || (n_moments != 16 && n_moments != 32))
+        return fail(nullptr, TAPIR_E_INVALID, "bad plan geometry");
     MomEpochPlan mp;
-    mom_epoch_plan(a, b, n_tiles, tile_points, &mp);
+    mom_epoch_plan(a, b, n_tiles, tile_points, n_moments, &mp);
     memcpy(out, &mp, sizeof mp);
     return TAPIR_OK;
 }

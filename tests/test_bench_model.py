@@ -35,7 +35,7 @@ def test_executed_work_model_matches_ncu_opcode_counts():
     op = _opcodes(files[-1], "profile_mom_kernel<4")
     from tapir_b200 import synthetic
     off, rates, T = synthetic.build("cfg2")
-    ex = bench.executed_fp64_ops(off, rates, T, 1024, 1, n_mom_epochs=4)
+    ex = bench.executed_fp64_ops(off, rates, T, 1024, 32, n_mom_epochs=4)
     assert abs(ex["dmma"] - op["DMMA"]) <= 0.005 * op["DMMA"], (ex["dmma"], op["DMMA"])
     scalar = sum(op.get(k, 0) for k in ("DMUL", "DFMA", "DADD", "DSETP", "DMNMX"))
     assert abs(ex["scalar"] - scalar) <= 0.10 * scalar, (ex["scalar"], scalar)
@@ -49,14 +49,14 @@ def test_site_classes_counts():
     loci[2][:5] = [0.0, np.nan, np.inf, 0.5, 1e-200]
     off = np.concatenate([[0], np.cumsum([len(x) for x in loci])]).astype(np.int64)
     rates = np.concatenate(loci)
-    n_slow, n_fast = bench.site_classes(off, rates, True, chunk=64)
+    n_slow, n_fast = bench.site_classes(off, rates, 32, chunk=64)
     for l, x in enumerate(loci):
         with np.errstate(over="ignore", invalid="ignore"):
             a = 16 * x * x
         act = np.isfinite(a) & (a != 0)
         slow = act & (x > 0) & (x < 0.01953125)
         assert (n_slow[l], n_fast[l]) == (int(slow.sum()), int((act & ~slow).sum())), l
-    n0, n1 = bench.site_classes(off, rates, False)
+    n0, n1 = bench.site_classes(off, rates, 0)
     assert n0.sum() == 0 and np.array_equal(n1, n_slow + n_fast)
 
 

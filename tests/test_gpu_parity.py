@@ -513,7 +513,7 @@ def test_cfg4_path_moment_form_2048_tiles_with_split_sites(eng):
     off, rates = pack_csr(loci, pinned=False)
     eng.upload(off, rates, T, [5, -1, 2047, 2048], synthetic.EPOCHS, want_profile=True)
     tm = eng.compute()
-    assert tm.profile_moment_form == 1 and tm.profile_tile_points == 2048, (tm.profile_moment_form, tm.profile_tile_points)
+    assert tm.profile_moment_form in (16, 32) and tm.profile_tile_points == 2048, (tm.profile_moment_form, tm.profile_tile_points)
     res = eng.download()
     tiles = (T + 2047) // 2048
     ts = sorted(set([0, 1, T - 1] + [2048 * k for k in range(tiles)] + [min(T, 2048 * (k + 1)) - 1 for k in range(tiles)]
@@ -536,31 +536,34 @@ def test_cfg4_path_moment_form_2048_tiles_with_split_sites(eng):
     assert np.array_equal(res.pi_net, again.pi_net) and np.array_equal(res.integral, again.integral)   # deterministic
 
 
-def _mom_plan(a, b, n_tiles, tile_points):
+def _mom_plan(a, b, n_tiles, tile_points, km=32):
     import ctypes
     from tapir_b200 import _lib
     out = _lib.MomEpoch()
-    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, ctypes.byref(out)))
+    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, km, ctypes.byref(out)))
     return out
 
 
+@pytest.mark.parametrize("km", [32, 16])
 @pytest.mark.parametrize("T", [1000, 2048, 4096])
-def test_moment_functional_epoch_sums(eng, T):
+def test_moment_functional_epoch_sums(monkeypatch, T, km):
     """Epoch sums of the slow sites come out of the profile's moments (mom_epoch.h); sites inside an epoch's excluded
     window, above its r_max, below its r_min, and faster sites are integrated per site, and the window sites'
     polynomial value is taken out again.  Every class, on both sides of every boundary, in one batch -- together
     with epochs the functional does not serve (wide, negative, beyond the grid) and more than eight epochs."""
     from oracle import capi
-    from tapir_b200.engine import pack_csr
+    from tapir_b200.engine import Engine, pack_csr
+    monkeypatch.setenv("TAPIR_MOM_TERMS", str(km))            # the class of 32 or of 16 moments, whatever the rates suggest
+    eng = Engine(0)
     rng = np.random.default_rng(T)
     epochs = [[32, 42], [88, 98], [164, 174], [0, 64], [120, 136], [1, 2], [0, 200], [-3, 5], [60, 68], [127, 129],
               [T - 30, T - 20], [T + 50, T + 60], [3 * T // 4, 3 * T // 4 + 11], [T - 3, T - 1], [500, 502]]
     tile_points = 1024 if T <= 1024 else 2048
     n_tiles = (T + tile_points - 1) // tile_points
-    plans = [_mom_plan(a, b, n_tiles, tile_points) for a, b in epochs]
+    plans = [_mom_plan(a, b, n_tiles, tile_points, km) for a, b in epochs]
     assert sum(p.eligible for p in plans) >= 11 and not plans[6].eligible and not plans[7].eligible
     assert sum(p.eligible and p.w_lo <= p.w_hi for p in plans) >= 2      # narrow far epochs: an excluded window exists
-    special = [1e-20, 1e-100, 2.4e-16, 2.6e-16, 0.0195, 0.019531, 0.01953125, 0.0196, 0.3]
+    special = [1e-20, 1e-100, 2.4e-16, 2.6e-16, 0.0195, 0.019531, 0.01953125, 0.0196, 0.3, 0.00488, 0.0048828125, 0.004883]
     for p in plans:
         if p.eligible:
             for edge in (p.w_lo, p.w_hi, p.r_max):
@@ -576,7 +579,7 @@ def test_moment_functional_epoch_sums(eng, T):
     off, rates = pack_csr(loci, pinned=False)
     eng.upload(off, rates, T, [1], epochs, want_profile=False)
     tm = eng.compute()
-    assert tm.profile_moment_form == 1 and tm.moment_epochs == sum(p.eligible for p in plans)
+    assert tm.profile_moment_form == km and tm.moment_epochs == sum(p.eligible for p in plans)
     res = eng.download()
     for l, lam in enumerate(loci):
         ok = lam[np.isfinite(lam)]
@@ -596,6 +599,7 @@ def test_moment_functional_epoch_sums(eng, T):
         assert res.argmax_epoch[l] == int(np.argmax(si))
     again = eng.run(off, rates, T, [1], epochs, want_profile=False)
     assert np.array_equal(res.integral, again.integral) and np.array_equal(res.abserr, again.abserr)
+    eng.close()
 
 
 def test_moment_functional_agrees_with_per_site_path(eng, monkeypatch):
@@ -622,7 +626,7 @@ def test_moment_functional_agrees_with_per_site_path(eng, monkeypatch):
     np.testing.assert_array_equal(a.mean_rate, b.mean_rate)
 
 
-@pytest.mark.parametrize("rh,mom", [(1, 0), (2, 0), (4, 0), (8, 0), (4, 1), (8, 1)])
+@pytest.mark.parametrize("rh,mom", [(1, 0), (2, 0), (4, 0), (8, 0), (4, 32), (8, 32), (4, 16), (8, 16)])
 def test_every_profile_kernel_variant(monkeypatch, rh, mom):
     """The tile-size model only ever picks some of the six profile kernels for a given shape; here each one is forced
     (TAPIR_CUDA_RH / TAPIR_PROF_MOM, read when the context is created) on the same ragged batch and grid."""
@@ -630,11 +634,14 @@ def test_every_profile_kernel_variant(monkeypatch, rh, mom):
     from tapir_b200 import synthetic
     from tapir_b200.engine import Engine, pack_csr
     monkeypatch.setenv("TAPIR_CUDA_RH", str(rh))
-    monkeypatch.setenv("TAPIR_PROF_MOM", str(mom))
+    monkeypatch.setenv("TAPIR_PROF_MOM", "1" if mom else "0")
+    if mom:
+        monkeypatch.setenv("TAPIR_MOM_TERMS", str(mom))
     rng = np.random.default_rng(rh * 10 + mom)
     T = 2500
     loci = [synthetic.uce_rates(rng, n, T, nan_frac=0.05) for n in (1, 33, 257, 700, 1500)]
     loci[3][:40] = rng.uniform(0.02, 1.0, 40)
+    loci[4][:100] = rng.uniform(0.004, 0.02, 100)           # between the two class bounds
     off, rates = pack_csr(loci, pinned=False)
     e = Engine(0)
     try:

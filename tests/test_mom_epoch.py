@@ -21,25 +21,29 @@ EPS = np.finfo(float).eps
 CLASS_BOUND = 0.01953125
 
 
-def plan(a, b, n_tiles=8, tile_points=1024):
+BOUND = {32: 0.01953125, 16: 0.0048828125}       # the moment classes of profile_mom_kernel<RH, KM>
+
+
+def plan(a, b, n_tiles=8, tile_points=1024, km=32):
     out = _lib.MomEpoch()
-    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, ctypes.byref(out)))
+    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, km, ctypes.byref(out)))
+    out.km = km
     return out
 
 
-def moments(rates, tile, hb, tile_points):
+def moments(rates, tile, hb, tile_points, km=32):
     """M[k] = sum_s a e^{-c T0} (-64 c)^k e^{-c (128 hb + 64)} of block hb of the tile (kernels.cuh, moment pass)."""
     lam = np.asarray(rates, dtype=np.float64)
     a, c = 16.0 * lam * lam, 4.0 * lam
     u0 = a * np.exp(-(c * float(tile * tile_points)))
     z = -64.0 * c
     w = np.exp(z) * np.exp(2.0 * z) ** hb            # q^64 (q^128)^hb
-    return np.array([np.sum((u0 * z ** k) * w) for k in range(32)])
+    return np.array([np.sum((u0 * z ** k) * w) if k < km else 0.0 for k in range(32)])
 
 
 def served(pl, rates):
     r = np.asarray(rates)
-    ok = (r > 1.57e-162) & (r < CLASS_BOUND) & (r >= pl.r_min) & (r <= pl.r_max)
+    ok = (r > 1.57e-162) & (r < BOUND[getattr(pl, "km", 32)]) & (r >= pl.r_min) & (r <= pl.r_max)
     return ok & ~((r >= pl.w_lo) & (r <= pl.w_hi))
 
 
@@ -47,40 +51,42 @@ EPOCHS = [(32, 42), (88, 98), (95, 105), (164, 174), (0, 10), (0, 1), (3, 40), (
           (127, 129), (500, 564), (1000, 1002), (1023, 1025), (2100, 2110), (4000, 4050), (7000, 7010)]
 
 
+@pytest.mark.parametrize("km", [32, 16])
 @pytest.mark.parametrize("span", EPOCHS)
-def test_functional_matches_quadpack_sums(span):
+def test_functional_matches_quadpack_sums(span, km):
     a, b = span
     for tile_points in (1024, 2048):
-        pl = plan(a, b, n_tiles=8, tile_points=tile_points)
+        pl = plan(a, b, n_tiles=8, tile_points=tile_points, km=km)
         assert pl.eligible, span
         C = 0.5 * (a + b)
         gb = int(C // 128)
         assert (pl.tile, pl.hb, pl.tb) == (gb // (tile_points // 128), gb % (tile_points // 128), 128.0 * gb + 64.0)
         rng = np.random.default_rng(a * 1000 + b)
-        lam = np.concatenate([rng.gamma(0.5, 0.004, 3000), rng.uniform(0, CLASS_BOUND, 1000),
+        lam = np.concatenate([rng.gamma(0.5, 0.004, 3000), rng.uniform(0, BOUND[km], 1000),
                               10.0 ** rng.uniform(-15, -3, 500)])
         lam = lam[served(pl, lam)]
-        assert lam.size > 300
+        assert lam.size > 300 and np.all(np.array(pl.p[km:]) == 0.0)
         integ, err, last = capi.epoch_sites(lam, a, b)
         assert np.all(last == 1)
         want = float(np.sum(integ))
-        got = float(np.dot(np.array(pl.p[:]), moments(lam, pl.tile, pl.hb, tile_points)))
+        got = float(np.dot(np.array(pl.p[:]), moments(lam, pl.tile, pl.hb, tile_points, km)))
         assert abs(got - want) <= 2e-11 * want, (span, got, want)
         # the error column: every served site carries the rounding floor
         np.testing.assert_allclose(np.sum(err), 50 * EPS * want, rtol=1e-12)
 
 
+@pytest.mark.parametrize("km", [32, 16])
 @pytest.mark.parametrize("span", EPOCHS)
-def test_served_sites_get_the_rounding_floor(span):
+def test_served_sites_get_the_rounding_floor(span, km):
     """Dense sweep of the served rate range, with extra points at the edges of the excluded window, at the class
     bound and at r_max: dqk21's estimate is exactly 50 eps resabs, dqagse accepts the first panel."""
     a, b = span
-    pl = plan(a, b)
-    edges = [pl.r_min, pl.r_max, pl.w_lo, pl.w_hi, CLASS_BOUND]
+    pl = plan(a, b, km=km)
+    edges = [pl.r_min, pl.r_max, pl.w_lo, pl.w_hi, BOUND[km]]
     near = np.concatenate([e * (1.0 + np.linspace(-3e-3, 3e-3, 601)) for e in edges if e > 0])
     C = 0.5 * (a + b)
     peak = np.linspace(0.9, 1.1, 4001) / (4.0 * C)             # sites whose PI curve peaks inside the epoch
-    lam = np.concatenate([np.geomspace(2.5e-16, CLASS_BOUND, 20000), near, peak,
+    lam = np.concatenate([np.geomspace(2.5e-16, BOUND[km], 20000), near, peak,
                           np.nextafter(pl.w_lo, 0.0, dtype=np.float64).reshape(1),
                           np.nextafter(pl.w_hi, 1.0, dtype=np.float64).reshape(1)])
     lam = np.unique(lam[served(pl, lam)])
@@ -94,15 +100,15 @@ def test_served_sites_get_the_rounding_floor(span):
 
 
 def test_window_sits_on_the_peak_and_is_narrow():
-    for (a, b) in EPOCHS:
-        pl = plan(a, b)
+    for (a, b), km in [(e, k) for e in EPOCHS for k in (32, 16)]:
+        pl = plan(a, b, km=km)
         C, h = 0.5 * (a + b), 0.5 * (b - a)
         if pl.w_lo <= pl.w_hi:
             # the window brackets the rate whose curve t e^{-4 r t} peaks at the epoch centre, if that rate is in range
             if 1.0 / (4 * C) < pl.r_max:
                 assert pl.w_lo < 1.0 / (4 * C) * (1 + (h / C) ** 2) and pl.w_hi > 1.0 / (4 * C)
             assert (pl.w_hi - pl.w_lo) <= 0.05 * pl.w_hi + 1e-300, (a, b, pl.w_lo, pl.w_hi)
-        assert pl.r_max <= CLASS_BOUND and pl.r_max * 4 * h <= 1.0 + 1e-12
+        assert pl.r_max <= BOUND[km] and pl.r_max * 4 * h <= 1.0 + 1e-12
 
 
 @pytest.mark.parametrize("span,n_tiles,why", [
@@ -117,13 +123,13 @@ def test_ineligible_epochs(span, n_tiles, why):
 
 def test_truncation_at_the_corner_of_the_range():
     """Largest remainder: a site at r_max of an epoch whose centre sits at the edge of its block."""
-    for (a, b) in [(120, 136), (0, 64), (250, 262), (1, 127)]:
-        pl = plan(a, b)
+    for (a, b), km in [(e, k) for e in [(120, 136), (0, 64), (250, 262), (1, 127)] for k in (32, 16)]:
+        pl = plan(a, b, km=km)
         if not pl.eligible:
             continue
         r = np.nextafter(pl.r_max, 0.0)
         if not served(pl, np.array([r]))[0]:
             continue
         integ, _, last = capi.epoch_sites(np.array([r]), a, b)
-        got = float(np.dot(np.array(pl.p[:]), moments(np.array([r]), pl.tile, pl.hb, 1024)))
+        got = float(np.dot(np.array(pl.p[:]), moments(np.array([r]), pl.tile, pl.hb, 1024, km)))
         assert last[0] == 1 and abs(got - integ[0]) <= 5e-11 * integ[0], (a, b, r, got, integ[0])
