@@ -44,6 +44,12 @@ extern "C" {
 
 /* tapir_problem.flags */
 #define TAPIR_WANT_PROFILE 1u /* copy pi_net[L*T] back to the host (it is always computed) */
+/* FP32 mode (BASELINE: "FP64, or FP32 with compensated summation ... <= 1e-5 in FP32 mode"): the PI profile is summed in
+ * single precision by profile_f32_kernel (per-lane partial sums closed by a reduction tree) and the epoch sums of the
+ * slow sites are taken from its FP32 moments; outputs stay float64 arrays, accurate to ~1e-6 relative (gate 1e-5).
+ * Per-site integrals (fast sites, rate statistics) and everything else stay FP64.  Also switched on for every call of a
+ * context created with TAPIR_FP32_MODE=1 in the environment. */
+#define TAPIR_FP32_MODE 2u
 
 #define TAPIR_MAX_EPOCHS 64
 #define TAPIR_MAX_TIMES 4096
@@ -85,11 +91,13 @@ typedef struct tapir_timing {
     float quad_ms;     /* GK21/QAGS epoch-integral kernel(s) */
     float finalize_ms; /* per-locus reduction / picks / maxima kernel */
     int32_t launches;  /* kernel launches issued */
-    /* what was launched for the profile: points per time tile (256 .. 2048), 1 = profile_mom_kernel (moment form) /
-     * 0 = profile_kernel (direct form), and how many of the batch's epochs took their sums from the moments */
+    /* what was launched for the profile: points per time tile (256 .. 2048), the moment form's moments per block
+     * (0 = profile_kernel, direct form), and how many of the batch's epochs took their sums from the moments */
     int32_t profile_tile_points;
-    int32_t profile_moment_form;
+    int32_t profile_moment_form; /* 0, or the number of moments per 128-point block (32 or 16) */
     int32_t moment_epochs;
+    int32_t profile_fp32;        /* 1: profile_f32_kernel ran (TAPIR_FP32_MODE) */
+    int32_t reserved;
 } tapir_timing;
 
 int tapir_cuda_version(void);
@@ -162,7 +170,8 @@ int tapir_cuda_site_integrals(tapir_cuda_ctx *ctx, double a, double b, const dou
  * slowly decaying sites of scipy.integrate.quad's value (tapir/compute.py:50-52, 81-94) is taken as
  * sum_j p[j] M[j][hb] from the n_moments (32 or 16) moments of block hb of tile `tile` (block centre tb); only sites
  * with r_min <= rate <= r_max outside [w_lo, w_hi] (and below the moment class bound, 0.01953125 for 32 moments,
- * 0.0048828125 for 16) are served that way. */
+ * 0.0048828125 for 16) are served that way.  class_x = 0 selects that FP64 class; class_x = 2.5 with 16 moments is the
+ * FP32 mode's (bound 0.009765625). */
 typedef struct tapir_mom_epoch {
     int32_t eligible;
     int32_t tile, hb;
@@ -171,7 +180,8 @@ typedef struct tapir_mom_epoch {
     double r_min, r_max;
     double w_lo, w_hi;
 } tapir_mom_epoch;
-int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, int32_t n_moments, tapir_mom_epoch *out);
+int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, int32_t n_moments, double class_x,
+                         tapir_mom_epoch *out);
 
 /* --- batched rate ingest (host only, no device needed): parse_site_rates' read half (compute.py:30-39) for
  * n_files HyPhy site-rate JSON files on n_threads threads into one CSR pack.  offsets[n_files + 1] is always

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libtapir_cuda.so")
 TAPIR_OK = 0
 TAPIR_E_INVALID, TAPIR_E_CUDA, TAPIR_E_NOMEM, TAPIR_E_STATE = -1, -2, -3, -4
 WANT_PROFILE = 1
+FP32_MODE = 2
 MAX_EPOCHS = 64
 MAX_TIMES = 4096
 
@@ -50,6 +51,8 @@ class Timing(ctypes.Structure):
         ("profile_tile_points", ctypes.c_int32),
         ("profile_moment_form", ctypes.c_int32),
         ("moment_epochs", ctypes.c_int32),
+        ("profile_fp32", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -94,7 +97,7 @@ SYMBOLS = {
     "tapir_cuda_pi_matrix": (ctypes.c_int, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "tapir_cuda_nansum_rows": (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "tapir_cuda_site_integrals": (ctypes.c_int, [_vp, _dbl, _dbl, _vp, _i64, _vp, _vp, _vp]),
-    "tapir_mom_epoch_plan": (ctypes.c_int, [_dbl, _dbl, _i64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(MomEpoch)]),
+    "tapir_mom_epoch_plan": (ctypes.c_int, [_dbl, _dbl, _i64, ctypes.c_int32, ctypes.c_int32, _dbl, ctypes.POINTER(MomEpoch)]),
     "tapir_ingest_rates": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), _i64, ctypes.c_int, _dbl, _vp, _vp, _i64,
                                           ctypes.POINTER(_i64)]),
     "tapir_ingest_open": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), _i64, ctypes.c_int, ctypes.POINTER(_vp), _vp,

@@ -472,9 +472,10 @@ __device__ __forceinline__ void prof_build_tables(double lam, bool ok, int64_t T
     }
 }
 
-// acc(lo,hi) += sum_s U[s][lo] * W[s][hi] over nk k-steps of 4 sites
+// acc(lo,hi) += sum_s U[s][lo] * W[s][hi] over nk k-steps of 4 sites; `last` = last k-step the tables hold (the
+// look-ahead fetch is clamped to it: the tables may end where the warp's shared memory ends)
 template <int RH>
-__device__ __forceinline__ void prof_contract(double (&acc)[4][RH][2], const double* fragU, const double* fragW, int nk)
+__device__ __forceinline__ void prof_contract(double (&acc)[4][RH][2], const double* fragU, const double* fragW, int nk, int last)
 {
     constexpr int WS = ProfCfg<RH>::WStride, US = kUStride;
     auto fetch = [&](double (&a)[4], double (&b)[RH], int step) {
@@ -502,9 +503,9 @@ __device__ __forceinline__ void prof_contract(double (&acc)[4][RH][2], const dou
     double a0[4], b0[RH], a1[4], b1[RH];
     fetch(a0, b0, 0);
     for (int s = 0; s < nk; s += 2) {
-        fetch(a1, b1, s + 1);
+        fetch(a1, b1, min(s + 1, last));
         mma_step(a0, b0);
-        fetch(a0, b0, min(s + 2, 7));
+        fetch(a0, b0, min(s + 2, last));
         mma_step(a1, b1);
     }
 }
@@ -929,7 +930,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                 const int cnt = min(16, n_fast - g0);
                 if (lane < 16) prof_build_tables<RH>((lane < cnt) ? Fs[g0 + lane] : 0.0, lane < cnt, T0, t0d, myU, myW);
                 __syncwarp();
-                prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2);
+                prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
                 __syncwarp();
             }
         } else if (n_fast > 32) {
@@ -958,7 +959,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                     __syncwarp();
                     if (lane < 16) prof_build_tables<RH>(lam, lane < cnt, T0, t0d, myU, myW);
                     __syncwarp();
-                    prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2);
+                    prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
                     __syncwarp();
                 }
                 if (!more) break;
@@ -974,6 +975,227 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
     }
     if constexpr (TRACE) {
         if (lane == 0) { tr[12] = clock64(); tr[13] = n_done; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// PI profile, FP32 mode (TAPIR_FP32_MODE; BASELINE: "FP32 with compensated summation ... <= 1e-5 in FP32 mode")
+// ------------------------------------------------------------------------------------------
+// The moment form again, in single precision and without any shared-memory tables: lane = site.  A slow site
+// (64 c <= 2.5, rate < 0.009765625: 16 Taylor moments per 128-point block leave a remainder of 1.3e-6, inside this mode's
+// 1e-5 gate) forms its 16 moments u0 z^k and its 8 block weights q^(128 hb + 64) in registers and adds their outer
+// product to 128 per-lane accumulators -- 128 independent FFMAs per site on the FP32 pipe (128 lanes per SM and clock
+// against the FP64 pipe's 64), no tensor-core fragment layout to feed.  Summation: every lane sums its own sites
+// (a 32nd of the locus) and a shuffle transpose-reduction tree closes the 128 sums over the lanes, so the error grows
+// with log2(32) + S/32 additions, not with S (the "compensated summation" the north star asks of an FP32 mode; measured
+// error ~1e-6).  The moments go back to times by a 16-term Horner evaluation per grid point (lane = grid point), faster
+// sites are added as they are met by the direct power form a q^(T0 + lane) (q^32)^j on the same 32 per-lane outputs, and
+// the epilogue is the FP64 kernels' (values leave as float64, times t, tile maximum).  The epoch sums of the slow
+// sites are the same linear functional of the moments (mom_epoch.h with 16 terms and the class bound 2.5), evaluated
+// in double on the FP32 moments.  One-warp CTAs, 1,024-point tiles only.
+constexpr int kF32Terms = 16;
+constexpr uint32_t kF32BoundHi = 0x3F840000u;  // high word of 0.009765625 = 2.5 / 256
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// sum over the 32 lanes of v[lane'] for every lane' at once: lane L returns the total of element L (31 shuffles)
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int n = 16; n >= 1; n >>= 1) {
+        const bool up = (lane & n) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = up ? v[i] : v[i + n];
+            const float keep = up ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(32, 8) profile_f32_kernel(const ProfArgs args)
+{
+    constexpr int TT = 1024, NB = 8, KM = kF32Terms;
+    __shared__ __align__(16) double s_q[64];     // compaction queue of the slow rates
+    __shared__ __align__(16) float s_m[NB * KM]; // moments [hb][k]
+    const int lane = threadIdx.x & 31;
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    for (;;) {
+        uint32_t it = 0;
+        if (lane == 0) it = atomicAdd(args.counter, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= uint32_t(args.n_items)) break;
+        const ProfItem item = args.items[it];
+        const int64_t T0 = int64_t(item.tile) * TT;
+        const double t0d = double(T0);
+        const double* rp = args.rates + item.site_begin;
+
+        float acc[KM][NB];   // per-lane sums of m_k w_hb over this lane's slow sites
+        float o[32];         // outputs of this lane: grid point T0 + 32 j + lane, value / t
+#pragma unroll
+        for (int k = 0; k < KM; ++k)
+#pragma unroll
+            for (int hb = 0; hb < NB; ++hb) acc[k][hb] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = 0.0f;
+
+        int qh = 0, qn = 0;
+        constexpr int kAhead = 4;
+        double lam_q[kAhead];
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) lam_q[k] = (32 * k + lane < item.n_sites) ? __ldg(rp + 32 * k + lane) : 0.0;
+        for (int base = 0;; base += 32) {
+            const bool more = base < item.n_sites;
+            if (more) {
+                const double lam_new = lam_q[0];
+#pragma unroll
+                for (int k = 0; k + 1 < kAhead; ++k) lam_q[k] = lam_q[k + 1];
+                {
+                    const int nb = base + 32 * kAhead + lane;
+                    lam_q[kAhead - 1] = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                }
+                const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
+                const bool slow = act && rate_is_slow(lam_new, kF32BoundHi);
+                const unsigned ballot = __ballot_sync(0xffffffffu, slow);
+                unsigned bfast = __ballot_sync(0xffffffffu, act && !slow);
+                if (slow) s_q[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                qn += __popc(ballot);
+                // faster sites, one at a time for the whole warp: lane = offset inside a 32-point run,
+                // a q^t = [a q^(T0 + lane)] (q^32)^j
+                while (bfast) {
+                    const int src = __ffs(bfast) - 1;
+                    bfast &= bfast - 1;
+                    // (clamped: 16 r^2 and r t stay finite in single precision; such a site is 0 from t = 1 on either way)
+                    const float lamf = fminf(fmaxf(float(__shfl_sync(0xffffffffu, lam_new, src)), -1.0e18f), 1.0e18f);
+                    const float l2q = -4.0f * lamf * kLog2e;              // log2 q (negative rates: growth, as the reference)
+                    const float a = fminf(16.0f * lamf * lamf, 3.0e38f);  // (a huge rate: q^t is 0 from t = 1 on, a 0 = 0)
+                    const float ulo = a * ex2_approx(l2q * float(T0 + lane));
+                    const float qB = ex2_approx(32.0f * l2q);
+                    float w = 1.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        o[j] = fmaf(ulo, w, o[j]);
+                        w *= qB;
+                    }
+                }
+                __syncwarp();
+            }
+            while (qn - qh >= 32 || (!more && qn > qh)) {
+                const int cnt = min(32, qn - qh);
+                const double lam = (lane < cnt) ? s_q[(qh + lane) & 63] : 0.0;
+                qh += cnt;
+                __syncwarp();
+                const float lamf = float(lam);                     // 0 for the lanes past cnt: every moment is 0
+                const float c = 4.0f * lamf;
+                float u0 = 16.0f * lamf * lamf;
+                if (T0 != 0) {
+                    // e^{-c T0}: the exponent is formed and reduced in double (c T0 reaches hundreds), 2^frac in single
+                    const double arg = -(4.0 * lam) * t0d * 1.4426950408889634;
+                    const double kd = rint(arg);
+                    u0 = ldexpf(u0 * ex2_approx(float(arg - kd)), int(fmax(kd, -300.0)));
+                }
+                const float z = -64.0f * c;
+                const float q64 = ex2_approx(z * kLog2e), q128 = q64 * q64;
+                float m[KM];
+                m[0] = u0;
+#pragma unroll
+                for (int k = 1; k < KM; ++k) m[k] = m[k - 1] * z;
+                float w = q64;
+#pragma unroll
+                for (int hb = 0; hb < NB; ++hb) {
+#pragma unroll
+                    for (int k = 0; k < KM; ++k) acc[k][hb] = fmaf(m[k], w, acc[k][hb]);
+                    w *= q128;
+                }
+            }
+            if (!more) break;
+        }
+
+        // ---- close the 128 sums over the lanes: lane L of block b ends with M[4 b + (L >> 3)][L & 7] ----
+#pragma unroll
+        for (int b = 0; b < KM * NB / 32; ++b) {
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = acc[4 * b + (i >> 3)][i & 7];
+            const float total = transpose_reduce32(v, lane);
+            s_m[(lane & 7) * KM + 4 * b + (lane >> 3)] = total;
+        }
+        __syncwarp();
+        // ---- epoch integrals of the slow sites from the moments (mom_epoch.h), in double ----
+        for (int me = 0; me < args.n_mom_epochs; ++me) {
+            const MomEpochDev ep = args.mom_epochs[me];
+            if (ep.tile != item.tile) continue;
+            double v = (lane < KM) ? __ldg(args.mom_p + 32 * ep.col + lane) * double(s_m[ep.hb * KM + lane]) : 0.0;
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0) args.mom_int[size_t(item.part) * args.e_total + ep.col] = v;
+        }
+        __syncwarp();
+        // 1/k! onto the moments
+#pragma unroll
+        for (int j = 0; j < KM * NB / 32; ++j) {
+            const int i = lane + 32 * j;
+            s_m[i] *= float(c_inv_fact[i & (KM - 1)]);
+        }
+        __syncwarp();
+        // ---- moments -> times: lane = grid point, 16-term Horner per point ----
+#pragma unroll
+        for (int hb = 0; hb < NB; ++hb) {
+            float cf[KM];
+#pragma unroll
+            for (int q = 0; q < KM / 4; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4*>(s_m + hb * KM + 4 * q);
+                cf[4 * q] = t4.x; cf[4 * q + 1] = t4.y; cf[4 * q + 2] = t4.z; cf[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float x = float(32 * r + lane - 64) * 0.015625f;
+                float pv = cf[KM - 1];
+#pragma unroll
+                for (int k = KM - 2; k >= 0; --k) pv = fmaf(pv, x, cf[k]);
+                o[4 * hb + r] += pv;
+            }
+        }
+        __syncwarp();
+
+        // ---- epilogue: float64 values times t, tile maximum (first maximum, as numpy.argmax), or the split workspace ----
+        if (item.slot >= 0) {
+            double* out = args.ws + size_t(item.slot) * TT;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[32 * j + lane] = double(o[j]);
+        } else {
+            double* out = args.pi_net + int64_t(item.locus) * args.T;
+            long long best_bits = -1;
+            int64_t best_t = T0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int64_t t = T0 + 32 * j + lane;
+                if (t < args.T) {
+                    const double v = double(o[j]) * double(t);
+                    out[t] = v;
+                    const long long bits = __double_as_longlong(v);
+                    if (bits > best_bits) { best_bits = bits; best_t = t; }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const long long ob = __shfl_xor_sync(0xffffffffu, best_bits, off);
+                const int64_t ot = __shfl_xor_sync(0xffffffffu, best_t, off);
+                if (ob > best_bits || (ob == best_bits && ot < best_t)) { best_bits = ob; best_t = ot; }
+            }
+            if (lane == 0) {
+                const int64_t k = int64_t(item.locus) * args.n_tiles + item.tile;
+                args.tile_max[k] = __longlong_as_double(best_bits);
+                args.tile_arg[k] = best_t;
+            }
+        }
     }
 }
 

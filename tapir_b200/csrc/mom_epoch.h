@@ -84,8 +84,14 @@ inline long double S(long double c, long double C, long double h)
 }
 }  // namespace momdetail
 
-// Plan of the epoch [a, b] on a grid of n_tiles tiles of TT points (TT a multiple of 128) for the class of km moments.
-inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, int km, MomEpochPlan* out)
+// FP32 mode (profile_f32_kernel): 16 moments with the class 64 c <= 2.5 (rate < 0.009765625) -- remainder 1.3e-6, inside
+// that mode's 1e-5 gate.
+constexpr double kMomClassF32 = 2.5;
+inline uint32_t mom_rate_bound_hi_x(double x) { return x == 2.5 ? 0x3F840000u : (x == 1.25 ? 0x3F740000u : 0x3F940000u); }
+
+// Plan of the epoch [a, b] on a grid of n_tiles tiles of TT points (TT a multiple of 128) for the class of km moments
+// with 64 c <= class_x (0: the FP64 class of km, mom_class_x).
+inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, int km, MomEpochPlan* out, double class_x = 0.0)
 {
     using namespace momdetail;
     std::memset(out, 0, sizeof *out);
@@ -101,8 +107,8 @@ inline void mom_epoch_plan(double a, double b, int64_t n_tiles, int TT, int km, 
     const int nb = TT / 128;
     const long double tb = 128.0L * gb + 64.0L, d = C - tb;
     // ---- rate range ----
-    const long double xk = mom_class_x(km);
-    long double r_max = mom_rate_bound(km);                   // class bound (exclusive; applied by the class test)
+    const long double xk = class_x > 0.0 ? class_x : mom_class_x(km);
+    long double r_max = xk / 256.0L;                          // class bound (exclusive; applied by the class test)
     r_max = fminl(r_max, 1.0L / (4.0L * h));                  // y = c h <= 1
     r_max = fminl(r_max, xk / (4.0L * (fabsl(d) + h)));       // series remainder as for the profile: (|d| + h) c <= x(km)
     r_max = fminl(r_max, 150.0L / (long double)b);            // c b <= 600: every exponential stays a normal number

@@ -93,6 +93,7 @@ struct Plan {
     int rh = 4;       // profile kernel variant
     bool mom_form = false;  // profile_mom_kernel<rh> (moment form) instead of profile_kernel<rh>
     int mom_terms = 32;     // moments per 128-point block of the moment form (32 or 16, see choose_moments)
+    bool fp32 = false;      // TAPIR_FP32_MODE: profile_f32_kernel (16 moments, class 64 c <= 2.5, 1,024-point tiles)
     int32_t TT = 1024, n_tiles = 1;
     int64_t n_prof_items = 0, n_quad_items = 0, ws_rows = 0, n_parts = 0;
     std::vector<EpochBatch> batches;
@@ -153,9 +154,11 @@ struct tapir_cuda_ctx {
     // per-device launch configuration, filled once in tapir_cuda_create (index: log2(RH))
     int prof_per_sm[4] = {0, 0, 0, 0}, mom_per_sm[4] = {0, 0, 0, 0}, mom16_per_sm[4] = {0, 0, 0, 0};
     int force_terms = 0;                       // TAPIR_MOM_TERMS = 16 / 32
+    int force_fp32 = 0;                        // TAPIR_FP32_MODE=1 in the environment: every batch of this context
+    int f32_per_sm = 0;
     // plans of the moment-functional epochs seen so far (they depend on the epoch and the tile geometry only; a
     // chunked run would otherwise recompute them for every chunk)
-    struct MomCacheEntry { double a, b; int64_t n_tiles; int32_t TT, km; MomEpochPlan plan; };
+    struct MomCacheEntry { double a, b; int64_t n_tiles; int32_t TT, km; double class_x; MomEpochPlan plan; };
     std::vector<MomCacheEntry> mom_cache;
     int prof_ctas_cap = 0, quad_ctas_cap = 0;  // TAPIR_PROF_CTAS_PER_SM / TAPIR_QUAD_CTAS_PER_SM (co-residency experiments)
     int force_rh = 0;                          // TAPIR_CUDA_RH
@@ -321,10 +324,12 @@ void choose_tile(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t T, d
 }
 
 // Moments per 128-point block for the moment form: 32 (class 64 c <= 5) or 16 (class 64 c <= 1.25: half the work per
-// slow site and per item, but every site between the two bounds goes through the power-table pass of the fast
-// sites).  Decided per batch from a strided sample of its rates -- expected FP64-pipe cycles per item, the fast groups
-// weighted by what their exposed latency costs (profiles/r02_moments_sweep.txt).
-int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0, int64_t l1, int rh)
+// slow site and per item, but every site between the two bounds goes through the power-table pass of the fast sites,
+// and through quad_kernel for its epoch integrals).  Decided per batch from a strided sample of its rates: expected
+// FP64-pipe cycles per (locus, tile) item -- the fast groups weighted 2.5x for their exposed latency -- plus what the
+// per-site integrals cost, in the same unit (23 ps per site of a 256-site block that holds such a site, 1.4 ps per
+// cycle: profiles/r02_moments_sweep.txt, where the model's 16/32 ratio is 0.77 against a measured 0.77 on config 5).
+int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0, int64_t l1, int rh, int n_tiles)
 {
     if (ctx->force_terms) return ctx->force_terms;
     const int64_t s0 = p->offsets[l0], s1 = p->offsets[l1];
@@ -342,16 +347,19 @@ int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0
         if (!(r >= 0.0 && r < mom_rate_bound(32))) ++n_ge32;
     }
     if (n_act == 0) return 32;
-    const double per_item = double(nnz) / double(L) * double(n_act) / double(n_sample);   // active sites per item
+    const double sites = double(nnz) / double(L);                              // sites per locus
+    const double per_item = sites * double(n_act) / double(n_sample);         // of them with a non-zero finite rate
     const int NT = rh / 4, NB = 8 * NT;
-    auto cost = [&](int km, double frac_fast) {
-        const double n_fast = per_item * frac_fast, n_slow = per_item - n_fast;
-        const double groups16 = std::ceil((n_fast + std::sqrt(n_fast)) / 16.0);
+    auto cost = [&](int km, int64_t n_ge) {
+        const double n_fast = per_item * double(n_ge) / double(n_act), n_slow = per_item - n_fast;
+        const double groups16 = std::max(1.0 - std::exp(-n_fast), (n_fast + std::sqrt(n_fast)) / 16.0);
         const double fast = groups16 * 2.5 * (256.0 * rh + 220.0) * (n_fast > 24.0 ? 1.2 : 1.0);
-        return n_slow * (0.5 * km * NT + (33.0 + km + NB) / 16.0) + 64.0 * km * NT + fast;
+        const double profile = n_slow * (0.5 * km * NT + (33.0 + km + NB) / 16.0) + 64.0 * km * NT + fast;
+        const double p_block = 1.0 - std::pow(1.0 - double(n_ge) / double(n_sample), 256.0);   // a quad item holds such a site
+        const double quad = p->n_epochs > 0 ? 16.4 * p_block * sites : 0.0;
+        return double(n_tiles) * profile + quad;
     };
-    const double c16 = cost(16, double(n_ge16) / double(n_act)), c32 = cost(32, double(n_ge32) / double(n_act));
-    return c16 < c32 ? 16 : 32;
+    return cost(16, n_ge16) < cost(32, n_ge32) ? 16 : 32;
 }
 
 void fill_batches(Plan& plan, const double* epoch_ab)
@@ -392,7 +400,7 @@ void fill_batches(Plan& plan, const double* epoch_ab)
                 eb.n_win = 0;
                 eb.scan_lo = 0u;
                 eb.mom_terms = plan.mom_terms;
-                eb.class_hi = mom_rate_bound_hi(plan.mom_terms);
+                eb.class_hi = plan.fp32 ? mom_rate_bound_hi_x(kMomClassF32) : mom_rate_bound_hi(plan.mom_terms);
                 eb.scan_hi = eb.class_hi;
             }
             if (!(size_t(e) < plan.mom.size() && plan.mom[e].eligible)) eb.mom_all = 0;
@@ -526,6 +534,7 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
         if ((env = getenv("TAPIR_MOM_INT"))) ctx->mom_int = atoi(env) != 0;
         if ((env = getenv("TAPIR_PROF_CTAS_PER_SM"))) ctx->prof_ctas_cap = atoi(env);
         if ((env = getenv("TAPIR_QUAD_CTAS_PER_SM"))) ctx->quad_ctas_cap = atoi(env);
+        if ((env = getenv("TAPIR_FP32_MODE"))) ctx->force_fp32 = atoi(env) != 0;
         if ((env = getenv("TAPIR_MOM_TERMS"))) {
             const int v = atoi(env);
             if (v == 16 || v == 32) ctx->force_terms = v;
@@ -547,6 +556,7 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
     if (e == cudaSuccess) e = configure_profile<2>(ctx, 1);
     if (e == cudaSuccess) e = configure_profile<4>(ctx, 2);
     if (e == cudaSuccess) e = configure_profile<8>(ctx, 3);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->f32_per_sm, profile_f32_kernel, 32, 0);
     for (Lane& ln : ctx->lanes) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ln.stream_q, cudaStreamNonBlocking);
@@ -657,12 +667,19 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     plan.flags = p->flags;
     plan.nnz = plan.L ? off[plan.L] - base : 0;
     choose_tile(ctx, p, std::max<int64_t>(plan.T, 1), plan.L ? double(plan.nnz) / double(plan.L) : 1.0, plan.rh, plan.mom_form);
+    plan.fp32 = ((p->flags & TAPIR_FP32_MODE) || ctx->force_fp32) && plan.T > 0 && plan.L > 0 && !ctx->prof_trace;
+    if (plan.fp32) {   // profile_f32_kernel: 1,024-point tiles, moment form
+        plan.rh = 4;
+        plan.mom_form = true;
+    }
     plan.TT = 32 * 8 * plan.rh;
     plan.n_tiles = int32_t(std::max<int64_t>(1, (plan.T + plan.TT - 1) / plan.TT));
     // epochs whose sums come out of the profile's moments (mom_epoch.h); the others, and the sites outside an
     // epoch's rate range, are integrated per site by quad_kernel
-    plan.mom_terms = plan.mom_form ? choose_moments(ctx, p, l0, l1, plan.rh) : 32;
+    plan.mom_terms = plan.mom_form ? choose_moments(ctx, p, l0, l1, plan.rh, plan.n_tiles) : 32;
     if (ctx->prof_trace) plan.mom_terms = 32;   // (the trace instantiation exists for 32 moments only)
+    if (plan.fp32) plan.mom_terms = kF32Terms;
+    const double class_x = plan.fp32 ? kMomClassF32 : mom_class_x(plan.mom_terms);
     plan.mom.assign(size_t(plan.E), MomEpochPlan());
     plan.n_mom = 0;
     plan.mom_mask = 0;
@@ -671,11 +688,12 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
             const double ea = p->epoch_ab[2 * e], eb_ = p->epoch_ab[2 * e + 1];
             const tapir_cuda_ctx::MomCacheEntry* hit = nullptr;
             for (const auto& ce : ctx->mom_cache)
-                if (ce.a == ea && ce.b == eb_ && ce.n_tiles == plan.n_tiles && ce.TT == plan.TT && ce.km == plan.mom_terms) { hit = &ce; break; }
+                if (ce.a == ea && ce.b == eb_ && ce.n_tiles == plan.n_tiles && ce.TT == plan.TT && ce.km == plan.mom_terms &&
+                    ce.class_x == class_x) { hit = &ce; break; }
             if (!hit) {
                 if (ctx->mom_cache.size() >= 4096) ctx->mom_cache.clear();
-                tapir_cuda_ctx::MomCacheEntry ce{ea, eb_, plan.n_tiles, plan.TT, plan.mom_terms, MomEpochPlan()};
-                mom_epoch_plan(ea, eb_, plan.n_tiles, plan.TT, plan.mom_terms, &ce.plan);
+                tapir_cuda_ctx::MomCacheEntry ce{ea, eb_, plan.n_tiles, plan.TT, plan.mom_terms, class_x, MomEpochPlan()};
+                mom_epoch_plan(ea, eb_, plan.n_tiles, plan.TT, plan.mom_terms, &ce.plan, class_x);
                 ctx->mom_cache.push_back(ce);
                 hit = &ctx->mom_cache.back();
             }
@@ -877,6 +895,11 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
             pa.n_mom_epochs = plan.mom_form ? plan.n_mom : 0;
             pa.e_total = plan.E;
             cudaError_t e = cudaSuccess;
+            if (plan.fp32) {
+                const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(plan.n_prof_items, int64_t(ctx->sm_count) * std::max(1, ctx->f32_per_sm)));
+                profile_f32_kernel<<<unsigned(grid), 32, 0, st>>>(pa);
+                e = cudaGetLastError();
+            } else
             switch (plan.rh) {
                 case 1: e = launch_profile<1>(ctx, ln, pa, plan.n_prof_items, false, 32); break;
                 case 2: e = launch_profile<2>(ctx, ln, pa, plan.n_prof_items, false, 32); break;
@@ -1053,6 +1076,7 @@ int lane_compute(tapir_cuda_ctx* ctx, Lane& ln, tapir_timing* timing, bool sync,
         timing->profile_tile_points = plan.TT;
         timing->profile_moment_form = plan.mom_form ? plan.mom_terms : 0;
         timing->moment_epochs = plan.mom_form ? plan.n_mom : 0;
+        timing->profile_fp32 = plan.fp32 ? 1 : 0;
     }
     return TAPIR_OK;
 }
@@ -1486,13 +1510,15 @@ int tapir_cuda_fp64_peak(tapir_cuda_ctx* ctx, double* tflops, float* ms_out)
     return TAPIR_OK;
 }
 
-int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, int32_t n_moments, tapir_mom_epoch* out)
+int tapir_mom_epoch_plan(double a, double b, int64_t n_tiles, int32_t tile_points, int32_t n_moments, double class_x,
+                         tapir_mom_epoch* out)
 {
     static_assert(sizeof(tapir_mom_epoch) == sizeof(MomEpochPlan), "public and internal plan structs agree");
     if (!out || n_tiles < 1 || tile_points < 1024 || tile_points % 1024 || (n_moments != 16 && n_moments != 32))
         return fail(nullptr, TAPIR_E_INVALID, "bad plan geometry");
     MomEpochPlan mp;
-    mom_epoch_plan(a, b, n_tiles, tile_points, n_moments, &mp);
+    if (!(class_x == 0.0 || class_x == 1.25 || class_x == 2.5 || class_x == 5.0)) return fail(nullptr, TAPIR_E_INVALID, "class_x is 0, 1.25, 2.5 or 5");
+    mom_epoch_plan(a, b, n_tiles, tile_points, n_moments, &mp, class_x);
     memcpy(out, &mp, sizeof mp);
     return TAPIR_OK;
 }

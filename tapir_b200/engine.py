@@ -164,9 +164,10 @@ class Engine:
 
     # ---- whole path, host buffers in / host buffers out ----
     def run(self, offsets, rates, n_grid, times, epochs, want_profile=True, flags=0, out: BatchResult = None,
-            pinned_results=False):
-        """H2D + kernels + D2H for one CSR batch.  Raises TapirCudaError on any failure."""
-        p, keep = self._prep(offsets, rates, n_grid, times, epochs, want_profile, flags)
+            pinned_results=False, fp32=False):
+        """H2D + kernels + D2H for one CSR batch.  Raises TapirCudaError on any failure.
+        fp32: TAPIR_FP32_MODE -- the profile (and the slow sites' epoch sums) in single precision, ~1e-6 relative."""
+        p, keep = self._prep(offsets, rates, n_grid, times, epochs, want_profile, flags | (_lib.FP32_MODE if fp32 else 0))
         if out is None:
             res, r = self._alloc_results(p.n_loci, p.n_grid, p.n_times, p.n_epochs, want_profile, pinned_results)
         else:
@@ -179,8 +180,8 @@ class Engine:
         return res
 
     # ---- staged path ----
-    def upload(self, offsets, rates, n_grid, times, epochs, want_profile=True, flags=0):
-        p, keep = self._prep(offsets, rates, n_grid, times, epochs, want_profile, flags)
+    def upload(self, offsets, rates, n_grid, times, epochs, want_profile=True, flags=0, fp32=False):
+        p, keep = self._prep(offsets, rates, n_grid, times, epochs, want_profile, flags | (_lib.FP32_MODE if fp32 else 0))
         check(self._lib.tapir_cuda_upload(self._ctx, ctypes.byref(p)), self._ctx)
         self._resident = (p.n_loci, p.n_grid, p.n_times, p.n_epochs, want_profile)
         del keep

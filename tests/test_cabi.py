@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     from tapir_b200 import _lib
     assert ctypes.sizeof(_lib.Problem) == 72
     assert ctypes.sizeof(_lib.Results) == 80
-    assert ctypes.sizeof(_lib.Timing) == 32
+    assert ctypes.sizeof(_lib.Timing) == 40
     assert ctypes.sizeof(_lib.MomEpoch) == 312
 
 

@@ -540,7 +540,7 @@ def _mom_plan(a, b, n_tiles, tile_points, km=32):
     import ctypes
     from tapir_b200 import _lib
     out = _lib.MomEpoch()
-    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, km, ctypes.byref(out)))
+    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, km, 0.0, ctypes.byref(out)))
     return out
 
 
@@ -655,3 +655,77 @@ def test_every_profile_kernel_variant(monkeypatch, rh, mom):
     assert rel(res.pi_net, pi_net) < RTOL and rel(res.integral, si) < RTOL
     np.testing.assert_allclose(res.abserr, se, rtol=ERR_RTOL, atol=1e-300)
     assert np.array_equal(res.argmax_t, np.argmax(pi_net, axis=1)) and np.array_equal(res.argmax_epoch, np.argmax(si, axis=1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FP32 mode (TAPIR_FP32_MODE): BASELINE's gate is 1e-5 relative for the profile and the integrals, identical argmax epoch
+# ---------------------------------------------------------------------------------------------------------------
+F32_RTOL = 1e-5
+
+
+def test_fp32_mode_goldens(eng, golden):
+    g, meta = golden
+    rates = g["cfg1/rates"]
+    off = np.array([0, rates.size], dtype=np.int64)
+    eng.upload(off, rates, 174, meta["times"], meta["epochs"], fp32=True)
+    tm = eng.compute()
+    assert tm.profile_fp32 == 1 and tm.profile_tile_points == 1024 and tm.profile_moment_form == 16
+    res = eng.download()
+    assert rel(res.pi_net[0], g["cfg1/pi_net"]) < F32_RTOL
+    assert rel(res.integral[0], g["cfg1/integral"]) < F32_RTOL
+    assert res.argmax_epoch[0] == 3 and res.n_finite[0] == 100
+    for tag in ("synA", "synB"):
+        off, rates, T = g[tag + "/offsets"], g[tag + "/rates"], int(g[tag + "/T"])
+        res = eng.run(off, rates, T, g[tag + "/times"], g[tag + "/epochs"], fp32=True)
+        assert rel(res.pi_net, g[tag + "/pi_net"], floor=1e-30) < F32_RTOL, tag
+        assert rel(res.integral, g[tag + "/integral"], floor=1e-30) < F32_RTOL, tag
+        assert np.array_equal(res.argmax_epoch, np.argmax(g[tag + "/integral"], axis=1))
+        np.testing.assert_allclose(res.mean_rate, g[tag + "/mean_rate"], rtol=1e-12)      # statistics stay FP64
+
+
+@pytest.mark.parametrize("T", [7, 300, 1000, 1025, 2500, 5000])
+def test_fp32_mode_vs_oracle(eng, T):
+    """Every site class of the FP32 kernel (slow below 0.009765625, faster, zero, culled), one and several 1,024-point
+    tiles, ragged loci; values far below the single-precision range (< 1e-30 of the row maximum) are outside the gate."""
+    from oracle import capi
+    from tapir_b200 import synthetic
+    from tapir_b200.engine import pack_csr
+    rng = np.random.default_rng(500 + T)
+    loci = [synthetic.uce_rates(rng, n, max(T, 50), nan_frac=0.05) for n in (1, 31, 32, 33, 257, 700)]
+    loci.append(rng.uniform(0.0, 0.5, size=90))                       # faster sites only
+    loci.append(rng.uniform(0.0090, 0.0105, size=300))                # straddling the class bound
+    off, rates = pack_csr(loci, pinned=False)
+    epochs = [[0, 10], [3, 40], [32, 42], [164, 174]]
+    times = [0, T - 1, T // 2]
+    res = eng.run(off, rates, T, times, epochs, fp32=True)
+    pi_net, si, se = capi.batch(off, rates, T, epochs)
+    floor = 1e-25 * np.max(pi_net, axis=1, keepdims=True) + 1e-290
+    assert float(np.max(np.abs(res.pi_net - pi_net) / (np.abs(pi_net) + floor))) < F32_RTOL
+    assert rel(res.integral, si, floor=1e-30) < F32_RTOL
+    np.testing.assert_allclose(res.abserr, se, rtol=2e-2, atol=1e-300)
+    assert np.array_equal(res.pi_times, res.pi_net[:, times])
+    assert np.array_equal(res.max_pi, np.max(res.pi_net, axis=1))
+    assert np.array_equal(res.argmax_epoch, np.argmax(si, axis=1))
+    assert list(res.n_finite) == [int(np.isfinite(x).sum()) for x in loci]
+    again = eng.run(off, rates, T, times, epochs, fp32=True)
+    assert np.array_equal(res.pi_net, again.pi_net) and np.array_equal(res.integral, again.integral)   # deterministic
+
+
+def test_fp32_mode_split_sites_and_error_growth(eng):
+    """A locus of 300,000 sites split over site ranges (workspace + fixed-order reduction), and the error of the
+    FP32 sums against the number of sites: per-lane partial sums closed by a tree keep it near 1e-6."""
+    from oracle import capi
+    from tapir_b200 import synthetic
+    from tapir_b200.engine import pack_csr
+    rng = np.random.default_rng(77)
+    T = 1500
+    loci = [synthetic.uce_rates(rng, n, T, nan_frac=0.02) for n in (300000, 5000, 300)]
+    off, rates = pack_csr(loci, pinned=False)
+    res = eng.run(off, rates, T, [5, -1], synthetic.EPOCHS, fp32=True)
+    ref = eng.run(off, rates, T, [5, -1], synthetic.EPOCHS)                     # the FP64 path, itself within 1e-9
+    assert rel(res.pi_net[:, 1:], ref.pi_net[:, 1:]) < F32_RTOL
+    assert rel(res.integral, ref.integral) < F32_RTOL
+    for l in range(3):
+        si, se, _ = capi.epochs(rates[off[l]:off[l + 1]][np.isfinite(rates[off[l]:off[l + 1]])], synthetic.EPOCHS)
+        assert rel(res.integral[l], si) < F32_RTOL
+    assert np.array_equal(res.argmax_epoch, ref.argmax_epoch)

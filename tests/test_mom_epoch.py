@@ -24,10 +24,11 @@ CLASS_BOUND = 0.01953125
 BOUND = {32: 0.01953125, 16: 0.0048828125}       # the moment classes of profile_mom_kernel<RH, KM>
 
 
-def plan(a, b, n_tiles=8, tile_points=1024, km=32):
+def plan(a, b, n_tiles=8, tile_points=1024, km=32, class_x=0.0):
     out = _lib.MomEpoch()
-    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, km, ctypes.byref(out)))
+    _lib.check(_lib.load().tapir_mom_epoch_plan(float(a), float(b), n_tiles, tile_points, km, class_x, ctypes.byref(out)))
     out.km = km
+    out.bound = class_x / 256.0 if class_x else BOUND[km]
     return out
 
 
@@ -43,7 +44,7 @@ def moments(rates, tile, hb, tile_points, km=32):
 
 def served(pl, rates):
     r = np.asarray(rates)
-    ok = (r > 1.57e-162) & (r < BOUND[getattr(pl, "km", 32)]) & (r >= pl.r_min) & (r <= pl.r_max)
+    ok = (r > 1.57e-162) & (r < getattr(pl, "bound", BOUND[32])) & (r >= pl.r_min) & (r <= pl.r_max)
     return ok & ~((r >= pl.w_lo) & (r <= pl.w_hi))
 
 
@@ -133,3 +134,25 @@ def test_truncation_at_the_corner_of_the_range():
         integ, _, last = capi.epoch_sites(np.array([r]), a, b)
         got = float(np.dot(np.array(pl.p[:]), moments(np.array([r]), pl.tile, pl.hb, 1024, km)))
         assert last[0] == 1 and abs(got - integ[0]) <= 5e-11 * integ[0], (a, b, r, got, integ[0])
+
+
+@pytest.mark.parametrize("span", EPOCHS)
+def test_fp32_mode_class(span):
+    """TAPIR_FP32_MODE: 16 moments with the class 64 c <= 2.5.  Soundness is unchanged (QUADPACK returns the first panel
+    with the rounding floor for every served site); the value is inside that mode's 1e-5 gate by an order of magnitude."""
+    a, b = span
+    pl = plan(a, b, km=16, class_x=2.5)
+    assert pl.eligible and pl.r_max <= 2.5 / 256
+    rng = np.random.default_rng(a + 7 * b)
+    lam = np.concatenate([rng.gamma(0.5, 0.004, 3000), rng.uniform(0, 2.5 / 256, 2000), [np.nextafter(pl.r_max, 0.0)]])
+    lam = lam[served(pl, lam)]
+    assert lam.size > 300
+    integ, err, last = capi.epoch_sites(lam, a, b)
+    assert np.all(last == 1)
+    np.testing.assert_allclose(err, 50 * EPS * integ, rtol=1e-13)
+    got = float(np.dot(np.array(pl.p[:]), moments(lam, pl.tile, pl.hb, 1024, 16)))
+    assert abs(got - np.sum(integ)) <= 2e-6 * np.sum(integ)
+    worst = np.array([np.nextafter(pl.r_max, 0.0)])
+    if served(pl, worst)[0]:
+        one = float(np.dot(np.array(pl.p[:]), moments(worst, pl.tile, pl.hb, 1024, 16)))
+        assert abs(one - capi.epoch_sites(worst, a, b)[0][0]) <= 5e-6 * one
