@@ -1218,10 +1218,12 @@ struct QuadArgs {
     uint32_t* fix_count; // entries appended by this launch (zeroed before it)
     uint32_t* queue;     // work-queue head of this launch (zeroed before it)
     int32_t n_items;
-    // moment-functional batches: quad_scan_kernel lists the items that hold a site quad_kernel has to integrate;
-    // quad_kernel then takes its items from the list (list == nullptr: every item, rate statistics included)
+    // moment-functional batches: quad_scan_kernel marks the sites quad_kernel may have to integrate, one ballot per
+    // 32 sites (list[8 item + round]); the chunked quad_kernel<NE, kQuadChunk> fetches only those (list == nullptr:
+    // quad_kernel<NE> takes every item, rate statistics included)
     uint32_t* list;
-    uint32_t* list_count;
+    uint32_t* list_count;  // unused
+    int32_t chunk;         // items per work unit of the chunked form (1 .. kQuadChunk)
 };
 
 // GK21 on one epoch with the exponentials factored as e^{-c(centre -/+ h x_j)} = E0 * e^{+/- c h x_j}:
@@ -1407,18 +1409,27 @@ __device__ __forceinline__ bool gk21_collapsed(const EpochBatch& eb, int e, doub
 // NE = eb.n (0..kEpochsPerLaunch) is a template parameter so that the per-site computation is one straight-line
 // block the scheduler can interleave (the NE exponentials of the common factors in particular).
 constexpr int kQuadWarps = 1;  // warps per CTA
+constexpr int kQuadChunk = 32; // items per work unit of the chunked form (moment-functional batches)
 
-template <int NE>
+// CH = 1: a work unit is one item; every site of the item is integrated here (and the item's rate statistics are
+// formed).  CH = kQuadChunk (moment-functional batches): a work unit is CH consecutive items of which only those that
+// quad_scan_kernel flagged are streamed at all, and of those only the sites the moments do not serve; the few such
+// sites of the whole unit share the 32-lane passes (a pass per item would run with one or two live lanes), a
+// segmented scan over the lanes hands every item its own sums.  Either way the order of the additions depends on the
+// unit's content only.
+template <int NE, int CH = 1>
 __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(const QuadArgs args, const EpochBatch eb)
 {
+    static_assert(kQuadWarps == 1 && CH >= 1 && CH <= 32, "one-warp CTAs; a unit's items map to the lanes");
     constexpr int NA = NE > 0 ? 2 * NE : 1;
-    __shared__ double s_q[kQuadWarps][64];                 // queue of active rates
-    __shared__ uint16_t s_src[kQuadWarps][64];             // their position inside the item
-    __shared__ double s_acc[kQuadWarps][NA][32];           // per-lane sums: integral / abserr per epoch
-    __shared__ uint32_t s_flag[kQuadWarps][kEpochsPerLaunch][kQuadBlock / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* q = s_q[warp];
-    uint16_t* qsrc = s_src[warp];
+    __shared__ double s_q[64];                                   // queue of active rates
+    __shared__ uint16_t s_src[64];                               // position inside the item (low byte), item of the unit (high byte)
+    __shared__ double s_acc[CH == 1 ? NA : 1][32];               // CH = 1: per-lane sums, integral / abserr per epoch
+    __shared__ double s_tot[CH == 1 ? 1 : CH][NA];               // CH > 1: per-item sums
+    __shared__ uint32_t s_flag[CH][kEpochsPerLaunch][kQuadBlock / 32];
+    const int lane = threadIdx.x & 31;
+    double* q = s_q;
+    uint16_t* qsrc = s_src;
     const int row = 2 * eb.e_total + 4;
     // bit e: the site takes the per-site path for epoch e (all epochs unless the moment functional serves it)
     auto need_mask = [&](double lam) -> uint32_t {
@@ -1435,169 +1446,257 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
         }
         return need;
     };
+    const int ch = (CH == 1) ? 1 : args.chunk;   // items per work unit (<= CH)
+    const int n_units = (args.n_items + ch - 1) / ch;
 
     for (;;) {
-        int it = 0;
-        if (lane == 0) {
-            it = int(atomicAdd(args.queue, 1u));
-            if (args.list) it = (uint32_t(it) < *args.list_count) ? int(args.list[it]) : args.n_items;
-        }
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= args.n_items) break;
-        const QuadItem item = args.items[it];
-        const double* rp = args.rates + item.site_begin;
+        int unit = 0;
+        if (lane == 0) unit = int(atomicAdd(args.queue, 1u));
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const int it0 = unit * ch, n_local = min(ch, args.n_items - it0);
+        // which items of the unit hold a site for this kernel (CH = 1: the item itself, always): lane = item, its
+        // eight ballots of candidate sites stay in the lane's registers
+        uint32_t todo = 1u;
+        uint32_t cand[kQuadBlock / 32];
+        long long my_begin = 0;   // CH > 1: first site of this lane's item
 #pragma unroll
-        for (int k = 0; k < NA; ++k) s_acc[warp][k][lane] = 0.0;
-        if (lane < kQuadBlock / 32) {
+        for (int r = 0; r < kQuadBlock / 32; ++r) cand[r] = 0u;
+        if constexpr (CH > 1) {
+            if (lane < n_local) {
+                my_begin = args.items[it0 + lane].site_begin;
+                const uint4* lp = reinterpret_cast<const uint4*>(args.list + size_t(it0 + lane) * (kQuadBlock / 32));
+                const uint4 w0 = __ldg(lp), w1 = __ldg(lp + 1);
+                cand[0] = w0.x; cand[1] = w0.y; cand[2] = w0.z; cand[3] = w0.w;
+                cand[4] = w1.x; cand[5] = w1.y; cand[6] = w1.z; cand[7] = w1.w;
+            }
+            uint32_t any = 0u;
 #pragma unroll
-            for (int e = 0; e < kEpochsPerLaunch; ++e) s_flag[warp][e][lane] = 0;
+            for (int r = 0; r < kQuadBlock / 32; ++r) any |= cand[r];
+            todo = __ballot_sync(0xffffffffu, any != 0u);
         }
-        double rs = 0.0, nn = 0.0, nf = 0.0;  // rate sum, #not-NaN, #finite of this lane's sites
+        if (todo == 0u) continue;
+        const uint32_t todo_all = todo;
+        if constexpr (CH == 1) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) s_acc[k][lane] = 0.0;
+        } else {
+            for (int i = lane; i < CH * NA; i += 32) (&s_tot[0][0])[i] = 0.0;
+        }
+        for (int i = lane; i < CH * kEpochsPerLaunch * (kQuadBlock / 32); i += 32) (&s_flag[0][0][0])[i] = 0u;
+        double rs = 0.0, nn = 0.0, nf = 0.0;  // rate sum, #not-NaN, #finite of this lane's sites (CH = 1)
         int qh = 0, qn = 0;
-        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-        double lam_in = (lane < item.count) ? __ldg(rp + lane) : qnan;        // fetched two rounds ahead, as in
-        double lam_in2 = (32 + lane < item.count) ? __ldg(rp + 32 + lane) : qnan;  // profile_kernel
         __syncwarp();
-        for (int base = 0;; base += 32) {
-            const bool more = base < item.count;
-            if (more) {
-                const double lam = lam_in;
-                lam_in = lam_in2;
-                {
-                    const int nb = base + 64 + lane;
-                    lam_in2 = (nb < item.count) ? __ldg(rp + nb) : qnan;
-                }
-                const bool notnan = lam == lam;  // lanes past the item hold NaN
-                const bool fin = fabs(lam) <= DBL_MAX;
-                rs += notnan ? lam : 0.0;
-                nn += notnan ? 1.0 : 0.0;
-                nf += fin ? 1.0 : 0.0;
-                const bool act = fin && (16.0 * (lam * lam) != 0.0) && need_mask(lam) != 0u;
-                const unsigned ballot = __ballot_sync(0xffffffffu, act);
-                if (act) {
-                    const int pos = (qn + __popc(ballot & ((1u << lane) - 1u))) & 63;
-                    q[pos] = lam;
-                    qsrc[pos] = uint16_t(base + lane);
-                }
-                qn += __popc(ballot);
-                __syncwarp();
-            }
-            if constexpr (NE > 0) {
-                while (qn - qh >= 32 || (!more && qn > qh)) {
-                    const int cnt = min(32, qn - qh);
-                    const bool on = lane < cnt;
-                    const double lam2 = on ? q[(qh + lane) & 63] : 0.0;
-                    const uint32_t src = on ? qsrc[(qh + lane) & 63] : 0u;
-                    qh += cnt;
-                    const double a = 16.0 * (lam2 * lam2);
-                    const double c = 4.0 * lam2;
-                    // fast path: all exponent arguments stay well inside the normal range, every node value >= 0
-                    const bool fast = on && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
-                    const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps idle lanes' arithmetic finite
-                    const uint32_t need = on ? need_mask(lam2) : 0u;
-                    const bool in_moments = on && eb.mom_any && rate_is_active(lam2) && rate_is_slow(lam2, eb.class_hi);
-                    PanelSums ps;
-                    // one copy of the GK21 code, looped over the epochs: the fully unrolled form (4 x ~350
-                    // instructions) thrashed the instruction cache once the warps ran out of step (18 % of the
-                    // stall samples were instruction fetches)
-                    // (for NE <= 2 the trip count is read from the batch, eb.n == NE: with a compile-time count of 1 or 2
-                    // the compiler flattens the loop and the longer live ranges spill 140-190 bytes -- E = 2: 0.105 ->
-                    // 0.087 ms on config 2)
-                    const int ne = NE <= 2 ? eb.n : NE;
+
+        // one pass of the GK21 code over `cnt` queued sites
+        auto run_pass = [&](int cnt) {
+            const bool on = lane < cnt;
+            const double lam2 = on ? q[(qh + lane) & 63] : 0.0;
+            const uint32_t src = on ? qsrc[(qh + lane) & 63] : 0xff00u;
+            qh += cnt;
+            const uint32_t pos = src & 0xffu, li = src >> 8;
+            const double a = 16.0 * (lam2 * lam2);
+            const double c = 4.0 * lam2;
+            // fast path: all exponent arguments stay well inside the normal range, every node value >= 0
+            const bool fast = on && eb.nonneg && (c >= 0.0) && (c * eb.bmax <= 600.0) && (a <= DBL_MAX);
+            const double cs = fast ? c : 0.0, as = fast ? a : 0.0;  // keeps idle lanes' arithmetic finite
+            const uint32_t need = on ? need_mask(lam2) : 0u;
+            const bool in_moments = on && eb.mom_any && rate_is_active(lam2) && rate_is_slow(lam2, eb.class_hi);
+            // CH > 1: the lanes of one item are consecutive; the last lane of a run adds the run's total to the item
+            uint32_t li_next = 0xffffu;
+            if constexpr (CH > 1) li_next = __shfl_down_sync(0xffffffffu, li, 1);
+            const bool seg_last = on && (lane == cnt - 1 || li_next != li);
+            PanelSums ps;
+            // one copy of the GK21 code, looped over the epochs: the fully unrolled form (4 x ~350
+            // instructions) thrashed the instruction cache once the warps ran out of step (18 % of the
+            // stall samples were instruction fetches)
+            // (for NE <= 2 the trip count is read from the batch, eb.n == NE: with a compile-time count of 1 or 2
+            // the compiler flattens the loop and the longer live ranges spill 140-190 bytes -- E = 2: 0.105 ->
+            // 0.087 ms on config 2)
+            const int ne = NE <= 2 ? eb.n : NE;
 #pragma unroll 1
-                    for (int e = 0; e < ne; ++e) {
-                        if (eb.new_half[e]) {
-                            double D[10], R[10];
-                            const double y = cs * eb.half[e];
-                            // slow sites (the bulk of UCE-like data), every y x_j below ln(2)/2 (x_0 log2 e = 1.4364...):
-                            // the sums from their power series, no node tables
-                            if (__all_sync(0xffffffffu, y * 1.4365 < 0.4999)) {
-                                panel_sums_series(eb.half[e], y, ps);
-                            } else {
+            for (int e = 0; e < ne; ++e) {
+                if (eb.new_half[e]) {
+                    double D[10], R[10];
+                    const double y = cs * eb.half[e];
+                    // slow sites (the bulk of UCE-like data), every y x_j below ln(2)/2 (x_0 log2 e = 1.4364...):
+                    // the sums from their power series, no node tables
+                    if (__all_sync(0xffffffffu, y * 1.4365 < 0.4999)) {
+                        panel_sums_series(eb.half[e], y, ps);
+                    } else {
 #pragma unroll
-                                for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
-                                panel_sums(eb.half[e], D, R, ps);
-                            }
-                        }
-                        // common factor a e^{-c centre} h; |c * centre| <= 600 on this path
-                        const double scale = (as * exp_bounded(-(cs * eb.center[e]))) * eb.half[e];
-                        double result, abserr, resabs, resasc = 0.0;
-                        const bool wanted = (need >> e) & 1u;   // this (site, epoch) is not served by the moments
-                        const bool live = fast && wanted;
-                        bool by_floor = gk21_collapsed(eb, e, scale, live, ps, result, abserr);
-                        if (!by_floor) {
-                            // rare: some site's estimate is not the floor.  The node tables are rebuilt here (same
-                            // function, same argument, same values) instead of being kept alive across the epochs.
-                            double D[10], R[10];
-                            const double y = cs * eb.half[e];
-#pragma unroll
-                            for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);
-                            by_floor = gk21_shared_exp(eb, e, scale, live, D, R, result, abserr, resabs, resasc);
-                        }
-                        // by_floor: abserr = 50 eps resabs <= 100 eps resabs and abserr != resasc, so dqagse's test
-                        // (round-off exit above errbnd, plain acceptance below) passes either way
-                        const bool keep = live && (by_floor || qags_first_panel_final(result, abserr, resabs, resasc));
-                        double vi = keep ? result : 0.0, ve = keep ? abserr : 0.0;
-                        if (eb.mom_any && eb.mom[e]) {
-                            // a site of the moment class that is integrated here (rate inside the epoch's window or
-                            // outside its range) is also part of the locus' moments: take out what the functional
-                            // adds for it -- a e^{-c tb} P(z), z = -64 c, the same polynomial on the same site
-                            const bool sub = in_moments && wanted;
-                            if (__any_sync(0xffffffffu, sub)) {
-                                const double* pc = eb.mom_p + 32 * eb.col[e];
-                                const double z = -64.0 * c;
-                                double hz = __ldg(pc + eb.mom_terms - 1);
-#pragma unroll 1
-                                for (int k = eb.mom_terms - 2; k >= 0; --k) hz = fma(hz, z, __ldg(pc + k));
-                                const double pv = (a * exp(-(c * eb.tb[e]))) * hz;
-                                if (sub) { vi -= pv; ve -= (kEpmach * 50.0) * pv; }
-                            }
-                        }
-                        s_acc[warp][2 * e][lane] += vi;
-                        s_acc[warp][2 * e + 1][lane] += ve;
-                        if (on && wanted && !keep)  // rare: hand the site (by its position in the item) to quad_fix_kernel
-                            atomicOr(&s_flag[warp][e][src >> 5], 1u << (src & 31));
+                        for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);  // 0 <= y x_j <= 600
+                        panel_sums(eb.half[e], D, R, ps);
                     }
+                }
+                // common factor a e^{-c centre} h; |c * centre| <= 600 on this path
+                const double scale = (as * exp_bounded(-(cs * eb.center[e]))) * eb.half[e];
+                double result, abserr, resabs, resasc = 0.0;
+                const bool wanted = (need >> e) & 1u;   // this (site, epoch) is not served by the moments
+                const bool live = fast && wanted;
+                bool by_floor = gk21_collapsed(eb, e, scale, live, ps, result, abserr);
+                if (!by_floor) {
+                    // rare: some site's estimate is not the floor.  The node tables are rebuilt here (same
+                    // function, same argument, same values) instead of being kept alive across the epochs.
+                    double D[10], R[10];
+                    const double y = cs * eb.half[e];
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) exp_pm_bounded(y * c_xgk[j], D[j], R[j]);
+                    by_floor = gk21_shared_exp(eb, e, scale, live, D, R, result, abserr, resabs, resasc);
+                }
+                // by_floor: abserr = 50 eps resabs <= 100 eps resabs and abserr != resasc, so dqagse's test
+                // (round-off exit above errbnd, plain acceptance below) passes either way
+                const bool keep = live && (by_floor || qags_first_panel_final(result, abserr, resabs, resasc));
+                double vi = keep ? result : 0.0, ve = keep ? abserr : 0.0;
+                if (eb.mom_any && eb.mom[e]) {
+                    // a site of the moment class that is integrated here (rate inside the epoch's window or
+                    // outside its range) is also part of the locus' moments: take out what the functional
+                    // adds for it -- a e^{-c tb} P(z), z = -64 c, the same polynomial on the same site
+                    const bool sub = in_moments && wanted;
+                    if (__any_sync(0xffffffffu, sub)) {
+                        const double* pc = eb.mom_p + 32 * eb.col[e];
+                        const double z = -64.0 * c;
+                        double hz = __ldg(pc + eb.mom_terms - 1);
+#pragma unroll 1
+                        for (int k = eb.mom_terms - 2; k >= 0; --k) hz = fma(hz, z, __ldg(pc + k));
+                        const double pv = (a * exp(-(c * eb.tb[e]))) * hz;
+                        if (sub) { vi -= pv; ve -= (kEpmach * 50.0) * pv; }
+                    }
+                }
+                if constexpr (CH == 1) {
+                    s_acc[2 * e][lane] += vi;
+                    s_acc[2 * e + 1][lane] += ve;
+                } else {
+                    // segmented inclusive scan over the lanes (runs of equal li), then one add per run and column
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double ui = __shfl_up_sync(0xffffffffu, vi, d), ue = __shfl_up_sync(0xffffffffu, ve, d);
+                        const uint32_t lu = __shfl_up_sync(0xffffffffu, li, d);
+                        if (lane >= d && lu == li) { vi += ui; ve += ue; }
+                    }
+                    if (seg_last) {
+                        s_tot[li][2 * e] += vi;
+                        s_tot[li][2 * e + 1] += ve;
+                    }
+                }
+                if (on && wanted && !keep)  // rare: hand the site (by its position in the item) to quad_fix_kernel
+                    atomicOr(&s_flag[CH == 1 ? 0 : li][e][pos >> 5], 1u << (pos & 31));
+            }
+            __syncwarp();
+        };
+
+        while (todo) {
+            const int li_now = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if constexpr (CH > 1) {
+                // only the candidate sites are fetched -- all of the item's at once, so that one memory latency is
+                // exposed per item; the exact test is run_pass's (a site the moments serve after all adds nothing there)
+                const double* rp = args.rates + __shfl_sync(0xffffffffu, my_begin, li_now);
+                uint32_t w[kQuadBlock / 32];
+                double val[kQuadBlock / 32];
+#pragma unroll
+                for (int r = 0; r < kQuadBlock / 32; ++r) {
+                    w[r] = __shfl_sync(0xffffffffu, cand[r], li_now);
+                    val[r] = ((w[r] >> lane) & 1u) ? __ldg(rp + 32 * r + lane) : 0.0;
+                }
+#pragma unroll
+                for (int r = 0; r < kQuadBlock / 32; ++r) {
+                    if (w[r] == 0u) continue;
+                    if ((w[r] >> lane) & 1u) {
+                        const int pos = (qn + __popc(w[r] & ((1u << lane) - 1u))) & 63;
+                        q[pos] = val[r];
+                        qsrc[pos] = uint16_t((32 * r + lane) | (li_now << 8));
+                    }
+                    qn += __popc(w[r]);
                     __syncwarp();
+                    if constexpr (NE > 0) {
+                        while (qn - qh >= 32) run_pass(32);
+                    }
+                }
+            } else {
+                const QuadItem item = args.items[it0 + li_now];
+                const double* rp = args.rates + item.site_begin;
+                const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+                double lam_in = (lane < item.count) ? __ldg(rp + lane) : qnan;        // fetched two rounds ahead, as in
+                double lam_in2 = (32 + lane < item.count) ? __ldg(rp + 32 + lane) : qnan;  // profile_kernel
+                for (int base = 0; base < item.count; base += 32) {
+                    const double lam = lam_in;
+                    lam_in = lam_in2;
+                    {
+                        const int nb = base + 64 + lane;
+                        lam_in2 = (nb < item.count) ? __ldg(rp + nb) : qnan;
+                    }
+                    const bool notnan = lam == lam;  // lanes past the item hold NaN
+                    const bool fin = fabs(lam) <= DBL_MAX;
+                    rs += notnan ? lam : 0.0;
+                    nn += notnan ? 1.0 : 0.0;
+                    nf += fin ? 1.0 : 0.0;
+                    const bool act = fin && (16.0 * (lam * lam) != 0.0) && need_mask(lam) != 0u;
+                    const unsigned ballot = __ballot_sync(0xffffffffu, act);
+                    if (act) {
+                        const int pos = (qn + __popc(ballot & ((1u << lane) - 1u))) & 63;
+                        q[pos] = lam;
+                        qsrc[pos] = uint16_t(base + lane);
+                    }
+                    qn += __popc(ballot);
+                    __syncwarp();
+                    if constexpr (NE > 0) {
+                        while (qn - qh >= 32) run_pass(32);
+                    }
                 }
             }
-            if (!more) break;
         }
-        // ---- close the item: one shuffle tree per column, fixed order ----
-        double* out = args.qpart + size_t(it) * row;
-#pragma unroll
-        for (int k = 0; k < 2 * NE; ++k) {
-            double v = s_acc[warp][k][lane];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if (lane == 0) out[2 * eb.col[k >> 1] + (k & 1)] = v;
+        if constexpr (NE > 0) {
+            while (qn > qh) run_pass(min(32, qn - qh));   // what is left of the unit
         }
-        if (eb.first && !args.list) {  // (listed items: quad_scan_kernel has written the statistics)
+
+        // ---- close the unit ----
+        if constexpr (CH == 1) {
+            // one shuffle tree per column, fixed order
+            const int it = it0;
+            double* out = args.qpart + size_t(it) * row;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                rs += __shfl_down_sync(0xffffffffu, rs, off);
-                nn += __shfl_down_sync(0xffffffffu, nn, off);
-                nf += __shfl_down_sync(0xffffffffu, nf, off);
+            for (int k = 0; k < 2 * NE; ++k) {
+                double v = s_acc[k][lane];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+                if (lane == 0) out[2 * eb.col[k >> 1] + (k & 1)] = v;
             }
-            if (lane == 0) {
-                out[2 * eb.e_total + 0] = rs;
-                out[2 * eb.e_total + 1] = nn;
-                out[2 * eb.e_total + 2] = nf;
-                out[2 * eb.e_total + 3] = 0.0;  // multi-panel count, accumulated by quad_fix_kernel
+            if (eb.first) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    rs += __shfl_down_sync(0xffffffffu, rs, off);
+                    nn += __shfl_down_sync(0xffffffffu, nn, off);
+                    nf += __shfl_down_sync(0xffffffffu, nf, off);
+                }
+                if (lane == 0) {
+                    out[2 * eb.e_total + 0] = rs;
+                    out[2 * eb.e_total + 1] = nn;
+                    out[2 * eb.e_total + 2] = nf;
+                    out[2 * eb.e_total + 3] = 0.0;  // multi-panel count, accumulated by quad_fix_kernel
+                }
+            }
+        } else {
+            // the flagged items' cells (quad_scan_kernel zeroed every item's, and wrote the statistics)
+            __syncwarp();
+            for (int i = lane; i < n_local * 2 * NE; i += 32) {
+                const int li = i / (2 * NE), k = i % (2 * NE);
+                if ((todo_all >> li) & 1u)
+                    args.qpart[size_t(it0 + li) * row + 2 * eb.col[k >> 1] + (k & 1)] = s_tot[li][k];
             }
         }
         __syncwarp();
-        if (lane < NE) {
-            const int e = lane;
+        for (int i = lane; i < n_local * NE; i += 32) {
+            const int li = i / max(NE, 1), e = i % max(NE, 1);
             uint32_t any = 0;
 #pragma unroll
-            for (int w = 0; w < kQuadBlock / 32; ++w) any |= s_flag[warp][e][w];
+            for (int w = 0; w < kQuadBlock / 32; ++w) any |= s_flag[li][e][w];
             if (any) {
                 FixEntry* fe = args.fix + atomicAdd(args.fix_count, 1u);
-                fe->item = it;
+                fe->item = it0 + li;
                 fe->slot = e;
 #pragma unroll
-                for (int w = 0; w < kQuadBlock / 32; ++w) fe->mask[w] = s_flag[warp][e][w];
+                for (int w = 0; w < kQuadBlock / 32; ++w) fe->mask[w] = s_flag[li][e][w];
             }
         }
         __syncwarp();
@@ -1606,7 +1705,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
 
 // Moment-functional batches: almost every site is served by the locus' moments (mom_epoch.h), so what is left of
 // the per-site path is a streaming pass over the rates that (i) writes the rate statistics of every item (the same
-// per-lane sums and shuffle tree as quad_kernel, bit for bit), (ii) zeroes the item's epoch cells and (iii) lists the
+// per-lane sums and shuffle tree as quad_kernel, bit for bit), (ii) zeroes the item's epoch cells and (iii) flags the
 // items holding at least one site quad_kernel must integrate.  The test is the conservative form of quad_kernel's
 // need_mask on the high words of the rates (a listed item is then filtered exactly by quad_kernel itself), integer
 // pipe only; the eight rounds of an item are loaded up front so that a warp keeps 2 KB in flight.
@@ -1626,7 +1725,7 @@ __global__ void __launch_bounds__(kScanThreads) quad_scan_kernel(const QuadArgs 
         for (int k = 0; k < kQuadBlock / 32; ++k) v[k] = (32 * k + lane < item.count) ? __ldg(rp + 32 * k + lane) : qnan;
         double rs = 0.0;
         int nn = 0, nf = 0;
-        bool rare = false;
+        uint32_t mine = 0u;   // lane k keeps the ballot of round k
 #pragma unroll
         for (int k = 0; k < kQuadBlock / 32; ++k) {
             const uint32_t hs = uint32_t(__double2hiint(v[k])), hi = hs & 0x7fffffffu, lo = uint32_t(__double2loint(v[k]));
@@ -1641,11 +1740,11 @@ __global__ void __launch_bounds__(kScanThreads) quad_scan_kernel(const QuadArgs 
             bool served = eb.mom_all && (hs - eb.scan_lo - 1u) < (eb.scan_hi - eb.scan_lo - 1u);
 #pragma unroll 1
             for (int w = 0; w < eb.n_win; ++w) served = served && (hs - eb.win_lo[w]) > (eb.win_hi[w] - eb.win_lo[w]);
-            rare = rare || (act && !served);
+            const uint32_t b = __ballot_sync(0xffffffffu, act && !served);
+            if (lane == k) mine = b;
         }
         nn = __reduce_add_sync(0xffffffffu, nn);
         nf = __reduce_add_sync(0xffffffffu, nf);
-        const bool any_rare = __any_sync(0xffffffffu, rare);
         double* out = args.qpart + size_t(it) * row;
         if (lane < 2 * eb.n) out[2 * eb.col[lane >> 1] + (lane & 1)] = 0.0;
         if (eb.first) {
@@ -1658,7 +1757,7 @@ __global__ void __launch_bounds__(kScanThreads) quad_scan_kernel(const QuadArgs 
                 out[2 * eb.e_total + 3] = 0.0;
             }
         }
-        if (any_rare && lane == 0) args.list[atomicAdd(args.list_count, 1u)] = uint32_t(it);
+        if (lane < kQuadBlock / 32) args.list[size_t(it) * (kQuadBlock / 32) + lane] = mine;   // 32 bytes per item
     }
 }
 

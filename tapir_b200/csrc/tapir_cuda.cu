@@ -327,8 +327,9 @@ void choose_tile(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t T, d
 // slow site and per item, but every site between the two bounds goes through the power-table pass of the fast sites,
 // and through quad_kernel for its epoch integrals).  Decided per batch from a strided sample of its rates: expected
 // FP64-pipe cycles per (locus, tile) item -- the fast groups weighted 2.5x for their exposed latency -- plus what the
-// per-site integrals cost, in the same unit (23 ps per site of a 256-site block that holds such a site, 1.4 ps per
-// cycle: profiles/r02_moments_sweep.txt, where the model's 16/32 ratio is 0.77 against a measured 0.77 on config 5).
+// per-site integrals of the sites outside the class cost in the same unit (~0.35 ns = 250 cycles each through the
+// chunked quad_kernel; profiles/r02_moments_sweep.txt, where the model's 16/32 ratio of the profile kernel is 0.77
+// against a measured 0.77 on config 5).
 int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0, int64_t l1, int rh, int n_tiles)
 {
     if (ctx->force_terms) return ctx->force_terms;
@@ -355,8 +356,7 @@ int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0
         const double groups16 = std::max(1.0 - std::exp(-n_fast), (n_fast + std::sqrt(n_fast)) / 16.0);
         const double fast = groups16 * 2.5 * (256.0 * rh + 220.0) * (n_fast > 24.0 ? 1.2 : 1.0);
         const double profile = n_slow * (0.5 * km * NT + (33.0 + km + NB) / 16.0) + 64.0 * km * NT + fast;
-        const double p_block = 1.0 - std::pow(1.0 - double(n_ge) / double(n_sample), 256.0);   // a quad item holds such a site
-        const double quad = p->n_epochs > 0 ? 16.4 * p_block * sites : 0.0;
+        const double quad = p->n_epochs > 0 ? 250.0 * n_fast : 0.0;   // per-site integrals of the sites outside the class
         return double(n_tiles) * profile + quad;
     };
     return cost(16, n_ge16) < cost(32, n_ge32) ? 16 : 32;
@@ -827,7 +827,7 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     CU(ctx, ln.d_qpart.ensure(size_t(n_quad) * qrow * 8 + 8));
     CU(ctx, ln.d_fix.ensure(size_t(n_quad) * kEpochsPerLaunch * sizeof(FixEntry) + 8));
     CU(ctx, ln.d_mom_int.ensure(size_t(n_parts) * size_t(plan.E) * 8 + 8));
-    CU(ctx, ln.d_rare_list.ensure(plan.n_mom ? size_t(n_quad) * plan.batches.size() * 4 + 8 : 8));
+    CU(ctx, ln.d_rare_list.ensure(plan.n_mom ? size_t(n_quad) * plan.batches.size() * (kQuadBlock / 32) * 4 + 64 : 64));
     CU(ctx, ln.d_pi_net.ensure(size_t(L) * plan.T * 8 + 16));
     CU(ctx, ln.d_small.ensure(plan.small_bytes + 8));
     CU(ctx, ln.h_small.ensure(plan.small_bytes + 8));
@@ -927,7 +927,7 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
                 qa.list = nullptr;
                 qa.list_count = nullptr;
                 if (eb.mom_any) {
-                    qa.list = ln.d_rare_list.as<uint32_t>() + size_t(k - 1) * size_t(plan.n_quad_items);
+                    qa.list = ln.d_rare_list.as<uint32_t>() + size_t(k - 1) * size_t(plan.n_quad_items) * (kQuadBlock / 32);
                     qa.list_count = ln.d_counter.as<uint32_t>() + 17 + (k - 1);
                     const int64_t warps = kScanThreads / 32;
                     const unsigned sgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>((plan.n_quad_items + warps - 1) / warps, int64_t(ctx->sm_count) * 8)));
@@ -935,21 +935,28 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
                     CU(ctx, cudaGetLastError());
                     ++launches;
                 }
-                const int64_t want = (plan.n_quad_items + kQuadWarps - 1) / kQuadWarps;
+                const bool chunked = eb.mom_any != 0;   // candidate sites only, several items per work unit
                 int q_per_sm = 12 / kQuadWarps;  // 12 warps per SM (168 registers)
                 if (ctx->quad_ctas_cap >= 1 && ctx->quad_ctas_cap <= q_per_sm) q_per_sm = ctx->quad_ctas_cap;
+                // unit size: as many items as keep every resident warp supplied with a few units
+                qa.chunk = int32_t(std::max<int64_t>(1, std::min<int64_t>(kQuadChunk, plan.n_quad_items / (4 * int64_t(ctx->sm_count) * q_per_sm))));
+                const int64_t want = chunked ? (plan.n_quad_items + qa.chunk - 1) / qa.chunk : plan.n_quad_items;
                 const unsigned qgrid = unsigned(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(ctx->sm_count) * q_per_sm)));
+#define TAPIR_QUAD_LAUNCH(NE)                                                                    \
+    if (chunked) quad_kernel<NE, kQuadChunk><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb);          \
+    else quad_kernel<NE><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb)
                 switch (eb.n) {
                     case 0: quad_kernel<0><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;  // rate statistics only
-                    case 1: quad_kernel<1><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
-                    case 2: quad_kernel<2><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
-                    case 3: quad_kernel<3><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
-                    case 4: quad_kernel<4><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
-                    case 5: quad_kernel<5><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
-                    case 6: quad_kernel<6><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
-                    case 7: quad_kernel<7><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
-                    default: quad_kernel<8><<<qgrid, kQuadWarps * 32, 0, sq>>>(qa, eb); break;
+                    case 1: TAPIR_QUAD_LAUNCH(1); break;
+                    case 2: TAPIR_QUAD_LAUNCH(2); break;
+                    case 3: TAPIR_QUAD_LAUNCH(3); break;
+                    case 4: TAPIR_QUAD_LAUNCH(4); break;
+                    case 5: TAPIR_QUAD_LAUNCH(5); break;
+                    case 6: TAPIR_QUAD_LAUNCH(6); break;
+                    case 7: TAPIR_QUAD_LAUNCH(7); break;
+                    default: TAPIR_QUAD_LAUNCH(8); break;
                 }
+#undef TAPIR_QUAD_LAUNCH
                 CU(ctx, cudaGetLastError());
                 quad_fix_kernel<<<unsigned(ctx->sm_count * 4), 128, 0, sq>>>(qa, eb);
                 CU(ctx, cudaGetLastError());
