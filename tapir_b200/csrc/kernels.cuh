@@ -1422,8 +1422,9 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
 {
     static_assert(kQuadWarps == 1 && CH >= 1 && CH <= 32, "one-warp CTAs; a unit's items map to the lanes");
     constexpr int NA = NE > 0 ? 2 * NE : 1;
-    __shared__ double s_q[64];                                   // queue of active rates
-    __shared__ uint16_t s_src[64];                               // position inside the item (low byte), item of the unit (high byte)
+    constexpr int QN = (CH == 1) ? 64 : 512;                     // queue entries: a pass' worth left over + one round / one item
+    __shared__ double s_q[QN];                                   // queue of active rates
+    __shared__ uint16_t s_src[QN];                               // position inside the item (low byte), item of the unit (high byte)
     __shared__ double s_acc[CH == 1 ? NA : 1][32];               // CH = 1: per-lane sums, integral / abserr per epoch
     __shared__ double s_tot[CH == 1 ? 1 : CH][NA];               // CH > 1: per-item sums
     __shared__ uint32_t s_flag[CH][kEpochsPerLaunch][kQuadBlock / 32];
@@ -1491,8 +1492,8 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
         // one pass of the GK21 code over `cnt` queued sites
         auto run_pass = [&](int cnt) {
             const bool on = lane < cnt;
-            const double lam2 = on ? q[(qh + lane) & 63] : 0.0;
-            const uint32_t src = on ? qsrc[(qh + lane) & 63] : 0xff00u;
+            const double lam2 = on ? q[(qh + lane) & (QN - 1)] : 0.0;
+            const uint32_t src = on ? qsrc[(qh + lane) & (QN - 1)] : 0xff00u;
             qh += cnt;
             const uint32_t pos = src & 0xffu, li = src >> 8;
             const double a = 16.0 * (lam2 * lam2);
@@ -1585,41 +1586,24 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
             __syncwarp();
         };
 
-        while (todo) {
-            const int li_now = __ffs(todo) - 1;
-            todo &= todo - 1;
-            if constexpr (CH > 1) {
-                // only the candidate sites are fetched -- all of the item's at once, so that one memory latency is
-                // exposed per item; the exact test is run_pass's (a site the moments serve after all adds nothing there)
-                const double* rp = args.rates + __shfl_sync(0xffffffffu, my_begin, li_now);
-                uint32_t w[kQuadBlock / 32];
-                double val[kQuadBlock / 32];
-#pragma unroll
-                for (int r = 0; r < kQuadBlock / 32; ++r) {
-                    w[r] = __shfl_sync(0xffffffffu, cand[r], li_now);
-                    val[r] = ((w[r] >> lane) & 1u) ? __ldg(rp + 32 * r + lane) : 0.0;
-                }
-#pragma unroll
-                for (int r = 0; r < kQuadBlock / 32; ++r) {
-                    if (w[r] == 0u) continue;
-                    if ((w[r] >> lane) & 1u) {
-                        const int pos = (qn + __popc(w[r] & ((1u << lane) - 1u))) & 63;
-                        q[pos] = val[r];
-                        qsrc[pos] = uint16_t((32 * r + lane) | (li_now << 8));
-                    }
-                    qn += __popc(w[r]);
-                    __syncwarp();
-                    if constexpr (NE > 0) {
-                        while (qn - qh >= 32) run_pass(32);
-                    }
-                }
-            } else {
-                const QuadItem item = args.items[it0 + li_now];
-                const double* rp = args.rates + item.site_begin;
-                const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-                double lam_in = (lane < item.count) ? __ldg(rp + lane) : qnan;        // fetched two rounds ahead, as in
-                double lam_in2 = (32 + lane < item.count) ? __ldg(rp + 32 + lane) : qnan;  // profile_kernel
-                for (int base = 0; base < item.count; base += 32) {
+        // Fill the queue until a full pass is there (or nothing is left), run ONE pass, repeat: a single call site of
+        // the GK21 code per instantiation (inlined at every place it used to be called from, it no longer fitted the
+        // instruction cache: 60 % of the stall samples were instruction fetches).
+        QuadItem item;
+        item.site_begin = 0; item.count = 0; item.locus = 0;
+        const double* rp = args.rates;
+        int base = 0;
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        double lam_in = qnan, lam_in2 = qnan;
+        if constexpr (CH == 1) {
+            item = args.items[it0];
+            rp = args.rates + item.site_begin;
+            lam_in = (lane < item.count) ? __ldg(rp + lane) : qnan;             // fetched two rounds ahead, as in
+            lam_in2 = (32 + lane < item.count) ? __ldg(rp + 32 + lane) : qnan;  // profile_kernel
+        }
+        for (;;) {
+            if constexpr (CH == 1) {
+                while (qn - qh < 32 && base < item.count) {
                     const double lam = lam_in;
                     lam_in = lam_in2;
                     {
@@ -1634,20 +1618,44 @@ __global__ void __launch_bounds__(kQuadWarps * 32, 12 / kQuadWarps) quad_kernel(
                     const bool act = fin && (16.0 * (lam * lam) != 0.0) && need_mask(lam) != 0u;
                     const unsigned ballot = __ballot_sync(0xffffffffu, act);
                     if (act) {
-                        const int pos = (qn + __popc(ballot & ((1u << lane) - 1u))) & 63;
+                        const int pos = (qn + __popc(ballot & ((1u << lane) - 1u))) & (QN - 1);
                         q[pos] = lam;
                         qsrc[pos] = uint16_t(base + lane);
                     }
                     qn += __popc(ballot);
+                    base += 32;
                     __syncwarp();
-                    if constexpr (NE > 0) {
-                        while (qn - qh >= 32) run_pass(32);
+                }
+            } else {
+                while (qn - qh < 32 && todo) {
+                    // the next flagged item: only its candidate sites are fetched -- all of them at once, so that one
+                    // memory latency is exposed per item; the exact test is run_pass's (a site the moments serve
+                    // after all adds nothing there)
+                    const int li_now = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const double* ip = args.rates + __shfl_sync(0xffffffffu, my_begin, li_now);
+                    uint32_t w[kQuadBlock / 32];
+                    double val[kQuadBlock / 32];
+#pragma unroll
+                    for (int r = 0; r < kQuadBlock / 32; ++r) {
+                        w[r] = __shfl_sync(0xffffffffu, cand[r], li_now);
+                        val[r] = ((w[r] >> lane) & 1u) ? __ldg(ip + 32 * r + lane) : 0.0;
                     }
+#pragma unroll
+                    for (int r = 0; r < kQuadBlock / 32; ++r) {
+                        if ((w[r] >> lane) & 1u) {
+                            const int pos = (qn + __popc(w[r] & ((1u << lane) - 1u))) & (QN - 1);
+                            q[pos] = val[r];
+                            qsrc[pos] = uint16_t((32 * r + lane) | (li_now << 8));
+                        }
+                        qn += __popc(w[r]);
+                    }
+                    __syncwarp();
                 }
             }
-        }
-        if constexpr (NE > 0) {
-            while (qn > qh) run_pass(min(32, qn - qh));   // what is left of the unit
+            if (qn == qh) break;
+            if constexpr (NE > 0) run_pass(min(32, qn - qh));
+            else qh = qn;
         }
 
         // ---- close the unit ----
