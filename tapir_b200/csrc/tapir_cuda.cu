@@ -336,16 +336,21 @@ int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0
     const int64_t s0 = p->offsets[l0], s1 = p->offsets[l1];
     const int64_t nnz = s1 - s0, L = l1 - l0;
     if (nnz <= 0 || L <= 0) return 32;
-    const int64_t n_sample = std::min<int64_t>(nnz, 16384);
-    const double stride = double(nnz) / double(n_sample);
-    int64_t n_act = 0, n_ge16 = 0, n_ge32 = 0;
-    for (int64_t i = 0; i < n_sample; ++i) {
-        const double r = p->rates[s0 + int64_t(double(i) * stride)];
-        const double a = 16.0 * (r * r);
-        if (!(std::fabs(a) <= DBL_MAX) || a == 0.0) continue;
-        ++n_act;
-        if (!(r >= 0.0 && r < mom_rate_bound(16))) ++n_ge16;
-        if (!(r >= 0.0 && r < mom_rate_bound(32))) ++n_ge32;
+    // 64 runs of 64 consecutive rates spread over the batch: 4,096 samples from ~500 cache lines of the (pinned) host
+    // array -- a strided sample of the same size costs a cache miss per rate, a millisecond on a call that takes one
+    const int64_t run_len = 64, n_runs = std::min<int64_t>(64, std::max<int64_t>(1, nnz / run_len));
+    int64_t n_sample = 0, n_act = 0, n_ge16 = 0, n_ge32 = 0;
+    for (int64_t k = 0; k < n_runs; ++k) {
+        const int64_t b0 = s0 + int64_t(double(k) * double(nnz - std::min(nnz, run_len)) / double(std::max<int64_t>(1, n_runs - 1)));
+        for (int64_t i = b0; i < std::min(s1, b0 + run_len); ++i) {
+            const double r = p->rates[i];
+            ++n_sample;
+            const double a = 16.0 * (r * r);
+            if (!(std::fabs(a) <= DBL_MAX) || a == 0.0) continue;
+            ++n_act;
+            if (!(r >= 0.0 && r < mom_rate_bound(16))) ++n_ge16;
+            if (!(r >= 0.0 && r < mom_rate_bound(32))) ++n_ge32;
+        }
     }
     if (n_act == 0) return 32;
     const double sites = double(nnz) / double(L);                              // sites per locus
@@ -653,7 +658,35 @@ void drop_graph(Lane& ln)
 }
 
 // Build the work lists of loci [l0, l1) of an already validated problem on lane `ln` and start their H2D copies.
-int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l0, int64_t l1, bool sync)
+// Which profile kernel a call runs: decided ONCE per call from the whole batch (tile size and form from the grid and
+// the mean locus, moments per block from a sample of the rates), so that every chunk of a pipelined tapir_cuda_run
+// uses the same kernel -- results do not depend on how a batch was cut -- and the sampling is not paid per chunk.
+struct Decision {
+    int rh = 1;
+    bool mom_form = false;
+    int mom_terms = 32;
+    bool fp32 = false;
+};
+
+Decision decide_batch(const tapir_cuda_ctx* ctx, const tapir_problem* p)
+{
+    Decision d;
+    const int64_t L = p->n_loci, nnz = L ? p->offsets[L] : 0, T = p->n_grid;
+    choose_tile(ctx, p, std::max<int64_t>(T, 1), L ? double(nnz) / double(L) : 1.0, d.rh, d.mom_form);
+    d.fp32 = ((p->flags & TAPIR_FP32_MODE) || ctx->force_fp32) && T > 0 && L > 0 && !ctx->prof_trace;
+    if (d.fp32) {   // profile_f32_kernel: 1,024-point tiles, moment form
+        d.rh = 4;
+        d.mom_form = true;
+    }
+    const int64_t TT = 256 * d.rh;
+    const int n_tiles = int(std::max<int64_t>(1, (T + TT - 1) / TT));
+    d.mom_terms = d.mom_form ? choose_moments(ctx, p, 0, L, d.rh, n_tiles) : 32;
+    if (ctx->prof_trace) d.mom_terms = 32;   // (the trace instantiation exists for 32 moments only)
+    if (d.fp32) d.mom_terms = kF32Terms;
+    return d;
+}
+
+int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l0, int64_t l1, bool sync, const Decision& dec)
 {
     ln.plan.valid = false;
     drop_graph(ln);
@@ -666,19 +699,14 @@ int lane_upload(tapir_cuda_ctx* ctx, Lane& ln, const tapir_problem* p, int64_t l
     plan.E = p->n_epochs;
     plan.flags = p->flags;
     plan.nnz = plan.L ? off[plan.L] - base : 0;
-    choose_tile(ctx, p, std::max<int64_t>(plan.T, 1), plan.L ? double(plan.nnz) / double(plan.L) : 1.0, plan.rh, plan.mom_form);
-    plan.fp32 = ((p->flags & TAPIR_FP32_MODE) || ctx->force_fp32) && plan.T > 0 && plan.L > 0 && !ctx->prof_trace;
-    if (plan.fp32) {   // profile_f32_kernel: 1,024-point tiles, moment form
-        plan.rh = 4;
-        plan.mom_form = true;
-    }
+    plan.rh = dec.rh;
+    plan.mom_form = dec.mom_form;
+    plan.fp32 = dec.fp32 && plan.L > 0;
     plan.TT = 32 * 8 * plan.rh;
     plan.n_tiles = int32_t(std::max<int64_t>(1, (plan.T + plan.TT - 1) / plan.TT));
     // epochs whose sums come out of the profile's moments (mom_epoch.h); the others, and the sites outside an
     // epoch's rate range, are integrated per site by quad_kernel
-    plan.mom_terms = plan.mom_form ? choose_moments(ctx, p, l0, l1, plan.rh, plan.n_tiles) : 32;
-    if (ctx->prof_trace) plan.mom_terms = 32;   // (the trace instantiation exists for 32 moments only)
-    if (plan.fp32) plan.mom_terms = kF32Terms;
+    plan.mom_terms = dec.mom_terms;
     const double class_x = plan.fp32 ? kMomClassF32 : mom_class_x(plan.mom_terms);
     plan.mom.assign(size_t(plan.E), MomEpochPlan());
     plan.n_mom = 0;
@@ -1298,7 +1326,7 @@ int tapir_cuda_upload(tapir_cuda_ctx* ctx, const tapir_problem* p)
     if (rc) return rc;
     ctx->lanes[0].plan.valid = false;
     if ((rc = validate(ctx, p)) != TAPIR_OK) return rc;
-    return lane_upload(ctx, ctx->lanes[0], p, 0, p->n_loci, true);
+    return lane_upload(ctx, ctx->lanes[0], p, 0, p->n_loci, true, decide_batch(ctx, p));
 }
 
 int tapir_cuda_compute(tapir_cuda_ctx* ctx, tapir_timing* timing)
@@ -1370,6 +1398,7 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
     }
     n_chunks = int64_t(cut.size());
     const int n_lanes = ctx->n_lanes;
+    const Decision dec = decide_batch(ctx, p);
     const double t_host0 = now_us();
     if (ctx->trace) CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream_h2d));
     int64_t l0 = 0;
@@ -1383,7 +1412,7 @@ int tapir_cuda_run(tapir_cuda_ctx* ctx, const tapir_problem* p, const tapir_resu
         Lane& ln = ctx->lanes[k % n_lanes];
         if (k >= n_lanes && (rc = lane_finish(ctx, ln)) != TAPIR_OK) break;  // its previous chunk (and its staging) is done
         if (ctx->trace) ln.host_us[0] = now_us() - t_host0;
-        if ((rc = lane_upload(ctx, ln, p, l0, l1, false)) != TAPIR_OK) break;
+        if ((rc = lane_upload(ctx, ln, p, l0, l1, false, dec)) != TAPIR_OK) break;
         ln.pending_row0 = l0;
         if (ctx->trace) ln.host_us[1] = now_us() - t_host0;
         if ((rc = lane_compute(ctx, ln, nullptr, false, false)) != TAPIR_OK) break;
