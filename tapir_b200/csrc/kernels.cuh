@@ -584,6 +584,64 @@ __device__ __forceinline__ void prof_epilogue(const ProfArgs& args, const double
     }
 }
 
+// The same for a sub-tile of 256 RH points that starts at grid point T0 (profile_mom_kernel's 1,024-point halves of a
+// 2,048-point tile): values times t into `row` (the locus' row of pi_net) with the running maximum of the lane kept in
+// best_bits / best_t for the caller to close, or -- raw -- the partial sums into `raw` (split workspace, at the sub-tile).
+template <int RH>
+__device__ __forceinline__ void prof_epilogue_at(const ProfArgs& args, const double (&acc)[4][RH][2], double* row, double* raw,
+                                                 int64_t T0, int lane, long long& best_bits, int64_t& best_t)
+{
+    constexpr int TT = ProfCfg<RH>::TT;
+    const int fk = lane & 3, fg = lane >> 2;
+    const double t0d = double(T0);
+    const int lo0 = 4 * chunk_pair(fg);
+    if (raw) {
+#pragma unroll
+        for (int j = 0; j < RH; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
+                double* o = raw + hi * 32 + lo0;
+                *reinterpret_cast<double2*>(o) = make_double2(acc[0][j][c], acc[1][j][c]);
+                *reinterpret_cast<double2*>(o + 2) = make_double2(acc[2][j][c], acc[3][j][c]);
+            }
+        return;
+    }
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    const int64_t t_left = args.T - T0;
+    const int t_end = int(t_left < int64_t(TT) ? (t_left < 0 ? 0 : t_left) : int64_t(TT));
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < RH; ++j) {
+            const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
+            const int o = hi * 32 + lo0;
+            const double td = t0d + double(o);
+            double v[4];
+            v[0] = acc[0][j][c] * td;
+            v[1] = acc[1][j][c] * (td + 1.0);
+            v[2] = acc[2][j][c] * (td + 2.0);
+            v[3] = acc[3][j][c] * (td + 3.0);
+            double* dst = row + T0 + o;
+            if (o + 3 < t_end && vec_ok) {
+                *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+                *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (o + i < t_end) dst[i] = v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long bits = __double_as_longlong(v[i]);
+                if (o + i < t_end && bits > best_bits) {   // offsets rise within a lane: the first maximum is kept
+                    best_bits = bits;
+                    best_t = T0 + o + i;
+                }
+            }
+        }
+}
+
 // ------------------------------------------------------------------------------------------
 // PI profile, moment form
 // ------------------------------------------------------------------------------------------
@@ -625,14 +683,18 @@ struct MomCfg {
     static constexpr int TT = ProfCfg<RH>::TT, NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
     static constexpr int MS = KM + 2;  // doubles per moment row (+ 2: rows 16 bytes off a multiple of 128, conflict-free 16-byte fragments)
     static constexpr int Tables = 32 * MS + 32 * WA;
-    static constexpr int Lin = kLinBlock * NB;   // moments -> times scratch, one padded row per 128-point block
-    static constexpr int Pow = 16 * (kUStride + ProfCfg<RH>::WStride);   // 16-site power tables of the fast-site pass
+    // moments -> times, the fast sites and the epilogue work on sub-tiles of 256 QR points, so that the accumulators of a
+    // 2,048-point tile (128 registers) never exist at once: twelve warps per SM instead of eight
+    static constexpr int QR = (RH == 8) ? 4 : RH, NH = RH / QR, QNB = 2 * QR;
+    static constexpr int Lin = kLinBlock * QNB;   // moments -> times scratch, one padded row per 128-point block
+    static constexpr int Pow = 16 * (kUStride + ProfCfg<QR>::WStride);   // 16-site power tables of the fast-site pass
     static constexpr int FastOff = (Tables > Lin ? Tables : Lin) > Pow ? (Tables > Lin ? Tables : Lin) : Pow;
     static constexpr int QueueOff = FastOff + 32;
     static constexpr int WarpDoubles = QueueOff + 64;
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
-    static constexpr int MinBlocks = (RH == 4 ? 14 : 8) / kProfWarps;  // 144 / 255 registers
-    static_assert(16 * (kUStride + ProfCfg<RH>::WStride) <= FastOff, "16-site power tables fit below the fast-site list");
+    static constexpr int MinBlocks = (RH == 4 ? 14 : 12) / kProfWarps;  // 144 / 168 registers
+    static_assert(Pow <= FastOff, "16-site power tables fit below the fast-site list");
+    static_assert(NT == 1 || NT == 2, "one or two column tiles");
     static_assert(KM * (NB + 4) <= FastOff, "moment scratch fits");
     static_assert(KM == 16 || KM == 32, "16 or 32 moments per block");
     static_assert((kLinBlock * 8) % 16 == 0, "16-byte reads of the scratch stay aligned");
@@ -652,7 +714,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
 {
     using Cfg = ProfCfg<RH>;
     using Mom = MomCfg<RH, KM>;
-    constexpr int TT = Cfg::TT, WS = Cfg::WStride, US = kUStride, MS = Mom::MS;
+    constexpr int TT = Cfg::TT, WS = ProfCfg<Mom::QR>::WStride, US = kUStride, MS = Mom::MS;
     constexpr int MI = KM / 8;   // moments per fragment row (moment = MI * mrow(fg) + i)
     constexpr int KS = KM / 4;   // k-steps of the moments -> times product
     constexpr uint32_t kBound = mom_bound_hi<KM>();
@@ -664,12 +726,13 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
     const int fk = lane & 3, fg = lane >> 2;
     double* Us = smem + size_t(warp) * Mom::WarpDoubles;
     double* Qs = Us + Mom::QueueOff;
-    // fast-site pass: power tables of 16 sites, U [16][US] then W [16][WS]
+    // fast-site pass: power tables of 16 sites in the sub-tile's geometry, U [16][US] then W [16][WS]
+    constexpr int QR = Mom::QR, NH = Mom::NH, QTT = 256 * QR;
     double* Ws = Us + 16 * US;
     double* myU = Us + (lane & 15) * US;
     double* myW = Ws + (lane & 15) * WS;
     const double* fragU = Us + fk * US + 4 * chunk_pair(fg);
-    const double* fragW = Ws + fk * WS + RH * w_chunk<RH>(fg);
+    const double* fragW = Ws + fk * WS + QR * w_chunk<QR>(fg);
     // moment pass: U' [32][MS] where profile_kernel keeps U (same stride), W' [32][WA] behind it
     double* myM = Us + lane * MS;
     double* WAs = Us + 32 * MS;
@@ -822,12 +885,11 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
         }
         stamp(17);
 
-        // ---------------- moments -> times, natural layout [128 hb + t], then into the accumulator layout ----------------
-        double acc[4][RH][2];
+        // ---------------- moments -> B fragments, the slow sites' epoch sums ----------------
+        double bf[KS][NT];  // B fragments: M[4 ks + fk][8 nt + fg] / k!
         {
             constexpr int SA = NB + 4;
             double* MA = Us;   // [KM][SA]
-            double* lin = Us;  // [TT], once the B fragments are in registers
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -836,7 +898,6 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                     for (int c = 0; c < 2; ++c)
                         MA[(MI * mrow + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c] + accB[i][j][c];
             __syncwarp();
-            double bf[KS][NT];  // B fragments: M[4 ks + fk][8 nt + fg]
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -879,94 +940,122 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                 for (int nt = 0; nt < NT; ++nt) bf[ks][nt] *= f;
             }
             __syncwarp();
-            // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact), one multiply per step;
-            // eight row tiles at a time, so that the eight DMMAs of a tile are not one dependent chain
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                double pw[8], x4[8], d[8][NT][2];
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const double x = double(8 * (8 * half + m) + fg - 64) * 0.015625;
-                    const double xx = x * x;
-                    x4[m] = xx * xx;
-                    pw[m] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;  // x^fk
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) d[m][nt][0] = d[m][nt][1] = 0.0;
-                }
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) dmma884(d[m][nt][0], d[m][nt][1], pw[m], bf[ks][nt]);
-                        pw[m] *= x4[m];  // -> x^(k+4), k = 4 ks + fk
-                    }
-                }
-#pragma unroll
-                for (int m = 0; m < 8; ++m)
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) lin[kLinBlock * (8 * nt + 2 * fk + c) + 8 * (8 * half + m) + fg] = d[m][nt][c];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < RH; ++j)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int hi = RH * w_chunk<RH>(2 * fk + c) + j;
-                    const double* src = lin + kLinBlock * (hi >> 2) + 32 * (hi & 3) + 4 * chunk_pair(fg);
-                    const double2 v01 = *reinterpret_cast<const double2*>(src);
-                    const double2 v23 = *reinterpret_cast<const double2*>(src + 2);
-                    acc[0][j][c] = v01.x; acc[1][j][c] = v01.y; acc[2][j][c] = v23.x; acc[3][j][c] = v23.y;
-                }
-            __syncwarp();
         }
         stamp(18);
 
-        // ---------------- the item's fast sites, power tables as in profile_kernel ----------------
-        if (n_fast > 0 && n_fast <= 32) {
-            for (int g0 = 0; g0 < n_fast; g0 += 16) {
-                const int cnt = min(16, n_fast - g0);
-                if (lane < 16) prof_build_tables<RH>((lane < cnt) ? Fs[g0 + lane] : 0.0, lane < cnt, T0, t0d, myU, myW);
-                __syncwarp();
-                prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
-                __syncwarp();
-            }
-        } else if (n_fast > 32) {
-            int qh = 0, qn = 0;
-            double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
-            double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
-            for (int base = 0;; base += 32) {
-                const bool more = base < item.n_sites;
-                if (more) {
-                    const double lam_new = lam_in;
-                    lam_in = lam_in2;
-                    {
-                        const int nb = base + 64 + lane;
-                        lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+        // ---------------- per sub-tile of 256 QR points: moments -> times, the fast sites, the epilogue ----------------
+        long long best_bits = -1;
+        int64_t best_t = T0;
+#pragma unroll 1
+        for (int h = 0; h < NH; ++h) {
+            const int64_t T0q = T0 + int64_t(h) * QTT;
+            const double t0q = double(T0q);
+            double acc[4][QR][2];
+            {
+                double* lin = Us;  // [QNB][kLinBlock]: natural layout [128 hb + t], then into the accumulator layout
+                double bq[KS];     // this sub-tile's column tile of the B fragments
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) bq[ks] = (NT == 1 || h == 0) ? bf[ks][0] : bf[ks][NT - 1];
+                // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact), one
+                // multiply per step; eight row tiles at a time, so that the DMMAs of a tile are not one dependent chain
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    double pw[8], x4[8], d[8][2];
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) {
+                        const double x = double(8 * (8 * half + m) + fg - 64) * 0.015625;
+                        const double xx = x * x;
+                        x4[m] = xx * xx;
+                        pw[m] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;  // x^fk
+                        d[m][0] = d[m][1] = 0.0;
                     }
-                    const bool fast = rate_is_active(lam_new) && !rate_is_slow(lam_new, kBound);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, fast);
-                    if (fast) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
-                    qn += __popc(ballot);
-                    __syncwarp();
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) {
+                            dmma884(d[m][0], d[m][1], pw[m], bq[ks]);
+                            pw[m] *= x4[m];  // -> x^(k+4), k = 4 ks + fk
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < 8; ++m)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) lin[kLinBlock * (2 * fk + c) + 8 * (8 * half + m) + fg] = d[m][c];
                 }
-                while (qn - qh >= 16 || (!more && qn > qh)) {
-                    const int cnt = min(16, qn - qh);
-                    const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
-                    qh += cnt;
-                    __syncwarp();
-                    if (lane < 16) prof_build_tables<RH>(lam, lane < cnt, T0, t0d, myU, myW);
-                    __syncwarp();
-                    prof_contract<RH>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
-                    __syncwarp();
-                }
-                if (!more) break;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < QR; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int hi = QR * w_chunk<QR>(2 * fk + c) + j;
+                        const double* src = lin + kLinBlock * (hi >> 2) + 32 * (hi & 3) + 4 * chunk_pair(fg);
+                        const double2 v01 = *reinterpret_cast<const double2*>(src);
+                        const double2 v23 = *reinterpret_cast<const double2*>(src + 2);
+                        acc[0][j][c] = v01.x; acc[1][j][c] = v01.y; acc[2][j][c] = v23.x; acc[3][j][c] = v23.y;
+                    }
+                __syncwarp();
             }
+
+            // the item's fast sites, power tables as in profile_kernel (sub-tile geometry)
+            if (n_fast > 0 && n_fast <= 32) {
+                for (int g0 = 0; g0 < n_fast; g0 += 16) {
+                    const int cnt = min(16, n_fast - g0);
+                    if (lane < 16) prof_build_tables<QR>((lane < cnt) ? Fs[g0 + lane] : 0.0, lane < cnt, T0q, t0q, myU, myW);
+                    __syncwarp();
+                    prof_contract<QR>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
+                    __syncwarp();
+                }
+            } else if (n_fast > 32) {
+                int qh = 0, qn = 0;
+                double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
+                double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
+                for (int base = 0;; base += 32) {
+                    const bool more = base < item.n_sites;
+                    if (more) {
+                        const double lam_new = lam_in;
+                        lam_in = lam_in2;
+                        {
+                            const int nb = base + 64 + lane;
+                            lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                        }
+                        const bool fast = rate_is_active(lam_new) && !rate_is_slow(lam_new, kBound);
+                        const unsigned ballot = __ballot_sync(0xffffffffu, fast);
+                        if (fast) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                        qn += __popc(ballot);
+                        __syncwarp();
+                    }
+                    while (qn - qh >= 16 || (!more && qn > qh)) {
+                        const int cnt = min(16, qn - qh);
+                        const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
+                        qh += cnt;
+                        __syncwarp();
+                        if (lane < 16) prof_build_tables<QR>(lam, lane < cnt, T0q, t0q, myU, myW);
+                        __syncwarp();
+                        prof_contract<QR>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
+                        __syncwarp();
+                    }
+                    if (!more) break;
+                }
+            }
+            prof_epilogue_at<QR>(args, acc, args.pi_net + int64_t(item.locus) * args.T,
+                                 item.slot >= 0 ? args.ws + size_t(item.slot) * TT + size_t(h) * QTT : nullptr, T0q, lane,
+                                 best_bits, best_t);
+            __syncwarp();
         }
         stamp(19);
-        prof_epilogue<RH>(args, acc, item.locus, item.tile, item.slot, lane);
+        if (item.slot < 0) {   // the tile's maximum over its sub-tiles and lanes (first maximum, as numpy.argmax)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const long long ob = __shfl_xor_sync(0xffffffffu, best_bits, off);
+                const int64_t ot = __shfl_xor_sync(0xffffffffu, best_t, off);
+                if (ob > best_bits || (ob == best_bits && ot < best_t)) { best_bits = ob; best_t = ot; }
+            }
+            if (lane == 0) {
+                const int64_t k = int64_t(item.locus) * args.n_tiles + item.tile;
+                args.tile_max[k] = __longlong_as_double(best_bits);
+                args.tile_arg[k] = best_t;
+            }
+        }
         stamp(20);
         if constexpr (TRACE) {
             if (lane == 0 && n_done == 1) { tr[22] = n_groups; tr[24] = n_fast; }
