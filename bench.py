@@ -639,6 +639,10 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     step_ms, kernel_ms, launches, tm = timed_steps(eng, sb, args.steps, args.warmup, barrier)
+    per_rank_ms = [step_ms]
+    if dist is not None:
+        per_rank_ms = [None] * world
+        dist.all_gather_object(per_rank_ms, step_ms)
     step_ms = allmax(step_ms)
 
     # ---- correctness of exactly what was timed: the resident batch's results ----
@@ -752,7 +756,7 @@ def run_ours(args, rank, world, local_rank):
                                        world, "NVLink peer-memory push fused after finalize (CUDA IPC)" if mode == "push"
                                        else "one NCCL gather per step")) if world > 1 else "single GPU",
                    "partition": {"sites_per_rank_max_over_mean": float(loads.max() / loads.mean())}},
-        "loci_per_s": L / (step_ms * 1e-3),
+        "loci_per_s": L / (step_ms * 1e-3), "ms_per_step_per_rank": [round(float(x), 4) for x in per_rank_ms],
         "kernel_ms": dict(kernel_ms, note="per-kernel times from a separate pass with the kernels serialised on one stream "
                                           "(rank 0); ms_per_step is the shipped two-stream configuration"),
         "roofline": {

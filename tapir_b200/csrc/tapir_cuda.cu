@@ -327,18 +327,18 @@ void choose_tile(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t T, d
 // slow site and per item, but every site between the two bounds goes through the power-table pass of the fast sites,
 // and through quad_kernel for its epoch integrals).  Decided per batch from a strided sample of its rates: expected
 // FP64-pipe cycles per (locus, tile) item -- the fast groups weighted 2.5x for their exposed latency -- plus what the
-// per-site integrals of the sites outside the class cost in the same unit (~0.35 ns = 250 cycles each through the
-// chunked quad_kernel; profiles/r02_moments_sweep.txt, where the model's 16/32 ratio of the profile kernel is 0.77
-// against a measured 0.77 on config 5).
+// per-site integrals of the sites outside the class cost in the same unit (~0.17 ns = 135 cycles each through the
+// chunked quad_kernel).  On config 5 the model says 21.1 k against 24.9 k cycles per locus for 16 against 32 moments,
+// the measurement 14.1 against 16.8 ms per step (profiles/r02_moments_sweep.txt).
 int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0, int64_t l1, int rh, int n_tiles)
 {
     if (ctx->force_terms) return ctx->force_terms;
     const int64_t s0 = p->offsets[l0], s1 = p->offsets[l1];
     const int64_t nnz = s1 - s0, L = l1 - l0;
     if (nnz <= 0 || L <= 0) return 32;
-    // 64 runs of 64 consecutive rates spread over the batch: 4,096 samples from ~500 cache lines of the (pinned) host
+    // 128 runs of 64 consecutive rates spread over the batch: 8,192 samples from ~1,000 cache lines of the (pinned) host
     // array -- a strided sample of the same size costs a cache miss per rate, a millisecond on a call that takes one
-    const int64_t run_len = 64, n_runs = std::min<int64_t>(64, std::max<int64_t>(1, nnz / run_len));
+    const int64_t run_len = 64, n_runs = std::min<int64_t>(128, std::max<int64_t>(1, nnz / run_len));
     int64_t n_sample = 0, n_act = 0, n_ge16 = 0, n_ge32 = 0;
     for (int64_t k = 0; k < n_runs; ++k) {
         const int64_t b0 = s0 + int64_t(double(k) * double(nnz - std::min(nnz, run_len)) / double(std::max<int64_t>(1, n_runs - 1)));
@@ -361,7 +361,7 @@ int choose_moments(const tapir_cuda_ctx* ctx, const tapir_problem* p, int64_t l0
         const double groups16 = std::max(1.0 - std::exp(-n_fast), (n_fast + std::sqrt(n_fast)) / 16.0);
         const double fast = groups16 * 2.5 * (256.0 * rh + 220.0) * (n_fast > 24.0 ? 1.2 : 1.0);
         const double profile = n_slow * (0.5 * km * NT + (33.0 + km + NB) / 16.0) + 64.0 * km * NT + fast;
-        const double quad = p->n_epochs > 0 ? 250.0 * n_fast : 0.0;   // per-site integrals of the sites outside the class
+        const double quad = p->n_epochs > 0 ? 135.0 * n_fast : 0.0;   // per-site integrals of the sites outside the class
         return double(n_tiles) * profile + quad;
     };
     return cost(16, n_ge16) < cost(32, n_ge32) ? 16 : 32;
