@@ -109,7 +109,23 @@ struct ProfArgs {
     double* mom_int;      // [parts][e_total]
     int32_t n_mom_epochs;
     int32_t e_total;
+    // profile_mom_kernel: seeds of the A fragments of the moments -> times product, [16 row tiles][32 lanes][2]:
+    // entry (mt, lane) = {x^fk, x^4}, x = (8 mt + fg - 64)/64 (kMtPowDoubles doubles, filled by mt_pow_table; one
+    // 16-byte load per row tile, 512 contiguous bytes per warp)
+    const double* mt_pow;
 };
+constexpr int kMtPowDoubles = 16 * 32 * 2;
+// (x is exact; x^2, x^3, x^4 are formed as the kernel formed them in registers before the table existed)
+inline void mt_pow_table(double* out)
+{
+    for (int mt = 0; mt < 16; ++mt)
+        for (int lane = 0; lane < 32; ++lane) {
+            const int fk = lane & 3, fg = lane >> 2;
+            const double x = double(8 * mt + fg - 64) * 0.015625, xx = x * x;
+            out[(mt * 32 + lane) * 2] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;
+            out[(mt * 32 + lane) * 2 + 1] = xx * xx;
+        }
+}
 
 template <int RH>
 struct ProfCfg {
@@ -674,10 +690,22 @@ __device__ __constant__ double c_inv_fact[32] = {
     9.183689863795546e-29, 3.279889237069838e-30, 1.1309962886447716e-31, 3.7699876288159054e-33,
     1.216125041553518e-34};
 
+// the same table in global memory, for lane-varying indices (a constant-bank read with 32 different indices is serialised)
+__device__ const double g_inv_fact[32] = {
+    1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333, 0.001388888888888889,
+    0.0001984126984126984, 2.48015873015873e-05, 2.7557319223985893e-06, 2.755731922398589e-07,
+    2.505210838544172e-08, 2.08767569878681e-09, 1.6059043836821613e-10, 1.1470745597729725e-11,
+    7.647163731819816e-13, 4.779477332387385e-14, 2.8114572543455206e-15, 1.5619206968586225e-16,
+    8.22063524662433e-18, 4.110317623312165e-19, 1.9572941063391263e-20, 8.896791392450574e-22,
+    3.868170170630684e-23, 1.6117375710961184e-24, 6.446950284384474e-26, 2.4795962632247976e-27,
+    9.183689863795546e-29, 3.279889237069838e-30, 1.1309962886447716e-31, 3.7699876288159054e-33,
+    1.216125041553518e-34};
+
 // Shared memory of one warp of profile_mom_kernel: the moment tables U' [32][34] + W' [32][WA]; later, over them, the
 // scratch of the moments -> times step ([32][NB+4] moments, then [TT] times) and the 16-site power tables of the
 // fast-site pass; behind all of them the list of up to 32 fast rates (filled during the moment pass, read after the
-// scratch has been used) and the 64-entry compaction queue.  12.25 KB for RH = 4: sixteen warps per SM.
+// scratch has been used), the 64-entry compaction queue(s) and the slots of the rates in flight.  13.25 KB for RH = 4,
+// KM = 32: sixteen warps per SM.
 template <int RH, int KM = 32>
 struct MomCfg {
     static constexpr int TT = ProfCfg<RH>::TT, NB = TT / 128, NT = NB / 8, WA = (NB == 8) ? 12 : NB + 2;
@@ -690,12 +718,16 @@ struct MomCfg {
     static constexpr int Pow = 16 * (kUStride + ProfCfg<QR>::WStride);   // 16-site power tables of the fast-site pass
     static constexpr int FastOff = (Tables > Lin ? Tables : Lin) > Pow ? (Tables > Lin ? Tables : Lin) : Pow;
     static constexpr int QueueOff = FastOff + 32;
-    static constexpr int WarpDoubles = QueueOff + 64;
+    // 2,048-point tiles keep two classes of slow sites (see profile_mom_kernel): a second 64-entry ring for the coarse one
+    static constexpr bool Coarse = (NT == 2);
+    // behind the rings: four slots of 32 rates for the rounds in flight from global memory (cp.async, lane-private)
+    static constexpr int RateOff = QueueOff + (Coarse ? 128 : 64);
+    static constexpr int WarpDoubles = RateOff + 4 * 32;
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
     static constexpr int MinBlocks = (RH == 4 ? 14 : 12) / kProfWarps;  // 144 / 168 registers
     static_assert(Pow <= FastOff, "16-site power tables fit below the fast-site list");
     static_assert(NT == 1 || NT == 2, "one or two column tiles");
-    static_assert(KM * (NB + 4) <= FastOff, "moment scratch fits");
+    static_assert(KM * (NB + 4) + (Coarse ? KM * 12 : 0) <= FastOff, "moment scratch fits");
     static_assert(KM == 16 || KM == 32, "16 or 32 moments per block");
     static_assert((kLinBlock * 8) % 16 == 0, "16-byte reads of the scratch stay aligned");
 };
@@ -705,6 +737,98 @@ struct MomCfg {
 __device__ __forceinline__ bool rate_is_slow(double r, uint32_t bound_hi) { return uint32_t(__double2hiint(r)) < bound_hi; }
 template <int KM>
 __device__ __forceinline__ constexpr uint32_t mom_bound_hi() { return KM == 16 ? 0x3F740000u : 0x3F940000u; }
+
+// Position of column hb of an eight-column W' table inside rows that are 18 doubles apart (the stride of the
+// sixteen-column table of the same kernel): 0 1 8 9 2 3 10 11.  The 8-byte fragment loads of a half warp (four rows fk,
+// four columns) then fall on sixteen different banks -- in natural order rows 2 banks apart collide two-way -- and the
+// pairs (hb, hb + 1) stay adjacent for the 16-byte stores.
+template <bool Swz>
+__device__ __forceinline__ constexpr int wcol(int hb)
+{
+    return Swz ? ((hb & 1) | ((hb & 2) << 2) | ((hb & 4) >> 1)) : hb;
+}
+
+// One group of up to 32 slow sites of profile_mom_kernel's moment pass, for a class with NG column tiles: blocks of
+// TT / (8 NG) points (half-length HB), the group's tables U' [32][MS] (moments u0 z^k, z = -HB c) and W' [32][WA]
+// (q^HB (q^2HB)^hb) built in the warp's shared memory, then  acE/acO[i][j][c] += U'^T W'  on the FP64 MMA path.
+template <int KM, int NG, int TT, int WA, int MS>
+__device__ __forceinline__ void mom_group(const double lam, const int cnt, const int lane, const int64_t T0, const double t0d,
+                                          double* myM, double* myWA, const double* fragM, const double* WAs,
+                                          double (&acE)[KM / 8][NG][2], double (&acO)[KM / 8][NG][2])
+{
+    constexpr int MI = KM / 8;
+    constexpr int GB = 8 * NG;                   // blocks of this class per tile
+    constexpr double HB = double(TT / GB / 2);   // 64 (fine) or 128 (coarse)
+    constexpr bool Swz = (NG == 1 && WA == 18);  // eight columns in rows made for sixteen: see wcol
+    const int fk = lane & 3, fg = lane >> 2;
+    {
+        // rows of lanes >= cnt: moments 0, W' = 1
+        const bool ok = lane < cnt;
+        const double c = ok ? 4.0 * lam : 0.0;
+        const double a = ok ? 16.0 * (lam * lam) : 0.0;
+        const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
+        // q^HB directly (HB c inside the class bound): one bounded exponential instead of exp(-c) and squarings
+        const double z = -HB * c;
+        const double q1 = exp_bounded_short(z), q2 = q1 * q1, q4 = q2 * q2;
+        // moments u0 z^k (the 1/k! lives in the moments -> times step): four chains of stride 4
+        const double z2 = z * z, z4 = z2 * z2;
+        double m0 = u0, m1 = u0 * z, m2 = u0 * z2, m3 = m1 * z2;
+#pragma unroll
+        for (int k = 0; k < KM / 4; ++k) {
+            st_shared_v2(myM + 4 * k, m0, m1);
+            st_shared_v2(myM + 4 * k + 2, m2, m3);
+            m0 *= z4; m1 *= z4; m2 *= z4; m3 *= z4;
+        }
+        // W'[hb] = q^HB (q^(2 HB))^hb, two chains of stride 4; column hb at position wcol<Swz>(hb)
+        const double q8 = q4 * q4;
+        double w = q1, v = q1 * q4;
+#pragma unroll
+        for (int k = 0; k < GB / 4; ++k) {
+            st_shared_v2(myWA + wcol<Swz>(4 * k), w, w * q2);
+            st_shared_v2(myWA + wcol<Swz>(4 * k + 2), v, v * q2);
+            w *= q8; v *= q8;
+        }
+    }
+    __syncwarp();
+    {
+        const double* fragWG = WAs + fk * WA + (Swz ? wcol<true>(fg) : NG * w_chunk<NG>(fg));
+        auto fetch = [&](double (&a)[MI], double (&b)[NG], int step) {
+            const double* mp = fragM + step * (4 * MS);
+            const double2 m01 = *reinterpret_cast<const double2*>(mp);
+            a[0] = m01.x; a[1] = m01.y;
+            if constexpr (MI == 4) {
+                const double2 m23 = *reinterpret_cast<const double2*>(mp + 2);
+                a[2] = m23.x; a[3] = m23.y;
+            }
+            const double* wp = fragWG + step * (4 * WA);
+            if constexpr (NG == 1) {
+                b[0] = wp[0];
+            } else {
+#pragma unroll
+                for (int r = 0; r < NG / 2; ++r) {
+                    const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
+                    b[2 * r] = v.x; b[2 * r + 1] = v.y;
+                }
+            }
+        };
+        auto mma_step = [&](double (&ac)[MI][NG][2], const double (&a)[MI], const double (&b)[NG]) {
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NG; ++j) dmma884(ac[i][j][0], ac[i][j][1], a[i], b[j]);
+        };
+        const int nk = (cnt + 3) >> 2;  // rows past cnt are zero, so an odd count rounds up
+        double a0[MI], b0[NG], a1[MI], b1[NG];
+        fetch(a0, b0, 0);
+        for (int st = 0; st < nk; st += 2) {
+            fetch(a1, b1, st + 1);
+            mma_step(acE, a0, b0);
+            fetch(a0, b0, min(st + 2, 7));
+            mma_step(acO, a1, b1);
+        }
+    }
+    __syncwarp();
+}
 
 // TRACE (measurement only): [0] SM id, [1] entry, [12] exit, [13] items done; for the warp's second item
 // [16] claimed, [17] moment pass done, [18] moments -> times done, [19] fast-site pass done, [20] epilogue done,
@@ -737,7 +861,9 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
     double* myM = Us + lane * MS;
     double* WAs = Us + 32 * MS;
     double* myWA = WAs + lane * WA;
-    const int mrow = (MI == 4) ? chunk_pair(fg) : fg;   // 16-byte chunks of a row: MI = 2 needs no permutation
+    // 16-byte chunks of a moment row, permuted so that the eight lanes of a quarter warp (four rows fk, two values of fg)
+    // read eight different bank groups: rows are 8 + 1 (MI = 2) or 16 + 1 (MI = 4) chunks apart
+    const int mrow = (MI == 4) ? chunk_pair(fg) : chunk_quad(fg);
     const double* fragM = Us + fk * MS + MI * mrow;
     const double* fragWA = WAs + fk * WA + NT * w_chunk<NT>(fg);
     double* Fs = Us + Mom::FastOff;  // up to 32 fast rates of the item, behind everything that is written before they are read
@@ -759,6 +885,22 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
         }
     };
 
+    // TRACE: cycles of the second item spent in [0] the groups of the moment pass, [1] moments -> times, [2] the fast
+    // sites, [3] the epilogue (sums over groups / sub-tiles; words 25..28)
+    long long t_sum[4] = {0, 0, 0, 0}, t_mark = 0;
+    auto tick = [&]() {
+        if constexpr (TRACE) {
+            __syncwarp();
+            t_mark = clock64();
+        }
+    };
+    auto tock = [&](int k) {
+        if constexpr (TRACE) {
+            __syncwarp();
+            if (n_done == 1) t_sum[k] += clock64() - t_mark;
+        }
+    };
+
     for (;;) {
         uint32_t it = 0;
         if (lane == 0) it = atomicAdd(args.counter, 1u);
@@ -774,111 +916,85 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
         // ---------------- moment pass: slow sites ----------------
         // accA[i][j][c]: moment = MI mrow + i, hb = NT w_chunk<NT>(2 fk + c) + j
         // (two sets, for the even and the odd k-steps: with NT = 1 a single set is a dependent chain of four DMMAs)
+        // 2,048-point tiles (Coarse): a site with 128 c inside the class bound -- half the rate bound -- is expanded on
+        // the eight 256-point blocks of the tile instead (accP/accQ, the same KM moments in z = -128 c: one column tile,
+        // half the DMMAs and half the W' table); the coarse moments are shifted onto the 128-point blocks after the pass.
+        constexpr bool Coarse = Mom::Coarse;
         double accA[MI][NT][2], accB[MI][NT][2];
+        double accP[MI][1][2], accQ[MI][1][2];   // unused (and removed) without the coarse class
 #pragma unroll
-        for (int i = 0; i < MI; ++i)
+        for (int i = 0; i < MI; ++i) {
 #pragma unroll
             for (int j = 0; j < NT; ++j) accA[i][j][0] = accA[i][j][1] = accB[i][j][0] = accB[i][j][1] = 0.0;
+            accP[i][0][0] = accP[i][0][1] = accQ[i][0][0] = accQ[i][0][1] = 0.0;
+        }
         int n_fast = 0;
+        bool any_coarse = false;
         {
-            int qh = 0, qn = 0;
-            // rates are fetched four rounds ahead: a group of this pass lasts about as long as one DRAM access
-            constexpr int kAhead = 4;
-            double lam_q[kAhead];
+            int qh = 0, qn = 0, ph = 0, pn = 0;   // rings: fine class (Qs), coarse class (Ps)
+            double* Ps = Qs + 64;
+            // Rates are fetched three rounds ahead, asynchronously into lane-private shared-memory slots (a register
+            // queue must be shifted every round, and the shift waits for the load issued one round earlier: rounds
+            // without a group in between then expose the whole DRAM latency).  One commit group per round, issued or
+            // empty, so that "all but the newest two" always means this round's rates have landed; four slots, so the
+            // slot a round refills is never the one it has just read.
+            constexpr int kAhead = 3;
+            double* ring = Us + Mom::RateOff + lane;
+            auto fetch_round = [&](int r) {   // rates [32 r, 32 r + 32) of the item -> slot r mod 4; zeros past the item
+                const int i = 32 * r + lane;
+                const bool in = i < item.n_sites;
+                const unsigned dst = unsigned(__cvta_generic_to_shared(ring + 32 * (r & 3)));
+                const double* src = in ? rp + i : rp;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(in ? 8 : 0) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
 #pragma unroll
-            for (int k = 0; k < kAhead; ++k) lam_q[k] = (32 * k + lane < item.n_sites) ? __ldg(rp + 32 * k + lane) : 0.0;
-            for (int base = 0;; base += 32) {
+            for (int k = 0; k < kAhead; ++k) fetch_round(k);
+            for (int base = 0, rnd = 0;; base += 32, ++rnd) {
                 const bool more = base < item.n_sites;
                 if (more) {
-                    const double lam_new = lam_q[0];
-#pragma unroll
-                    for (int k = 0; k + 1 < kAhead; ++k) lam_q[k] = lam_q[k + 1];
-                    {
-                        const int nb = base + 32 * kAhead + lane;
-                        lam_q[kAhead - 1] = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
-                    }
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");
+                    const double lam_new = ring[32 * (rnd & 3)];
+                    fetch_round(rnd + kAhead);
                     const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
                     const bool slow = act && rate_is_slow(lam_new, kBound);
-                    const unsigned ballot = __ballot_sync(0xffffffffu, slow);
+                    const bool coarse = Coarse && act && rate_is_slow(lam_new, kBound - 0x00100000u);   // half the bound
+                    const unsigned ballot = __ballot_sync(0xffffffffu, slow && !coarse);
                     {   // the first 32 fast sites are kept aside, so that their pass need not stream the item again
                         const unsigned bf = __ballot_sync(0xffffffffu, act && !slow);
                         const int pos = n_fast + __popc(bf & ((1u << lane) - 1u));
                         if (act && !slow && pos < 32) Fs[pos] = lam_new;
                         n_fast += __popc(bf);
                     }
-                    if (slow) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                    if (slow && !coarse) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
                     qn += __popc(ballot);
+                    if constexpr (Coarse) {
+                        const unsigned bc = __ballot_sync(0xffffffffu, coarse);
+                        if (coarse) Ps[(pn + __popc(bc & ((1u << lane) - 1u))) & 63] = lam_new;
+                        pn += __popc(bc);
+                    }
                     __syncwarp();
+                }
+                if constexpr (Coarse) {
+                    while (pn - ph >= 32 || (!more && pn > ph)) {
+                        const int cnt = min(32, pn - ph);
+                        const double lam = (lane < cnt) ? Ps[(ph + lane) & 63] : 0.0;
+                        ph += cnt;
+                        any_coarse = true;
+                        ++n_groups;
+                        tick();
+                        mom_group<KM, 1, TT, WA, MS>(lam, cnt, lane, T0, t0d, myM, myWA, fragM, WAs, accP, accQ);
+                        tock(0);
+                    }
                 }
                 while (qn - qh >= 32 || (!more && qn > qh)) {
                     const int cnt = min(32, qn - qh);
                     const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
                     qh += cnt;
-                    {
-                        // rows of lanes >= cnt: moments 0, W' = 1
-                        const bool ok = lane < cnt;
-                        const double c = ok ? 4.0 * lam : 0.0;
-                        const double a = ok ? 16.0 * (lam * lam) : 0.0;
-                        const double u0 = (T0 == 0) ? a : a * exp_full(-(c * t0d));
-                        // q^64 directly (64 c <= 5): one bounded exponential instead of exp(-c) and six squarings
-                        const double z = -64.0 * c;
-                        const double q64 = exp_bounded(z), q128 = q64 * q64, q256 = q128 * q128;
-                        // moments u0 z^k (the 1/k! lives in the moments -> times step): four chains of stride 4
-                        const double z2 = z * z, z4 = z2 * z2;
-                        double m0 = u0, m1 = u0 * z, m2 = u0 * z2, m3 = m1 * z2;
-#pragma unroll
-                        for (int k = 0; k < KM / 4; ++k) {
-                            st_shared_v2(myM + 4 * k, m0, m1);
-                            st_shared_v2(myM + 4 * k + 2, m2, m3);
-                            m0 *= z4; m1 *= z4; m2 *= z4; m3 *= z4;
-                        }
-                        // W'[hb] = q^64 (q^128)^hb
-                        double w = q64;
-#pragma unroll
-                        for (int k = 0; k < NB / 2; ++k) {
-                            st_shared_v2(myWA + 2 * k, w, w * q128);
-                            w *= q256;
-                        }
-                    }
                     ++n_groups;
-                    __syncwarp();
-                    {
-                        auto fetch = [&](double (&a)[MI], double (&b)[NT], int step) {
-                            const double* mp = fragM + step * (4 * MS);
-                            const double2 m01 = *reinterpret_cast<const double2*>(mp);
-                            a[0] = m01.x; a[1] = m01.y;
-                            if constexpr (MI == 4) {
-                                const double2 m23 = *reinterpret_cast<const double2*>(mp + 2);
-                                a[2] = m23.x; a[3] = m23.y;
-                            }
-                            const double* wp = fragWA + step * (4 * WA);
-                            if constexpr (NT == 1) {
-                                b[0] = wp[0];
-                            } else {
-#pragma unroll
-                                for (int r = 0; r < NT / 2; ++r) {
-                                    const double2 v = *reinterpret_cast<const double2*>(wp + 2 * r);
-                                    b[2 * r] = v.x; b[2 * r + 1] = v.y;
-                                }
-                            }
-                        };
-                        auto mma_step = [&](double (&ac)[MI][NT][2], const double (&a)[MI], const double (&b)[NT]) {
-#pragma unroll
-                            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                                for (int j = 0; j < NT; ++j) dmma884(ac[i][j][0], ac[i][j][1], a[i], b[j]);
-                        };
-                        const int nk = (cnt + 3) >> 2;  // rows past cnt are zero, so an odd count rounds up
-                        double a0[MI], b0[NT], a1[MI], b1[NT];
-                        fetch(a0, b0, 0);
-                        for (int st = 0; st < nk; st += 2) {
-                            fetch(a1, b1, st + 1);
-                            mma_step(accA, a0, b0);
-                            fetch(a0, b0, min(st + 2, 7));
-                            mma_step(accB, a1, b1);
-                        }
-                    }
-                    __syncwarp();
+                    tick();
+                    mom_group<KM, NT, TT, WA, MS>(lam, cnt, lane, T0, t0d, myM, myWA, fragM, WAs, accA, accB);
+                    tock(0);
                 }
                 if (!more) break;
             }
@@ -897,6 +1013,47 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
                         MA[(MI * mrow + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c] + accB[i][j][c];
+            if constexpr (Coarse) {
+                // Coarse moments onto the fine blocks.  A 256-point block (variable y = (t - centre)/128) holds the
+                // polynomial sum_k N[k]/k! y^k; on its two halves y = (x -+ 1)/2, so the 128-point blocks 2 j + s receive
+                //   M[m][2 j + s] += sum_{k >= m} S_s[m][k] N[k][j],   S_s[m][k] = 2^-k (-+1)^(k-m) / (k-m)!
+                // -- an exact change of variable of the (truncated) polynomial, one small product per half on the
+                // moments' own fragment layout: rows m, columns j, the upper-triangular S as the A operand.
+                constexpr int SB = 12;
+                double* MB = MA + KM * SA;   // [KM][SB]
+                if (any_coarse) {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) MB[(MI * mrow + i) * SB + 2 * fk + c] = accP[i][0][c] + accQ[i][0][c];
+                }
+                __syncwarp();
+                if (any_coarse) {
+                    double nb[KS];
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) nb[ks] = MB[(4 * ks + fk) * SB + fg];
+#pragma unroll
+                    for (int mt = 0; mt < MI; ++mt) {
+                        double dl[2] = {0.0, 0.0}, dr[2] = {0.0, 0.0};
+#pragma unroll
+                        for (int ks = 0; ks < KS; ++ks) {
+                            if (4 * ks + 3 < 8 * mt) continue;   // S is upper triangular
+                            const int k = 4 * ks + fk, n = k - (8 * mt + fg);
+                            // 2^-k / n!, zero below the diagonal
+                            const double sr = (n < 0) ? 0.0 : g_inv_fact[n] * __hiloint2double((1023 - k) << 20, 0);
+                            const double sl = (n & 1) ? -sr : sr;
+                            dmma884(dl[0], dl[1], sl, nb[ks]);
+                            dmma884(dr[0], dr[1], sr, nb[ks]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            double* dst = MA + (8 * mt + fg) * SA + 2 * (2 * fk + c);
+                            dst[0] += dl[c];
+                            dst[1] += dr[c];
+                        }
+                    }
+                }
+            }
             __syncwarp();
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks)
@@ -951,6 +1108,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
             const int64_t T0q = T0 + int64_t(h) * QTT;
             const double t0q = double(T0q);
             double acc[4][QR][2];
+            tick();
             {
                 double* lin = Us;  // [QNB][kLinBlock]: natural layout [128 hb + t], then into the accumulator layout
                 double bq[KS];     // this sub-tile's column tile of the B fragments
@@ -958,15 +1116,17 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                 for (int ks = 0; ks < KS; ++ks) bq[ks] = (NT == 1 || h == 0) ? bf[ks][0] : bf[ks][NT - 1];
                 // rows t = 8 mt + fg of the block: A fragment of step ks is x^(4 ks + fk), x = (t - 64)/64 (exact), one
                 // multiply per step; eight row tiles at a time, so that the DMMAs of a tile are not one dependent chain
+                // (x^fk and x^4 come from an 8 KB table that stays in L1, args.mt_pow: forming them in registers took an
+                // int -> double conversion, three multiplies and three selects per row tile)
+                const double2* xp = reinterpret_cast<const double2*>(args.mt_pow) + lane;
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     double pw[8], x4[8], d[8][2];
 #pragma unroll
                     for (int m = 0; m < 8; ++m) {
-                        const double x = double(8 * (8 * half + m) + fg - 64) * 0.015625;
-                        const double xx = x * x;
-                        x4[m] = xx * xx;
-                        pw[m] = (fk == 0) ? 1.0 : (fk == 1) ? x : (fk == 2) ? xx : xx * x;  // x^fk
+                        const double2 v = __ldg(xp + 32 * (8 * half + m));
+                        pw[m] = v.x;
+                        x4[m] = v.y;
                         d[m][0] = d[m][1] = 0.0;
                     }
 #pragma unroll
@@ -974,7 +1134,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
 #pragma unroll
                         for (int m = 0; m < 8; ++m) {
                             dmma884(d[m][0], d[m][1], pw[m], bq[ks]);
-                            pw[m] *= x4[m];  // -> x^(k+4), k = 4 ks + fk
+                            if (ks + 1 < KS) pw[m] *= x4[m];  // -> x^(k+4), k = 4 ks + fk
                         }
                     }
 #pragma unroll
@@ -996,6 +1156,8 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                 __syncwarp();
             }
 
+            tock(1);
+            tick();
             // the item's fast sites, power tables as in profile_kernel (sub-tile geometry)
             if (n_fast > 0 && n_fast <= 32) {
                 for (int g0 = 0; g0 < n_fast; g0 += 16) {
@@ -1037,10 +1199,13 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                     if (!more) break;
                 }
             }
+            tock(2);
+            tick();
             prof_epilogue_at<QR>(args, acc, args.pi_net + int64_t(item.locus) * args.T,
                                  item.slot >= 0 ? args.ws + size_t(item.slot) * TT + size_t(h) * QTT : nullptr, T0q, lane,
                                  best_bits, best_t);
             __syncwarp();
+            tock(3);
         }
         stamp(19);
         if (item.slot < 0) {   // the tile's maximum over its sub-tiles and lanes (first maximum, as numpy.argmax)
@@ -1058,7 +1223,10 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
         }
         stamp(20);
         if constexpr (TRACE) {
-            if (lane == 0 && n_done == 1) { tr[22] = n_groups; tr[24] = n_fast; }
+            if (lane == 0 && n_done == 1) {
+                tr[22] = n_groups; tr[24] = n_fast;
+                tr[25] = t_sum[0]; tr[26] = t_sum[1]; tr[27] = t_sum[2]; tr[28] = t_sum[3];
+            }
             ++n_done;
         }
     }

@@ -145,6 +145,7 @@ struct tapir_cuda_ctx {
     int use_graphs = 1;      // staged path replays a captured CUDA graph (TAPIR_CUDA_GRAPHS=0 disables)
     int n_lanes = 8;         // lanes the chunks of tapir_cuda_run rotate over
     int ramp = 4;            // tapir_cuda_run opens with chunks of 1/ramp, 2/ramp, ... of the regular size (<= 1: off)
+    double* d_mt_pow = nullptr;       // profile_mom_kernel's table of powers (kernels.cuh mt_pow_table), written once
     long long* prof_trace = nullptr;  // TAPIR_PROF_TRACE=<file>: per-warp time stamps of profile_kernel, dumped by tapir_cuda_compute
     size_t prof_trace_words = 0;
     std::string prof_trace_path;
@@ -260,6 +261,8 @@ cudaError_t configure_profile(tapir_cuda_ctx* ctx, int idx)
             e = cudaFuncSetAttribute(profile_mom_kernel<RH, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom16::SmemBytes));
         if (e == cudaSuccess)
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->mom16_per_sm[idx], profile_mom_kernel<RH, false, 16>, kProfWarps * 32, Mom16::SmemBytes);
+        if (e == cudaSuccess && ctx->prof_trace)
+            e = cudaFuncSetAttribute(profile_mom_kernel<RH, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Mom16::SmemBytes));
     }
     return e;
 }
@@ -276,9 +279,12 @@ cudaError_t launch_profile(tapir_cuda_ctx* ctx, Lane& ln, const ProfArgs& pa, in
     const int64_t need = (n_items + kProfWarps - 1) / kProfWarps;
     const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(need, int64_t(ctx->sm_count) * per_sm));
     if constexpr (RH >= 4) {
-        if (mom && km == 16 && !pa.trace) {
+        if (mom && km == 16) {
             using Mom16 = MomCfg<RH, 16>;
-            profile_mom_kernel<RH, false, 16><<<unsigned(grid), kProfWarps * 32, Mom16::SmemBytes, ln.stream>>>(pa);
+            if (pa.trace)
+                profile_mom_kernel<RH, true, 16><<<unsigned(grid), kProfWarps * 32, Mom16::SmemBytes, ln.stream>>>(pa);
+            else
+                profile_mom_kernel<RH, false, 16><<<unsigned(grid), kProfWarps * 32, Mom16::SmemBytes, ln.stream>>>(pa);
             return cudaGetLastError();
         }
         if (mom) {
@@ -556,8 +562,14 @@ int tapir_cuda_create(int device, tapir_cuda_ctx** out)
             ctx->use_graphs = 0;
         }
     }
+    {
+        std::vector<double> tab(kMtPowDoubles);
+        mt_pow_table(tab.data());
+        e = cudaMalloc(&ctx->d_mt_pow, tab.size() * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpy(ctx->d_mt_pow, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+    }
     // launch configuration of the profile kernels on this device (shared-memory opt-in, resident CTAs per SM)
-    e = configure_profile<1>(ctx, 0);
+    if (e == cudaSuccess) e = configure_profile<1>(ctx, 0);
     if (e == cudaSuccess) e = configure_profile<2>(ctx, 1);
     if (e == cudaSuccess) e = configure_profile<4>(ctx, 2);
     if (e == cudaSuccess) e = configure_profile<8>(ctx, 3);
@@ -613,6 +625,7 @@ int tapir_cuda_destroy(tapir_cuda_ctx* ctx)
     if (ctx->stream_d2h) { cudaStreamSynchronize(ctx->stream_d2h); cudaStreamDestroy(ctx->stream_d2h); }
     if (ctx->gather_mapped) cudaIpcCloseMemHandle(ctx->gather_mapped);
     if (ctx->prof_trace) cudaFree(ctx->prof_trace);
+    if (ctx->d_mt_pow) cudaFree(ctx->d_mt_pow);
     DevBuf* bufs[] = {&ctx->d_scratch_a, &ctx->d_scratch_b, &ctx->d_scratch_c, &ctx->d_flush, &ctx->d_counter, &ctx->d_gather};
     for (DevBuf* b : bufs) b->release();
     for (auto& ev : ctx->ev)
@@ -681,7 +694,6 @@ Decision decide_batch(const tapir_cuda_ctx* ctx, const tapir_problem* p)
     const int64_t TT = 256 * d.rh;
     const int n_tiles = int(std::max<int64_t>(1, (T + TT - 1) / TT));
     d.mom_terms = d.mom_form ? choose_moments(ctx, p, 0, L, d.rh, n_tiles) : 32;
-    if (ctx->prof_trace) d.mom_terms = 32;   // (the trace instantiation exists for 32 moments only)
     if (d.fp32) d.mom_terms = kF32Terms;
     return d;
 }
@@ -922,6 +934,7 @@ int enqueue_kernels(tapir_cuda_ctx* ctx, Lane& ln, bool inner_events, int& launc
             pa.mom_int = ln.d_mom_int.as<double>();
             pa.n_mom_epochs = plan.mom_form ? plan.n_mom : 0;
             pa.e_total = plan.E;
+            pa.mt_pow = ctx->d_mt_pow;
             cudaError_t e = cudaSuccess;
             if (plan.fp32) {
                 const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(plan.n_prof_items, int64_t(ctx->sm_count) * std::max(1, ctx->f32_per_sm)));

@@ -316,6 +316,50 @@ def test_moment_form_classes(eng, case):
     assert np.array_equal(res.pi_times, res.pi_net[:, [1, 500, 999]])
 
 
+@pytest.mark.parametrize("km", [16, 32])
+@pytest.mark.parametrize("case", ["coarse_only", "at_half_bound", "all_three_classes", "coarse_second_tile"])
+def test_moment_form_coarse_class(km, case, monkeypatch):
+    """On 2,048-point tiles profile_mom_kernel expands the sites below HALF the class bound on 256-point blocks and
+    shifts those moments onto the 128-point blocks (an exact change of variable of the truncated polynomial).  Sites
+    at the half bound carry the class remainder on the long block; the profile, the picks, the maxima and the epoch sums
+    (which read the shifted moments) must agree with the oracle as for the one-level form."""
+    from oracle import capi
+    from tapir_b200.engine import Engine, pack_csr
+    monkeypatch.setenv("TAPIR_CUDA_RH", "8")
+    monkeypatch.setenv("TAPIR_PROF_MOM", "1")
+    monkeypatch.setenv("TAPIR_MOM_TERMS", str(km))
+    bound = {16: 0.0048828125, 32: 0.01953125}[km]
+    half = 0.5 * bound
+    rng = np.random.default_rng(km + len(case))
+    T = 2048 if case != "coarse_second_tile" else 4000
+    if case == "coarse_only":
+        loci = [rng.uniform(0, half, n) for n in (1, 31, 32, 33, 300, 64)]
+    elif case == "at_half_bound":
+        edge = [half, np.nextafter(half, 0.0), np.nextafter(half, 1.0), half * (1 - 1e-9), half * (1 + 1e-9)]
+        loci = [np.array(edge * 20), rng.uniform(0.98 * half, 1.02 * half, 300), np.array(edge)]
+    elif case == "all_three_classes":
+        loci = [rng.permutation(np.concatenate([rng.uniform(0, half, 150), rng.uniform(half, bound, 150),
+                                                rng.uniform(bound, 4 * bound, 40), np.zeros(30)])) for _ in range(5)]
+        loci.append(rng.uniform(half, bound, 100))                  # no coarse site at all: the shift is skipped
+    else:
+        loci = [rng.gamma(0.5, 4.0 / T, 500) for _ in range(4)]
+    epochs = [[32, 42], [88, 98], [164, 174], [120, 136], [250, 262], [1000, 1010], [T - 40, T - 30]]
+    off, rates = pack_csr(loci, pinned=False)
+    eng = Engine(0)
+    try:
+        eng.upload(off, rates, T, [1, 127, 128, 255, 256, T - 1], epochs, want_profile=True)
+        tm = eng.compute()
+        assert tm.profile_tile_points == 2048 and tm.profile_moment_form == km
+        res = eng.download()
+    finally:
+        eng.close()
+    pi_net, integ, _ = capi.batch(off, rates, T, epochs)
+    assert rel(res.pi_net, pi_net) < 5e-11
+    assert np.array_equal(res.argmax_t, np.argmax(pi_net, axis=1))
+    assert rel(res.integral, integ) < RTOL
+    assert np.array_equal(res.argmax_epoch, np.argmax(integ, axis=1))
+
+
 def test_chunked_run_equals_single_pass(eng):
     """tapir_cuda_run cuts a large batch into chunks that alternate between two lanes (copies overlap
     kernels); the result must be bit-identical to the unchunked staged path, ragged loci included."""

@@ -10,6 +10,7 @@ For the sites the plan declares served by the moments, two things must hold agai
 No GPU is used; the kernels' use of the plan is covered by tests/test_gpu_parity.py.
 """
 import ctypes
+import math
 
 import numpy as np
 import pytest
@@ -32,14 +33,28 @@ def plan(a, b, n_tiles=8, tile_points=1024, km=32, class_x=0.0):
     return out
 
 
-def moments(rates, tile, hb, tile_points, km=32):
-    """M[k] = sum_s a e^{-c T0} (-64 c)^k e^{-c (128 hb + 64)} of block hb of the tile (kernels.cuh, moment pass)."""
+def moments(rates, tile, hb, tile_points, km=32, bound=None):
+    """M[k] = sum_s a e^{-c T0} (-64 c)^k e^{-c (128 hb + 64)} of block hb of the tile (kernels.cuh, moment pass).
+    On 2,048-point tiles the sites below half the class bound are expanded on 256-point blocks (z = -128 c) and their
+    moments shifted onto the 128-point blocks,  M[m] += sum_{k >= m} 2^-k (-+1)^(k-m) / (k-m)! N[k]  -- as the kernel does."""
     lam = np.asarray(rates, dtype=np.float64)
-    a, c = 16.0 * lam * lam, 4.0 * lam
-    u0 = a * np.exp(-(c * float(tile * tile_points)))
-    z = -64.0 * c
-    w = np.exp(z) * np.exp(2.0 * z) ** hb            # q^64 (q^128)^hb
-    return np.array([np.sum((u0 * z ** k) * w) if k < km else 0.0 for k in range(32)])
+    bound = BOUND[km] if bound is None else bound
+    coarse = (lam < 0.5 * bound) if tile_points == 2048 else np.zeros(lam.shape, dtype=bool)
+
+    def block_moments(lam, half, blk):
+        a, c = 16.0 * lam * lam, 4.0 * lam
+        u0 = a * np.exp(-(c * float(tile * tile_points)))
+        z = -half * c
+        w = np.exp(z) * np.exp(2.0 * z) ** blk       # q^half (q^(2 half))^blk
+        return np.array([np.sum((u0 * z ** k) * w) if k < km else 0.0 for k in range(32)])
+
+    M = block_moments(lam[~coarse], 64.0, hb)
+    if coarse.any():
+        N = block_moments(lam[coarse], 128.0, hb // 2)
+        o = 1.0 if hb % 2 else -1.0
+        for m in range(km):
+            M[m] += sum(2.0 ** -k * o ** (k - m) / math.factorial(k - m) * N[k] for k in range(m, km))
+    return M
 
 
 def served(pl, rates):
@@ -150,9 +165,9 @@ def test_fp32_mode_class(span):
     integ, err, last = capi.epoch_sites(lam, a, b)
     assert np.all(last == 1)
     np.testing.assert_allclose(err, 50 * EPS * integ, rtol=1e-13)
-    got = float(np.dot(np.array(pl.p[:]), moments(lam, pl.tile, pl.hb, 1024, 16)))
+    got = float(np.dot(np.array(pl.p[:]), moments(lam, pl.tile, pl.hb, 1024, 16, bound=2.5 / 256)))
     assert abs(got - np.sum(integ)) <= 2e-6 * np.sum(integ)
     worst = np.array([np.nextafter(pl.r_max, 0.0)])
     if served(pl, worst)[0]:
-        one = float(np.dot(np.array(pl.p[:]), moments(worst, pl.tile, pl.hb, 1024, 16)))
+        one = float(np.dot(np.array(pl.p[:]), moments(worst, pl.tile, pl.hb, 1024, 16, bound=2.5 / 256)))
         assert abs(one - capi.epoch_sites(worst, a, b)[0][0]) <= 5e-6 * one

@@ -79,3 +79,10 @@ if m.any():
     for k, nm in enumerate(names):
         print("  %-28s" % nm, q(ph[:, 17 + k] - ph[:, 16 + k]))
     print("  %-28s" % "whole item", q(ph[:, 20] - ph[:, 16]))
+    if (ph[:, 25:29] > 0).any():
+        print("  of which, summed over the item's groups / sub-tiles:")
+        for k, nm in enumerate(["groups of the moment pass (tables + DMMAs)", "moments -> times proper", "fast sites",
+                                "epilogue (stores, maximum)"]):
+            print("    %-44s" % nm, q(ph[:, 25 + k]))
+        rounds = (ph[:, 17] - ph[:, 16]) - ph[:, 25]
+        print("    %-44s" % "moment pass outside its groups (rate rounds)", q(rounds))
