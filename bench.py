@@ -233,17 +233,23 @@ def measured_peaks():
 MOM_BOUND = {32: 0.01953125, 16: 0.0048828125}     # moment classes of profile_mom_kernel<RH, KM> (mom_epoch.h)
 
 
-def site_classes(offsets, rates, moment_form, chunk=1 << 26, coarse=False):
+def site_classes(offsets, rates, moment_form, chunk=1 << 26, coarse=False, tile_points=0):
     """Per locus: (# sites of profile_mom_kernel's moment class, # other sites with a non-zero finite rate).
     moment_form: 0 (direct form: no moment class) or the number of moments per block, 32 or 16 (True = 32).
     coarse=True (2,048-point tiles): a third array, the sites below half the bound (expanded on 256-point blocks),
-    which are then not counted in the first."""
+    which are then not counted in the first.  tile_points > 0: a last array, the whole-tile class (rate below
+    0.0048828125 x 128 / tile_points), counted in none of the others."""
     bound = MOM_BOUND[16 if moment_form == 16 else 32]
     off = np.asarray(offsets, dtype=np.int64)
     L = off.size - 1
     n_slow, n_fast, n_coarse = np.zeros(L, dtype=np.int64), np.zeros(L, dtype=np.int64), np.zeros(L, dtype=np.int64)
+    n_whole = np.zeros(L, dtype=np.int64)
+
+    def result():
+        out = (n_slow, n_fast) + ((n_coarse,) if coarse else ())
+        return out + ((n_whole,) if tile_points else ())
     if L == 0 or rates.size == 0:
-        return (n_slow, n_fast, n_coarse) if coarse else (n_slow, n_fast)
+        return result()
     l0 = 0
     while l0 < L:                                           # whole loci per chunk of at most ~`chunk` sites
         l1 = int(np.searchsorted(off, off[l0] + chunk, side="right")) - 1
@@ -255,12 +261,13 @@ def site_classes(offsets, rates, moment_form, chunk=1 << 26, coarse=False):
         seg = off[l0:l1] - off[l0]
         lens = off[l0 + 1:l1 + 1] - off[l0:l1]
         full = np.nonzero(lens > 0)[0]                       # reduceat over the non-empty loci only (their segments tile r)
-        low = slow & (r < 0.5 * bound) if coarse else np.zeros_like(active)
-        for mask, dst in ((slow & ~low, n_slow), (active & ~slow, n_fast), (low, n_coarse)):
+        whole = slow & (r < 0.0048828125 * 128.0 / tile_points) if tile_points else np.zeros_like(active)
+        low = slow & ~whole & (r < 0.5 * bound) if coarse else np.zeros_like(active)
+        for mask, dst in ((slow & ~low & ~whole, n_slow), (active & ~slow, n_fast), (low, n_coarse), (whole, n_whole)):
             if full.size:
                 dst[l0 + full] = np.add.reduceat(mask, seg[full], dtype=np.int64)
         l0 = l1
-    return (n_slow, n_fast, n_coarse) if coarse else (n_slow, n_fast)
+    return result()
 
 
 def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=0):
@@ -271,8 +278,13 @@ def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=
     NT = max(1, NB // 8)
     KM = 16 if moment_form == 16 else 32
     two_level = bool(moment_form) and TT == 2048        # MomCfg::Coarse
-    n_slow, n_fast, n_coarse = site_classes(offsets, rates, moment_form, coarse=True) if two_level else \
-        site_classes(offsets, rates, moment_form) + (None,)
+    n_coarse = n_whole = None
+    if two_level:
+        n_slow, n_fast, n_coarse, n_whole = site_classes(offsets, rates, moment_form, coarse=True, tile_points=TT)
+    elif moment_form:
+        n_slow, n_fast, n_whole = site_classes(offsets, rates, moment_form, tile_points=TT)
+    else:
+        n_slow, n_fast = site_classes(offsets, rates, moment_form)
 
     def ksteps(cnt, group):
         """k-steps (4 sites each, issued in pairs) summed over the groups of `group` sites of every item."""
@@ -291,13 +303,21 @@ def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=
         per_item = 16 * NT + 16 * (5 + KM // 4) + 16 * RH
         scalar0 = groups * per_group + per_item + fgroups * 110
         scalar1 = groups * (per_group + 27) + per_item + fgroups * 136
+        # the whole-tile class: per group of 32 sites c, a, z, the exponential (18), 16 additions and 16 multiplies, no
+        # DMMA; per item with such sites the halving reduction (16 additions), 16 scalings, six DMMAs of the shift and
+        # four additions into the moment scratch
+        wgroups = (n_whole + 31) // 32
+        has_w = n_whole > 0
+        dmma = dmma + np.where(has_w, 6, 0)
+        scalar0 = scalar0 + wgroups * 55 + np.where(has_w, 36, 0)
+        scalar1 = scalar1 + wgroups * 64 + np.where(has_w, 36, 0)
         if two_level:
             # the coarse class: one column tile per k-step, half the W' table; per item with such sites the shift onto
             # the 128-point blocks (two DMMAs per non-zero 8 x 4 block of the upper-triangular S, one multiply each,
             # 4 KM/8 additions into the moment scratch + KM/4 for the two accumulator sets)
             cgroups = (n_coarse + 31) // 32
             shift = sum(1 for mt in range(KM // 8) for ks in range(KM // 4) if 4 * ks + 3 >= 8 * mt)
-            has = n_coarse > 0
+            has = (n_coarse > 0) | has_w
             dmma = dmma + (KM // 8) * ksteps(n_coarse, 32) + np.where(has, 2 * shift, 0)
             scalar0 = scalar0 + cgroups * (25 + KM + NB // 2) + np.where(has, shift + 6 * (KM // 8), 0)
             scalar1 = scalar1 + cgroups * (25 + KM + NB // 2 + 27) + np.where(has, shift + 6 * (KM // 8), 0)
@@ -311,7 +331,7 @@ def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=
     dmma_total = int(dmma.sum()) * n_tiles
     scalar_total = int(scalar0.sum()) + int(scalar1.sum()) * (n_tiles - 1)
     return {"dmma": dmma_total, "scalar": scalar_total, "lane_ops": 256 * dmma_total + 32 * scalar_total,
-            "n_active": int(n_slow.sum() + n_fast.sum() + (n_coarse.sum() if n_coarse is not None else 0))}
+            "n_active": int(n_slow.sum() + n_fast.sum() + sum(int(x.sum()) for x in (n_coarse, n_whole) if x is not None))}
 
 
 def executed_f32_ops(offsets, rates, T):

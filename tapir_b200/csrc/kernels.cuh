@@ -490,7 +490,7 @@ __device__ __forceinline__ void prof_build_tables(double lam, bool ok, int64_t T
 
 // acc(lo,hi) += sum_s U[s][lo] * W[s][hi] over nk k-steps of 4 sites; `last` = last k-step the tables hold (the
 // look-ahead fetch is clamped to it: the tables may end where the warp's shared memory ends)
-template <int RH>
+template <int RH, bool ROLLED = false>   // ROLLED: the k-step loop is not unrolled (profile_mom_kernel: code size)
 __device__ __forceinline__ void prof_contract(double (&acc)[4][RH][2], const double* fragU, const double* fragW, int nk, int last)
 {
     constexpr int WS = ProfCfg<RH>::WStride, US = kUStride;
@@ -518,11 +518,21 @@ __device__ __forceinline__ void prof_contract(double (&acc)[4][RH][2], const dou
     };
     double a0[4], b0[RH], a1[4], b1[RH];
     fetch(a0, b0, 0);
-    for (int s = 0; s < nk; s += 2) {
-        fetch(a1, b1, min(s + 1, last));
-        mma_step(a0, b0);
-        fetch(a0, b0, min(s + 2, last));
-        mma_step(a1, b1);
+    if constexpr (ROLLED) {
+#pragma unroll 1
+        for (int s = 0; s < nk; s += 2) {
+            fetch(a1, b1, min(s + 1, last));
+            mma_step(a0, b0);
+            fetch(a0, b0, min(s + 2, last));
+            mma_step(a1, b1);
+        }
+    } else {
+        for (int s = 0; s < nk; s += 2) {
+            fetch(a1, b1, min(s + 1, last));
+            mma_step(a0, b0);
+            fetch(a0, b0, min(s + 2, last));
+            mma_step(a1, b1);
+        }
     }
 }
 
@@ -658,6 +668,53 @@ __device__ __forceinline__ void prof_epilogue_at(const ProfArgs& args, const dou
         }
 }
 
+constexpr int kLinBlock = 130;  // doubles per 128-point block of the moments -> times scratch (128 + 2: the four row groups
+                                // of a store land 8 banks apart instead of on the same banks)
+// The same from shared memory: `lin` holds the sub-tile's 256 RH sums in their natural order, kLinBlock doubles per
+// 128-point block.  A rolled loop, one block per round -- each lane four consecutive times, the warp 1 KB of the row per
+// store pair -- instead of the unrolled walk over the accumulator registers: 60 instructions of code for 860 (the
+// moment kernel is bound by instruction fetch, not by any pipe: every straight-line stretch counts).
+template <int RH>
+__device__ __forceinline__ void prof_epilogue_lin(const ProfArgs& args, const double* lin, double* row, double* raw, int64_t T0,
+                                                  int lane, long long& best_bits, int64_t& best_t)
+{
+    constexpr int TT = ProfCfg<RH>::TT;
+    const int64_t t_left = args.T - T0;
+    const int t_end = int(t_left < int64_t(TT) ? (t_left < 0 ? 0 : t_left) : int64_t(TT));
+    const bool vec_ok = raw || ((reinterpret_cast<uintptr_t>(row + T0) & 15) == 0);
+    const double* src = lin + 4 * lane;
+    double* dst = raw ? raw + 4 * lane : row + T0 + 4 * lane;
+    double td = double(T0) + double(4 * lane);
+#pragma unroll 1
+    for (int b = 0; b < 2 * RH; ++b, src += kLinBlock, dst += 128, td += 128.0) {
+        const double2 a01 = *reinterpret_cast<const double2*>(src);
+        const double2 a23 = *reinterpret_cast<const double2*>(src + 2);
+        const int o = 128 * b + 4 * lane;
+        double v[4] = {a01.x, a01.y, a23.x, a23.y};
+        if (!raw) {
+            v[0] *= td; v[1] *= td + 1.0; v[2] *= td + 2.0; v[3] *= td + 3.0;
+        }
+        if ((raw || o + 3 < t_end) && vec_ok) {
+            *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (o + i < t_end) dst[i] = v[i];
+        }
+        if (!raw) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long bits = __double_as_longlong(v[i]);
+                if (o + i < t_end && bits > best_bits) {   // offsets rise within a lane: the first maximum is kept
+                    best_bits = bits;
+                    best_t = T0 + o + i;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // PI profile, moment form
 // ------------------------------------------------------------------------------------------
@@ -677,8 +734,6 @@ __device__ __forceinline__ void prof_epilogue_at(const ProfArgs& args, const dou
 // (KM = 16: sites with 64 c <= 1.25, rate < 0.0048828125, need only 16 moments for the same remainder -- half the
 // DMMAs, multiplies and shared-memory traffic of the moment pass and of the moments -> times step; the host picks KM
 // per batch from a sample of the rates, tapir_cuda.cu choose_tile)
-constexpr int kLinBlock = 130;  // doubles per 128-point block of the moments -> times scratch (128 + 2: the four row groups
-                                // of a store land 8 banks apart instead of on the same banks)
 // 1/k!, k = 0..31
 __device__ __constant__ double c_inv_fact[32] = {
     1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333, 0.001388888888888889,
@@ -719,15 +774,34 @@ struct MomCfg {
     static constexpr int FastOff = (Tables > Lin ? Tables : Lin) > Pow ? (Tables > Lin ? Tables : Lin) : Pow;
     static constexpr int QueueOff = FastOff + 32;
     // 2,048-point tiles keep two classes of slow sites (see profile_mom_kernel): a second 64-entry ring for the coarse one
+#if defined(TAPIR_NO_COARSE)   // measurement builds only (tools/gpu_variants.sh)
+    static constexpr bool Coarse = false;
+#else
     static constexpr bool Coarse = (NT == 2);
-    // behind the rings: four slots of 32 rates for the rounds in flight from global memory (cp.async, lane-private)
-    static constexpr int RateOff = QueueOff + (Coarse ? 128 : 64);
-    static constexpr int WarpDoubles = RateOff + 4 * 32;
+#endif
+#if defined(TAPIR_NO_WHOLE)
+    static constexpr bool Whole = false;
+#else
+    static constexpr bool Whole = true;
+#endif
+    // the ring of the whole-tile class behind them, then four slots of 32 rates for the rounds in flight from global
+    // memory (cp.async, lane-private).  With eight-column W' tables (WA = 12) the slots are the four unused doubles at
+    // the end of every W' row instead: those kernels run sixteen warps per SM and have no shared memory to spare.
+    // Ring length: 2,048-point tiles run twelve warps per SM and have shared memory to spare -- rings of 256 let an
+    // item of up to ~250 sites per class finish its rounds first and then drain class by class, every loop's code
+    // entered once per item instead of once per group (the kernel is bound by instruction fetch)
+    static constexpr int Ring = Coarse ? 256 : 64;
+    static constexpr int TileQOff = QueueOff + (Coarse ? 2 : 1) * Ring;
+    static constexpr bool RateInPad = (WA == 12);
+    static constexpr int RateOff = TileQOff + Ring;
+    static constexpr int WarpDoubles = RateOff + (RateInPad ? 0 : 4 * 32);
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
     static constexpr int MinBlocks = (RH == 4 ? 14 : 12) / kProfWarps;  // 144 / 168 registers
+    static constexpr int GroupUnroll = (RH == 8) ? TAPIR_G8 : 4;           // pairs of k-steps per loop body of mom_group
+    static constexpr bool RolledContract = (RH == 8) && TAPIR_ROLL8;       // fast-site contraction not unrolled
     static_assert(Pow <= FastOff, "16-site power tables fit below the fast-site list");
     static_assert(NT == 1 || NT == 2, "one or two column tiles");
-    static_assert(KM * (NB + 4) + (Coarse ? KM * 12 : 0) <= FastOff, "moment scratch fits");
+    static_assert(KM * (NB + 4) + (Coarse ? KM * 12 : 0) + 32 <= FastOff, "moment scratch fits");
     static_assert(KM == 16 || KM == 32, "16 or 32 moments per block");
     static_assert((kLinBlock * 8) % 16 == 0, "16-byte reads of the scratch stay aligned");
 };
@@ -737,6 +811,43 @@ struct MomCfg {
 __device__ __forceinline__ bool rate_is_slow(double r, uint32_t bound_hi) { return uint32_t(__double2hiint(r)) < bound_hi; }
 template <int KM>
 __device__ __forceinline__ constexpr uint32_t mom_bound_hi() { return KM == 16 ? 0x3F740000u : 0x3F940000u; }
+
+// Whole-tile class of profile_mom_kernel: V[n][j] = (2 j - 7)^n / n!, the shift of a polynomial on the tile (variable
+// y in [-1, 1)) onto its eight equal parts (y = (x + 2 j - 7)/8); correctly rounded
+__device__ const double g_tile_shift[16 * 8] = {
+    1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0,
+    -7.0, -5.0, -3.0, -1.0, 1.0, 3.0, 5.0, 7.0,
+    24.5, 12.5, 4.5, 0.5, 0.5, 4.5, 12.5, 24.5,
+    -57.166666666666664, -20.833333333333332, -4.5, -0.16666666666666666, 0.16666666666666666, 4.5, 20.833333333333332, 57.166666666666664,
+    100.04166666666667, 26.041666666666668, 3.375, 0.041666666666666664, 0.041666666666666664, 3.375, 26.041666666666668, 100.04166666666667,
+    -140.05833333333334, -26.041666666666668, -2.025, -0.008333333333333333, 0.008333333333333333, 2.025, 26.041666666666668, 140.05833333333334,
+    163.4013888888889, 21.70138888888889, 1.0125, 0.001388888888888889, 0.001388888888888889, 1.0125, 21.70138888888889, 163.4013888888889,
+    -163.4013888888889, -15.500992063492063, -0.43392857142857144, -0.0001984126984126984, 0.0001984126984126984, 0.43392857142857144, 15.500992063492063, 163.4013888888889,
+    142.97621527777778, 9.68812003968254, 0.1627232142857143, 2.48015873015873e-05, 2.48015873015873e-05, 0.1627232142857143, 9.68812003968254, 142.97621527777778,
+    -111.20372299382716, -5.3822889109347445, -0.05424107142857143, -2.7557319223985893e-06, 2.7557319223985893e-06, 0.05424107142857143, 5.3822889109347445, 111.20372299382716,
+    77.84260609567902, 2.6911444554673722, 0.016272321428571428, 2.755731922398589e-07, 2.755731922398589e-07, 0.016272321428571428, 2.6911444554673722, 77.84260609567902,
+    -49.53620387906846, -1.2232474797578965, -0.004437905844155844, -2.505210838544172e-08, 2.505210838544172e-08, 0.004437905844155844, 1.2232474797578965, 49.53620387906846,
+    28.896118929456602, 0.5096864498991235, 0.001109476461038961, 2.08767569878681e-09, 2.08767569878681e-09, 0.001109476461038961, 0.5096864498991235, 28.896118929456602,
+    -15.559448654322786, -0.19603324996120136, -0.00025603302947052944, -1.6059043836821613e-10, 1.6059043836821613e-10, 0.00025603302947052944, 0.19603324996120136, 15.559448654322786,
+    7.779724327161393, 0.07001187498614334, 5.486422060082774e-05, 1.1470745597729725e-11, 1.1470745597729725e-11, 5.486422060082774e-05, 0.07001187498614334, 7.779724327161393,
+    -3.6305380193419836, -0.02333729166204778, -1.0972844120165549e-05, -7.647163731819816e-13, 7.647163731819816e-13, 1.0972844120165549e-05, 0.02333729166204778, 3.6305380193419836,
+};
+
+// v[0..15] of every lane -> the 16 sums over the warp; lane L returns the sum of index L >> 1 (halving exchange:
+// 16 double shuffles and 16 additions instead of 16 x 5)
+__device__ __forceinline__ double transpose_reduce16(const double (&v)[16], int lane)
+{
+    double a[8], b[4], c[2];
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (h4 ? v[8 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, h4 ? v[i] : v[8 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (h3 ? a[4 + i] : a[i]) + __shfl_xor_sync(0xffffffffu, h3 ? a[i] : a[4 + i], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) c[i] = (h2 ? b[2 + i] : b[i]) + __shfl_xor_sync(0xffffffffu, h2 ? b[i] : b[2 + i], 4);
+    const double d = (h1 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, h1 ? c[0] : c[1], 2);
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
 
 // Position of column hb of an eight-column W' table inside rows that are 18 doubles apart (the stride of the
 // sixteen-column table of the same kernel): 0 1 8 9 2 3 10 11.  The 8-byte fragment loads of a half warp (four rows fk,
@@ -748,10 +859,21 @@ __device__ __forceinline__ constexpr int wcol(int hb)
     return Swz ? ((hb & 1) | ((hb & 2) << 2) | ((hb & 4) >> 1)) : hb;
 }
 
+// Code size of the 2,048-point kernels: they carry three classes of slow sites, and beyond ~2,500 instructions (40 KB)
+// the SM's instruction cache misses and the GPC-level cache behind it saturates -- the kernel is then bound by
+// instruction fetch (measured: hit rate 87 %, 10.2 ms; 99.7 %, 9.9 ms with less unrolling).  So their k-step loops are
+// unrolled less than the compiler would (four-fold: ~250 instructions each); MomCfg::GroupUnroll, RolledContract.
+#ifndef TAPIR_G8
+#define TAPIR_G8 1
+#endif
+#ifndef TAPIR_ROLL8
+#define TAPIR_ROLL8 1
+#endif
+
 // One group of up to 32 slow sites of profile_mom_kernel's moment pass, for a class with NG column tiles: blocks of
 // TT / (8 NG) points (half-length HB), the group's tables U' [32][MS] (moments u0 z^k, z = -HB c) and W' [32][WA]
 // (q^HB (q^2HB)^hb) built in the warp's shared memory, then  acE/acO[i][j][c] += U'^T W'  on the FP64 MMA path.
-template <int KM, int NG, int TT, int WA, int MS>
+template <int KM, int NG, int TT, int WA, int MS, int UNROLL>
 __device__ __forceinline__ void mom_group(const double lam, const int cnt, const int lane, const int64_t T0, const double t0d,
                                           double* myM, double* myWA, const double* fragM, const double* WAs,
                                           double (&acE)[KM / 8][NG][2], double (&acO)[KM / 8][NG][2])
@@ -820,6 +942,7 @@ __device__ __forceinline__ void mom_group(const double lam, const int cnt, const
         const int nk = (cnt + 3) >> 2;  // rows past cnt are zero, so an odd count rounds up
         double a0[MI], b0[NG], a1[MI], b1[NG];
         fetch(a0, b0, 0);
+#pragma unroll(UNROLL)
         for (int st = 0; st < nk; st += 2) {
             fetch(a1, b1, st + 1);
             mma_step(acE, a0, b0);
@@ -928,22 +1051,31 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
             for (int j = 0; j < NT; ++j) accA[i][j][0] = accA[i][j][1] = accB[i][j][0] = accB[i][j][1] = 0.0;
             accP[i][0][0] = accP[i][0][1] = accQ[i][0][0] = accQ[i][0][1] = 0.0;
         }
+        // Whole-tile class: a site with (TT/2) c <= 1.25 (rate < 0.0048828125 x 128/TT) is one polynomial of 16 terms on
+        // the whole tile; its moments u z^k, z = -(TT/2) c, u = a e^{-c (T0 + TT/2)}, are summed per lane in registers --
+        // no table, no DMMA -- and shifted onto the tile's eight parts after the pass.
+        constexpr uint32_t kBoundTile = 0x3F740000u - (TT == 2048 ? 4u : 3u) * 0x00100000u;
+        double tileS[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) tileS[k] = 0.0;
         int n_fast = 0;
-        bool any_coarse = false;
+        bool any_coarse = false, any_tile = false;
         {
-            int qh = 0, qn = 0, ph = 0, pn = 0;   // rings: fine class (Qs), coarse class (Ps)
-            double* Ps = Qs + 64;
+            int qh = 0, qn = 0, ph = 0, pn = 0, ah = 0, an = 0;   // rings: fine class (Qs), coarse class (Ps), whole tile (As)
+            constexpr int RM = Mom::Ring - 1;
+            double* Ps = Qs + Mom::Ring;
+            double* As = Us + Mom::TileQOff;
             // Rates are fetched three rounds ahead, asynchronously into lane-private shared-memory slots (a register
             // queue must be shifted every round, and the shift waits for the load issued one round earlier: rounds
             // without a group in between then expose the whole DRAM latency).  One commit group per round, issued or
             // empty, so that "all but the newest two" always means this round's rates have landed; four slots, so the
             // slot a round refills is never the one it has just read.
             constexpr int kAhead = 3;
-            double* ring = Us + Mom::RateOff + lane;
+            double* ring = Mom::RateInPad ? myWA + 8 : Us + Mom::RateOff + 4 * lane;   // this lane's four slots
             auto fetch_round = [&](int r) {   // rates [32 r, 32 r + 32) of the item -> slot r mod 4; zeros past the item
                 const int i = 32 * r + lane;
                 const bool in = i < item.n_sites;
-                const unsigned dst = unsigned(__cvta_generic_to_shared(ring + 32 * (r & 3)));
+                const unsigned dst = unsigned(__cvta_generic_to_shared(ring + (r & 3)));
                 const double* src = in ? rp + i : rp;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(in ? 8 : 0) : "memory");
                 asm volatile("cp.async.commit_group;" ::: "memory");
@@ -954,46 +1086,76 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                 const bool more = base < item.n_sites;
                 if (more) {
                     asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");
-                    const double lam_new = ring[32 * (rnd & 3)];
+                    const double lam_new = ring[rnd & 3];
                     fetch_round(rnd + kAhead);
                     const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
                     const bool slow = act && rate_is_slow(lam_new, kBound);
-                    const bool coarse = Coarse && act && rate_is_slow(lam_new, kBound - 0x00100000u);   // half the bound
-                    const unsigned ballot = __ballot_sync(0xffffffffu, slow && !coarse);
+                    const bool whole = Mom::Whole && act && rate_is_slow(lam_new, kBoundTile);
+                    const bool coarse = Coarse && act && !whole && rate_is_slow(lam_new, kBound - 0x00100000u);   // half the bound
+                    const unsigned ballot = __ballot_sync(0xffffffffu, slow && !coarse && !whole);
                     {   // the first 32 fast sites are kept aside, so that their pass need not stream the item again
                         const unsigned bf = __ballot_sync(0xffffffffu, act && !slow);
                         const int pos = n_fast + __popc(bf & ((1u << lane) - 1u));
                         if (act && !slow && pos < 32) Fs[pos] = lam_new;
                         n_fast += __popc(bf);
                     }
-                    if (slow && !coarse) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                    if (slow && !coarse && !whole) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & RM] = lam_new;
                     qn += __popc(ballot);
+                    if constexpr (Mom::Whole) {
+                        const unsigned ba = __ballot_sync(0xffffffffu, whole);
+                        if (whole) As[(an + __popc(ba & ((1u << lane) - 1u))) & RM] = lam_new;
+                        an += __popc(ba);
+                    }
                     if constexpr (Coarse) {
                         const unsigned bc = __ballot_sync(0xffffffffu, coarse);
-                        if (coarse) Ps[(pn + __popc(bc & ((1u << lane) - 1u))) & 63] = lam_new;
+                        if (coarse) Ps[(pn + __popc(bc & ((1u << lane) - 1u))) & RM] = lam_new;
                         pn += __popc(bc);
                     }
                     __syncwarp();
                 }
+                if (Mom::Whole && (an - ah > Mom::Ring - 32 || !more))
+                while (an - ah >= 32 || (!more && an > ah)) {
+                    const int cnt = min(32, an - ah);
+                    const bool ok = lane < cnt;
+                    const double lam = ok ? As[(ah + lane) & RM] : 0.0;
+                    ah += cnt;
+                    any_tile = true;
+                    tick();
+                    const double c = 4.0 * lam;               // lanes >= cnt: lam = 0, a = 0
+                    const double a = 16.0 * (lam * lam);
+                    const double z = -double(TT / 2) * c;
+                    const double m = (T0 == 0) ? a * exp_bounded_short(z) : a * exp_full(-(c * (t0d + double(TT / 2))));
+                    // u z^k: four chains of stride 4 (depth 5 instead of 16)
+                    const double z2 = z * z, z4 = z2 * z2;
+                    double m0 = m, m1 = m * z, m2 = m * z2, m3 = m1 * z2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        tileS[4 * k] += m0; tileS[4 * k + 1] += m1; tileS[4 * k + 2] += m2; tileS[4 * k + 3] += m3;
+                        if (k < 3) { m0 *= z4; m1 *= z4; m2 *= z4; m3 *= z4; }
+                    }
+                    tock(0);
+                }
                 if constexpr (Coarse) {
+                    if (pn - ph > Mom::Ring - 32 || !more)
                     while (pn - ph >= 32 || (!more && pn > ph)) {
                         const int cnt = min(32, pn - ph);
-                        const double lam = (lane < cnt) ? Ps[(ph + lane) & 63] : 0.0;
+                        const double lam = (lane < cnt) ? Ps[(ph + lane) & RM] : 0.0;
                         ph += cnt;
                         any_coarse = true;
                         ++n_groups;
                         tick();
-                        mom_group<KM, 1, TT, WA, MS>(lam, cnt, lane, T0, t0d, myM, myWA, fragM, WAs, accP, accQ);
+                        mom_group<KM, 1, TT, WA, MS, Mom::GroupUnroll>(lam, cnt, lane, T0, t0d, myM, myWA, fragM, WAs, accP, accQ);
                         tock(0);
                     }
                 }
+                if (qn - qh > Mom::Ring - 32 || !more)
                 while (qn - qh >= 32 || (!more && qn > qh)) {
                     const int cnt = min(32, qn - qh);
-                    const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
+                    const double lam = (lane < cnt) ? Qs[(qh + lane) & RM] : 0.0;
                     qh += cnt;
                     ++n_groups;
                     tick();
-                    mom_group<KM, NT, TT, WA, MS>(lam, cnt, lane, T0, t0d, myM, myWA, fragM, WAs, accA, accB);
+                    mom_group<KM, NT, TT, WA, MS, Mom::GroupUnroll>(lam, cnt, lane, T0, t0d, myM, myWA, fragM, WAs, accA, accB);
                     tock(0);
                 }
                 if (!more) break;
@@ -1013,25 +1175,55 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
                         MA[(MI * mrow + i) * SA + NT * w_chunk<NT>(2 * fk + c) + j] = accA[i][j][c] + accB[i][j][c];
+            // Whole-tile sums onto the tile's eight parts (256-point blocks of a 2,048-point tile: the coarse moments;
+            // 128-point blocks of a 1,024-point tile: the moments themselves).  With y = (x + o_j)/8, o_j = 2 j - 7,
+            //   N[m][j] += sum_n T[m][n] V[n][j],   T[m][n] = 8^-(m+n) S[m+n] (zero from m + n = 16),  V[n][j] = o_j^n / n!
+            // -- six DMMAs (the zero blocks of the Hankel matrix T are skipped).
+            constexpr int SBc = 12;
+            double* MBc = MA + KM * SA;                          // [KM][SBc], coarse moments (Coarse only)
+            double* TS = MBc + (Coarse ? KM * SBc : 0);          // [32]: scaled sums, zero-padded
+            if (any_tile) {
+                const double tot = transpose_reduce16(tileS, lane);
+                const int k = lane >> 1;
+                if (lane & 1) TS[16 + k] = 0.0;                                        // odd lanes: the padding
+                else TS[k] = tot * __hiloint2double((1023 - 3 * k) << 20, 0);         // 8^-k, exact
+            }
+            if constexpr (Coarse) {
+                if (any_coarse || any_tile) {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) MBc[(MI * mrow + i) * SBc + 2 * fk + c] = accP[i][0][c] + accQ[i][0][c];
+                }
+            }
+            __syncwarp();
+            if (any_tile) {
+                double* dstN = Coarse ? MBc : MA;
+                constexpr int SN = Coarse ? SBc : SA;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    double d[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (8 * mt + 4 * ks >= 16) continue;   // T[m][n] = 0 from m + n = 16
+                        const double tv = TS[8 * mt + fg + 4 * ks + fk];
+                        dmma884(d[0], d[1], tv, __ldg(g_tile_shift + 8 * (4 * ks + fk) + fg));
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) dstN[(8 * mt + fg) * SN + 2 * fk + c] += d[c];
+                }
+                __syncwarp();
+            }
             if constexpr (Coarse) {
                 // Coarse moments onto the fine blocks.  A 256-point block (variable y = (t - centre)/128) holds the
                 // polynomial sum_k N[k]/k! y^k; on its two halves y = (x -+ 1)/2, so the 128-point blocks 2 j + s receive
                 //   M[m][2 j + s] += sum_{k >= m} S_s[m][k] N[k][j],   S_s[m][k] = 2^-k (-+1)^(k-m) / (k-m)!
                 // -- an exact change of variable of the (truncated) polynomial, one small product per half on the
                 // moments' own fragment layout: rows m, columns j, the upper-triangular S as the A operand.
-                constexpr int SB = 12;
-                double* MB = MA + KM * SA;   // [KM][SB]
-                if (any_coarse) {
-#pragma unroll
-                    for (int i = 0; i < MI; ++i)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) MB[(MI * mrow + i) * SB + 2 * fk + c] = accP[i][0][c] + accQ[i][0][c];
-                }
-                __syncwarp();
-                if (any_coarse) {
+                if (any_coarse || any_tile) {
                     double nb[KS];
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) nb[ks] = MB[(4 * ks + fk) * SB + fg];
+                    for (int ks = 0; ks < KS; ++ks) nb[ks] = MBc[(4 * ks + fk) * SBc + fg];
 #pragma unroll
                     for (int mt = 0; mt < MI; ++mt) {
                         double dl[2] = {0.0, 0.0}, dr[2] = {0.0, 0.0};
@@ -1107,10 +1299,9 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
         for (int h = 0; h < NH; ++h) {
             const int64_t T0q = T0 + int64_t(h) * QTT;
             const double t0q = double(T0q);
-            double acc[4][QR][2];
             tick();
             {
-                double* lin = Us;  // [QNB][kLinBlock]: natural layout [128 hb + t], then into the accumulator layout
+                double* lin = Us;  // [QNB][kLinBlock]: natural layout [128 hb + t]
                 double bq[KS];     // this sub-tile's column tile of the B fragments
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) bq[ks] = (NT == 1 || h == 0) ? bf[ks][0] : bf[ks][NT - 1];
@@ -1143,6 +1334,16 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                         for (int c = 0; c < 2; ++c) lin[kLinBlock * (2 * fk + c) + 8 * (8 * half + m) + fg] = d[m][c];
                 }
                 __syncwarp();
+            }
+            tock(1);
+            tick();
+            // the item's fast sites, power tables as in profile_kernel (sub-tile geometry), sixteen at a time in their
+            // order in the item: from the side list, or -- more than 32 of them -- compacted from a second stream of the
+            // item's rates.  One build-and-contract site for both.  The sums go through profile_kernel's accumulator
+            // layout: read from the scratch (the tables overwrite it), contracted onto, written back.
+            if (n_fast > 0) {
+                double* lin = Us;
+                double acc[4][QR][2];
 #pragma unroll
                 for (int j = 0; j < QR; ++j)
 #pragma unroll
@@ -1154,56 +1355,57 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                         acc[0][j][c] = v01.x; acc[1][j][c] = v01.y; acc[2][j][c] = v23.x; acc[3][j][c] = v23.y;
                     }
                 __syncwarp();
-            }
-
-            tock(1);
-            tick();
-            // the item's fast sites, power tables as in profile_kernel (sub-tile geometry)
-            if (n_fast > 0 && n_fast <= 32) {
+                const bool listed = n_fast <= 32;
+                int qh = 0, qn = 0, base = 0;
+                double lam_in = 0.0, lam_in2 = 0.0;
+                if (!listed) {
+                    lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
+                    lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
+                }
                 for (int g0 = 0; g0 < n_fast; g0 += 16) {
                     const int cnt = min(16, n_fast - g0);
-                    if (lane < 16) prof_build_tables<QR>((lane < cnt) ? Fs[g0 + lane] : 0.0, lane < cnt, T0q, t0q, myU, myW);
-                    __syncwarp();
-                    prof_contract<QR>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
-                    __syncwarp();
-                }
-            } else if (n_fast > 32) {
-                int qh = 0, qn = 0;
-                double lam_in = (lane < item.n_sites) ? __ldg(rp + lane) : 0.0;
-                double lam_in2 = (32 + lane < item.n_sites) ? __ldg(rp + 32 + lane) : 0.0;
-                for (int base = 0;; base += 32) {
-                    const bool more = base < item.n_sites;
-                    if (more) {
-                        const double lam_new = lam_in;
-                        lam_in = lam_in2;
-                        {
-                            const int nb = base + 64 + lane;
-                            lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                    if (!listed) {
+                        while (qn - qh < cnt) {   // n_fast counted these sites: the stream holds them
+                            const double lam_new = lam_in;
+                            lam_in = lam_in2;
+                            {
+                                const int nb = base + 64 + lane;
+                                lam_in2 = (nb < item.n_sites) ? __ldg(rp + nb) : 0.0;
+                            }
+                            base += 32;
+                            const bool fast = rate_is_active(lam_new) && !rate_is_slow(lam_new, kBound);
+                            const unsigned ballot = __ballot_sync(0xffffffffu, fast);
+                            if (fast) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
+                            qn += __popc(ballot);
+                            __syncwarp();
                         }
-                        const bool fast = rate_is_active(lam_new) && !rate_is_slow(lam_new, kBound);
-                        const unsigned ballot = __ballot_sync(0xffffffffu, fast);
-                        if (fast) Qs[(qn + __popc(ballot & ((1u << lane) - 1u))) & 63] = lam_new;
-                        qn += __popc(ballot);
-                        __syncwarp();
                     }
-                    while (qn - qh >= 16 || (!more && qn > qh)) {
-                        const int cnt = min(16, qn - qh);
-                        const double lam = (lane < cnt) ? Qs[(qh + lane) & 63] : 0.0;
-                        qh += cnt;
-                        __syncwarp();
-                        if (lane < 16) prof_build_tables<QR>(lam, lane < cnt, T0q, t0q, myU, myW);
-                        __syncwarp();
-                        prof_contract<QR>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
-                        __syncwarp();
-                    }
-                    if (!more) break;
+                    const double* from = listed ? Fs + g0 : Qs;
+                    const int at = listed ? lane : (qh + lane) & 63;
+                    const double lam = (lane < cnt) ? from[at] : 0.0;
+                    qh += cnt;
+                    __syncwarp();
+                    if (lane < 16) prof_build_tables<QR>(lam, lane < cnt, T0q, t0q, myU, myW);
+                    __syncwarp();
+                    prof_contract<QR, Mom::RolledContract>(acc, fragU, fragW, (cnt + 3) >> 2, 3);
+                    __syncwarp();
                 }
+#pragma unroll
+                for (int j = 0; j < QR; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int hi = QR * w_chunk<QR>(2 * fk + c) + j;
+                        double* d = lin + kLinBlock * (hi >> 2) + 32 * (hi & 3) + 4 * chunk_pair(fg);
+                        st_shared_v2(d, acc[0][j][c], acc[1][j][c]);
+                        st_shared_v2(d + 2, acc[2][j][c], acc[3][j][c]);
+                    }
+                __syncwarp();
             }
             tock(2);
             tick();
-            prof_epilogue_at<QR>(args, acc, args.pi_net + int64_t(item.locus) * args.T,
-                                 item.slot >= 0 ? args.ws + size_t(item.slot) * TT + size_t(h) * QTT : nullptr, T0q, lane,
-                                 best_bits, best_t);
+            prof_epilogue_lin<QR>(args, Us, args.pi_net + int64_t(item.locus) * args.T,
+                                  item.slot >= 0 ? args.ws + size_t(item.slot) * TT + size_t(h) * QTT : nullptr, T0q, lane,
+                                  best_bits, best_t);
             __syncwarp();
             tock(3);
         }

@@ -316,6 +316,52 @@ def test_moment_form_classes(eng, case):
     assert np.array_equal(res.pi_times, res.pi_net[:, [1, 500, 999]])
 
 
+@pytest.mark.parametrize("rh", [4, 8])
+@pytest.mark.parametrize("km", [16, 32])
+@pytest.mark.parametrize("case", ["whole_only", "at_the_bound", "every_class", "later_tiles"])
+def test_moment_form_whole_tile_class(rh, km, case, monkeypatch):
+    """Sites below 0.0048828125 x 128 / (tile points) are one 16-term polynomial on the whole tile: per-lane sums of
+    u z^k, then shifted onto the tile's eight parts (and from there, on 2,048-point tiles, onto the 128-point blocks).
+    Group sizes around 32, rates at the class bound (largest remainder, on the longest block), all classes mixed,
+    and tiles after the first (u carries e^{-c T0})."""
+    from oracle import capi
+    from tapir_b200.engine import Engine, pack_csr
+    monkeypatch.setenv("TAPIR_CUDA_RH", str(rh))
+    monkeypatch.setenv("TAPIR_PROF_MOM", "1")
+    monkeypatch.setenv("TAPIR_MOM_TERMS", str(km))
+    TP = 256 * rh
+    edge = 0.0048828125 * 128.0 / TP
+    bound = {16: 0.0048828125, 32: 0.01953125}[km]
+    rng = np.random.default_rng(100 * rh + km + len(case))
+    T = TP if case != "later_tiles" else 3 * TP - 100
+    if case == "whole_only":
+        loci = [rng.uniform(0, edge, n) for n in (1, 31, 32, 33, 64, 65, 500)] + [10.0 ** rng.uniform(-12, -4, 200)]
+    elif case == "at_the_bound":
+        e = [edge, np.nextafter(edge, 0.0), np.nextafter(edge, 1.0), edge * (1 - 1e-9), edge * (1 + 1e-9)]
+        loci = [np.array(e * 20), rng.uniform(0.98 * edge, 1.02 * edge, 300), np.array(e)]
+    elif case == "every_class":
+        loci = [rng.permutation(np.concatenate([rng.uniform(0, edge, 150), rng.uniform(edge, bound, 200),
+                                                rng.uniform(bound, 4 * bound, 40), np.zeros(30)])) for _ in range(5)]
+        loci.append(rng.uniform(edge, bound, 100))                  # no whole-tile site: the shift is skipped
+    else:
+        loci = [rng.gamma(0.5, 4.0 / T, 500) for _ in range(4)]
+    epochs = [[32, 42], [88, 98], [164, 174], [120, 136], [250, 262], [TP - 40, TP - 30], [T - 40, T - 30]]
+    off, rates = pack_csr(loci, pinned=False)
+    eng = Engine(0)
+    try:
+        eng.upload(off, rates, T, [1, 127, 128, 255, 256, T - 1], epochs, want_profile=True)
+        tm = eng.compute()
+        assert tm.profile_tile_points == TP and tm.profile_moment_form == km
+        res = eng.download()
+    finally:
+        eng.close()
+    pi_net, integ, _ = capi.batch(off, rates, T, epochs)
+    assert rel(res.pi_net, pi_net) < 5e-11
+    assert np.array_equal(res.argmax_t, np.argmax(pi_net, axis=1))
+    assert rel(res.integral, integ) < RTOL
+    assert np.array_equal(res.argmax_epoch, np.argmax(integ, axis=1))
+
+
 @pytest.mark.parametrize("km", [16, 32])
 @pytest.mark.parametrize("case", ["coarse_only", "at_half_bound", "all_three_classes", "coarse_second_tile"])
 def test_moment_form_coarse_class(km, case, monkeypatch):

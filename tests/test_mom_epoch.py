@@ -33,27 +33,36 @@ def plan(a, b, n_tiles=8, tile_points=1024, km=32, class_x=0.0):
     return out
 
 
-def moments(rates, tile, hb, tile_points, km=32, bound=None):
-    """M[k] = sum_s a e^{-c T0} (-64 c)^k e^{-c (128 hb + 64)} of block hb of the tile (kernels.cuh, moment pass).
-    On 2,048-point tiles the sites below half the class bound are expanded on 256-point blocks (z = -128 c) and their
-    moments shifted onto the 128-point blocks,  M[m] += sum_{k >= m} 2^-k (-+1)^(k-m) / (k-m)! N[k]  -- as the kernel does."""
+def moments(rates, tile, hb, tile_points, km=32, bound=None, one_level=False):
+    """M[k] = sum_s a e^{-c T0} (-64 c)^k e^{-c (128 hb + 64)} of block hb of the tile -- formed as profile_mom_kernel
+    forms it (kernels.cuh, moment pass): sites below 0.0048828125 x 128 / tile_points are one 16-term polynomial on the
+    whole tile, shifted onto its eight parts; on 2,048-point tiles the sites below half the class bound are expanded on
+    256-point blocks (z = -128 c) and those moments, with the whole-tile part, shifted onto the 128-point blocks:
+    M[m] += sum_{k >= m} s^-k o^(k-m) / (k-m)! N[k]  for a part at offset o of a block s times as long."""
     lam = np.asarray(rates, dtype=np.float64)
     bound = BOUND[km] if bound is None else bound
-    coarse = (lam < 0.5 * bound) if tile_points == 2048 else np.zeros(lam.shape, dtype=bool)
+    whole = lam < (0.0 if one_level else 0.0048828125 * 128.0 / tile_points)      # one_level: profile_f32_kernel
+    coarse = (lam < 0.5 * bound) & ~whole if tile_points == 2048 and not one_level else np.zeros(lam.shape, dtype=bool)
 
-    def block_moments(lam, half, blk):
+    def block_moments(lam, half, blk, terms):
         a, c = 16.0 * lam * lam, 4.0 * lam
         u0 = a * np.exp(-(c * float(tile * tile_points)))
         z = -half * c
         w = np.exp(z) * np.exp(2.0 * z) ** blk       # q^half (q^(2 half))^blk
-        return np.array([np.sum((u0 * z ** k) * w) if k < km else 0.0 for k in range(32)])
+        return np.array([np.sum((u0 * z ** k) * w) if k < terms else 0.0 for k in range(32)])
 
-    M = block_moments(lam[~coarse], 64.0, hb)
-    if coarse.any():
-        N = block_moments(lam[coarse], 128.0, hb // 2)
-        o = 1.0 if hb % 2 else -1.0
-        for m in range(km):
-            M[m] += sum(2.0 ** -k * o ** (k - m) / math.factorial(k - m) * N[k] for k in range(m, km))
+    def shift(N, scale, o, terms):
+        return np.array([sum(float(scale) ** -k * o ** (k - m) / math.factorial(k - m) * N[k] for k in range(m, terms))
+                         if m < terms else 0.0 for m in range(32)])
+
+    M = block_moments(lam[~coarse & ~whole], 64.0, hb, km)
+    if tile_points == 2048:
+        N = block_moments(lam[coarse], 128.0, hb // 2, km)
+        if whole.any():
+            N = N + shift(block_moments(lam[whole], 1024.0, 0, 16), 8, 2.0 * (hb // 2) - 7.0, 16)
+        M = M + shift(N, 2, 1.0 if hb % 2 else -1.0, km)
+    elif whole.any():
+        M = M + shift(block_moments(lam[whole], tile_points / 2.0, 0, 16), 8, 2.0 * hb - 7.0, 16)
     return M
 
 
@@ -165,9 +174,9 @@ def test_fp32_mode_class(span):
     integ, err, last = capi.epoch_sites(lam, a, b)
     assert np.all(last == 1)
     np.testing.assert_allclose(err, 50 * EPS * integ, rtol=1e-13)
-    got = float(np.dot(np.array(pl.p[:]), moments(lam, pl.tile, pl.hb, 1024, 16, bound=2.5 / 256)))
+    got = float(np.dot(np.array(pl.p[:]), moments(lam, pl.tile, pl.hb, 1024, 16, bound=2.5 / 256, one_level=True)))
     assert abs(got - np.sum(integ)) <= 2e-6 * np.sum(integ)
     worst = np.array([np.nextafter(pl.r_max, 0.0)])
     if served(pl, worst)[0]:
-        one = float(np.dot(np.array(pl.p[:]), moments(worst, pl.tile, pl.hb, 1024, 16, bound=2.5 / 256)))
+        one = float(np.dot(np.array(pl.p[:]), moments(worst, pl.tile, pl.hb, 1024, 16, bound=2.5 / 256, one_level=True)))
         assert abs(one - capi.epoch_sites(worst, a, b)[0][0]) <= 5e-6 * one
