@@ -756,6 +756,17 @@ __device__ const double g_inv_fact[32] = {
     9.183689863795546e-29, 3.279889237069838e-30, 1.1309962886447716e-31, 3.7699876288159054e-33,
     1.216125041553518e-34};
 
+// Code size of the 2,048-point kernels: they carry three classes of slow sites, and beyond ~2,500 instructions (40 KB)
+// the SM's instruction cache misses and the GPC-level cache behind it saturates -- the kernel is then bound by
+// instruction fetch (measured: hit rate 87 %, 10.2 ms; 99.7 %, 9.9 ms with less unrolling).  So their k-step loops are
+// unrolled less than the compiler would (four-fold: ~250 instructions each); MomCfg::GroupUnroll, RolledContract.
+#ifndef TAPIR_G8
+#define TAPIR_G8 1
+#endif
+#ifndef TAPIR_ROLL8
+#define TAPIR_ROLL8 1
+#endif
+
 // Shared memory of one warp of profile_mom_kernel: the moment tables U' [32][34] + W' [32][WA]; later, over them, the
 // scratch of the moments -> times step ([32][NB+4] moments, then [TT] times) and the 16-site power tables of the
 // fast-site pass; behind all of them the list of up to 32 fast rates (filled during the moment pass, read after the
@@ -859,16 +870,6 @@ __device__ __forceinline__ constexpr int wcol(int hb)
     return Swz ? ((hb & 1) | ((hb & 2) << 2) | ((hb & 4) >> 1)) : hb;
 }
 
-// Code size of the 2,048-point kernels: they carry three classes of slow sites, and beyond ~2,500 instructions (40 KB)
-// the SM's instruction cache misses and the GPC-level cache behind it saturates -- the kernel is then bound by
-// instruction fetch (measured: hit rate 87 %, 10.2 ms; 99.7 %, 9.9 ms with less unrolling).  So their k-step loops are
-// unrolled less than the compiler would (four-fold: ~250 instructions each); MomCfg::GroupUnroll, RolledContract.
-#ifndef TAPIR_G8
-#define TAPIR_G8 1
-#endif
-#ifndef TAPIR_ROLL8
-#define TAPIR_ROLL8 1
-#endif
 
 // One group of up to 32 slow sites of profile_mom_kernel's moment pass, for a class with NG column tiles: blocks of
 // TT / (8 NG) points (half-length HB), the group's tables U' [32][MS] (moments u0 z^k, z = -HB c) and W' [32][WA]
