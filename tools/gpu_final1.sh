@@ -23,9 +23,10 @@ PY
 SECONDS=0
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_ref.json 2> gpurun_out/${tag}_ref.err; echo "reference arm rc=$? wall=${SECONDS}s"; cut -c1-400 gpurun_out/${tag}_ref.json
 CMD="python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu-baseline --no-host-side --no-other-configs"
-timeout 300 $CMD > gpurun_out/${tag}_plain.log 2>&1 &&
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_ncu_list.log 2>&1
-echo "ncu list rc=$?"
+CMDL="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-host-side --no-other-configs"
+timeout 300 $CMDL > gpurun_out/${tag}_plain.log 2>&1 &&
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $CMDL > gpurun_out/${tag}_ncu_list.log 2>&1
+echo "ncu list (default workload) rc=$?"
 timeout 300 $CMD > gpurun_out/${tag}_plain2.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'profile_mom_kernel|quad_scan_kernel|quad_kernel|finalize' -s 4 -c 4 -o gpurun_out/${tag}_prof_cfg2 -f $CMD > gpurun_out/${tag}_ncu_full.log 2>&1
 echo "ncu full cfg2 rc=$?"
