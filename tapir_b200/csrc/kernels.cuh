@@ -671,9 +671,9 @@ __device__ __forceinline__ void prof_epilogue_at(const ProfArgs& args, const dou
 constexpr int kLinBlock = 130;  // doubles per 128-point block of the moments -> times scratch (128 + 2: the four row groups
                                 // of a store land 8 banks apart instead of on the same banks)
 // The same from shared memory: `lin` holds the sub-tile's 256 RH sums in their natural order, kLinBlock doubles per
-// 128-point block.  A rolled loop, one block per round -- each lane four consecutive times, the warp 1 KB of the row per
-// store pair -- instead of the unrolled walk over the accumulator registers: 60 instructions of code for 860 (the
-// moment kernel is bound by instruction fetch, not by any pipe: every straight-line stretch counts).
+// 128-point block.  A rolled loop, one block per round -- the warp 1 KB of the row per store pair -- instead of the
+// unrolled walk over the accumulator registers: 110 instructions of code for 860 (the moment kernel's code has to stay
+// inside the instruction cache: every straight-line stretch counts).
 template <int RH>
 __device__ __forceinline__ void prof_epilogue_lin(const ProfArgs& args, const double* lin, double* row, double* raw, int64_t T0,
                                                   int lane, long long& best_bits, int64_t& best_t)
@@ -682,33 +682,39 @@ __device__ __forceinline__ void prof_epilogue_lin(const ProfArgs& args, const do
     const int64_t t_left = args.T - T0;
     const int t_end = int(t_left < int64_t(TT) ? (t_left < 0 ? 0 : t_left) : int64_t(TT));
     const bool vec_ok = raw || ((reinterpret_cast<uintptr_t>(row + T0) & 15) == 0);
-    const double* src = lin + 4 * lane;
-    double* dst = raw ? raw + 4 * lane : row + T0 + 4 * lane;
-    double td = double(T0) + double(4 * lane);
+    // per 128-point block a lane takes the times 2 lane, 2 lane + 1 and 64 + 2 lane, 65 + 2 lane: both 16-byte loads of
+    // the warp are 512 contiguous bytes of shared memory (four consecutive times per lane would be two-way conflicted),
+    // both stores 512 contiguous bytes of the row
+    const double* src = lin + 2 * lane;
+    double* dst = raw ? raw + 2 * lane : row + T0 + 2 * lane;
+    double td = double(T0) + double(2 * lane);
 #pragma unroll 1
     for (int b = 0; b < 2 * RH; ++b, src += kLinBlock, dst += 128, td += 128.0) {
         const double2 a01 = *reinterpret_cast<const double2*>(src);
-        const double2 a23 = *reinterpret_cast<const double2*>(src + 2);
-        const int o = 128 * b + 4 * lane;
+        const double2 a23 = *reinterpret_cast<const double2*>(src + 64);
+        const int o = 128 * b + 2 * lane;
         double v[4] = {a01.x, a01.y, a23.x, a23.y};
         if (!raw) {
-            v[0] *= td; v[1] *= td + 1.0; v[2] *= td + 2.0; v[3] *= td + 3.0;
+            v[0] *= td; v[1] *= td + 1.0; v[2] *= td + 64.0; v[3] *= td + 65.0;
         }
-        if ((raw || o + 3 < t_end) && vec_ok) {
+        if ((raw || o + 65 < t_end) && vec_ok) {
             *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
-            *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
+            *reinterpret_cast<double2*>(dst + 64) = make_double2(v[2], v[3]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (o + i < t_end) dst[i] = v[i];
+            for (int i = 0; i < 4; ++i) {
+                const int oi = o + (i & 1) + 32 * (i & 2);
+                if (oi < t_end) dst[(i & 1) + 32 * (i & 2)] = v[i];
+            }
         }
         if (!raw) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                const int oi = o + (i & 1) + 32 * (i & 2);
                 const long long bits = __double_as_longlong(v[i]);
-                if (o + i < t_end && bits > best_bits) {   // offsets rise within a lane: the first maximum is kept
+                if (oi < t_end && bits > best_bits) {   // offsets rise within a lane: the first maximum is kept
                     best_bits = bits;
-                    best_t = T0 + o + i;
+                    best_t = T0 + oi;
                 }
             }
         }
@@ -1072,11 +1078,14 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
             // empty, so that "all but the newest two" always means this round's rates have landed; four slots, so the
             // slot a round refills is never the one it has just read.
             constexpr int kAhead = 3;
-            double* ring = Mom::RateInPad ? myWA + 8 : Us + Mom::RateOff + 4 * lane;   // this lane's four slots
+            // this lane's four slots: 32 doubles apart, or -- in the W' padding, rows 12 doubles apart -- rotated by
+            // lane / 4 so that the sixteen lanes of a half warp touch sixteen different banks
+            double* ring = Mom::RateInPad ? myWA + 8 : Us + Mom::RateOff + lane;
+            auto slot_of = [&](int r) { return Mom::RateInPad ? ((r + (lane >> 2)) & 3) : 32 * (r & 3); };
             auto fetch_round = [&](int r) {   // rates [32 r, 32 r + 32) of the item -> slot r mod 4; zeros past the item
                 const int i = 32 * r + lane;
                 const bool in = i < item.n_sites;
-                const unsigned dst = unsigned(__cvta_generic_to_shared(ring + (r & 3)));
+                const unsigned dst = unsigned(__cvta_generic_to_shared(ring + slot_of(r)));
                 const double* src = in ? rp + i : rp;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(in ? 8 : 0) : "memory");
                 asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1087,7 +1096,7 @@ __global__ void __launch_bounds__(kProfWarps * 32, MomCfg<RH, KM>::MinBlocks) pr
                 const bool more = base < item.n_sites;
                 if (more) {
                     asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");
-                    const double lam_new = ring[rnd & 3];
+                    const double lam_new = ring[slot_of(rnd)];
                     fetch_round(rnd + kAhead);
                     const bool act = rate_is_active(lam_new);  // lanes past the item hold 0
                     const bool slow = act && rate_is_slow(lam_new, kBound);

@@ -17,7 +17,9 @@ WANT = [
     "sm__ops_path_tensor_src_fp64.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
