@@ -295,22 +295,25 @@ def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=
     if moment_form:
         groups, fgroups = (n_slow + 31) // 32, (n_fast + 15) // 16
         dmma = (KM // 8) * NT * ksteps(n_slow, 32) + 4 * KM * NT + (KM // 4) * NT * ((n_mom_epochs + 7) // 8) + 4 * RH * ksteps(n_fast, 16)
-        # scalar FP64 warp instructions.  Per group of the moment pass: c, a, z (4 after folding), bounded exp (18),
-        # q^128, q^256, z^2, z^4, three moment seeds, KM chain multiplies, NB column multiplies (+ a full exp and a multiply for tiles
-        # after the first).  Per item: two accumulator sets added (8 NT), 1/k! onto the moments (8 NT), A fragments of
-        # the moments -> times step (2 x 8 x (5 + KM/4)), epilogue (16 RH).  Per group of 16 fast sites: two exps + tables.
-        per_group = 25 + KM + NB
-        per_item = 16 * NT + 16 * (5 + KM // 4) + 16 * RH
-        scalar0 = groups * per_group + per_item + fgroups * 110
-        scalar1 = groups * (per_group + 27) + per_item + fgroups * 136
-        # the whole-tile class: per group of 32 sites c, a, z, the exponential (18), 16 additions and 16 multiplies, no
+        # scalar FP64 warp instructions (read off kernels.cuh).  Per group of the moment pass: c, a, z (4), the bounded
+        # exponential in Estrin form (21), q^2, q^4, z^2, z^4, three moment seeds, KM - 4 chain multiplies, q^8 and the second
+        # chain's seed, NB column multiplies (+ a full exponential and a multiply for tiles after the first).  Per item:
+        # two accumulator sets added (2 MI NT), 1/k! onto the moments (KS NT), per 1,024-point sub-tile 16 (KS - 1)
+        # multiplies of the moments -> times powers (seeds from a table), epilogue 16 per 256 points (four multiplies
+        # and four additions per 128-point block).  Per group of 16 fast sites: one / two exponentials + the tables.
+        MI, KS, NH = KM // 8, KM // 4, max(1, RH // 4)
+        per_group = 30 + KM + NB
+        per_item = 2 * MI * NT + KS * NT + NH * 16 * (KS - 1) + 16 * RH
+        scalar0 = groups * per_group + per_item + fgroups * NH * 103
+        scalar1 = groups * (per_group + 27) + per_item + fgroups * NH * 130
+        # the whole-tile class: per group of 32 sites c, a, z, the exponential (21), 16 additions and 17 multiplies, no
         # DMMA; per item with such sites the halving reduction (16 additions), 16 scalings, six DMMAs of the shift and
         # four additions into the moment scratch
         wgroups = (n_whole + 31) // 32
         has_w = n_whole > 0
         dmma = dmma + np.where(has_w, 6, 0)
-        scalar0 = scalar0 + wgroups * 55 + np.where(has_w, 36, 0)
-        scalar1 = scalar1 + wgroups * 64 + np.where(has_w, 36, 0)
+        scalar0 = scalar0 + wgroups * 59 + np.where(has_w, 36, 0)
+        scalar1 = scalar1 + wgroups * 66 + np.where(has_w, 36, 0)
         if two_level:
             # the coarse class: one column tile per k-step, half the W' table; per item with such sites the shift onto
             # the 128-point blocks (two DMMAs per non-zero 8 x 4 block of the upper-triangular S, one multiply each,
@@ -319,8 +322,8 @@ def executed_fp64_ops(offsets, rates, T, tile_points, moment_form, n_mom_epochs=
             shift = sum(1 for mt in range(KM // 8) for ks in range(KM // 4) if 4 * ks + 3 >= 8 * mt)
             has = (n_coarse > 0) | has_w
             dmma = dmma + (KM // 8) * ksteps(n_coarse, 32) + np.where(has, 2 * shift, 0)
-            scalar0 = scalar0 + cgroups * (25 + KM + NB // 2) + np.where(has, shift + 6 * (KM // 8), 0)
-            scalar1 = scalar1 + cgroups * (25 + KM + NB // 2 + 27) + np.where(has, shift + 6 * (KM // 8), 0)
+            scalar0 = scalar0 + cgroups * (30 + KM + NB // 2) + np.where(has, shift + 6 * (KM // 8), 0)
+            scalar1 = scalar1 + cgroups * (30 + KM + NB // 2 + 27) + np.where(has, shift + 6 * (KM // 8), 0)
     else:
         n_all = n_slow + n_fast
         groups = (n_all + 31) // 32
