@@ -216,6 +216,33 @@ def profile_traffic(workload):
     return total or None
 
 
+def profile_ncu_utilisation(workload):
+    """Unit utilisations of the profile kernel from the same committed capture (percent of peak): what actually bounds
+    the kernel next to the FP64-pipe fraction the roofline object reports.  {} when no capture is committed."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_%s.txt" % workload)))
+    if not files:
+        return {}
+    want = {"sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active": "dmma_subpipe_pct",
+            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "other_fp64_pct",
+            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_data_pipe_pct",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_pct",
+            "sm__icc_request_hit_rate.pct": "instruction_cache_hit_pct",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct"}
+    out, inside, seen = {}, False, 0
+    for line in open(files[-1]):
+        if line.startswith("== "):
+            inside = ("profile_kernel" in line or "profile_mom_kernel" in line) and seen == 0
+            seen += 1 if inside else 0
+        m = re.match(r"(\S+)\s+([0-9.]+)\s+%", line)
+        if inside and m and m.group(1) in want:
+            out[want[m.group(1)]] = round(float(m.group(2)), 1)
+    if out:
+        out["source"] = "profiles/" + os.path.basename(files[-1])
+    return out
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -813,6 +840,9 @@ def run_ours(args, rank, world, local_rank):
                         "formulation -- over the same kernel time; the moment form executes about a quarter of it, so "
                         "this ratio is an algebra speed-up and may exceed 1, not a pipe utilisation"},
             "traffic": profile_traffic(args.workload),
+            # the committed ncu capture of the same kernel: the FP64 pipe is not what bounds the moment form (the L1
+            # data pipe -- the shared-memory transposition of the group tables -- is busier); see DESIGN.md 3.1a
+            "ncu_utilisation": profile_ncu_utilisation(args.workload),
             "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has HBM and bf16 entries only; "
                            "tools/microbench/fp64_pipes.cu: DMMA 37.0, DFMA 36.6 TFLOP/s, one shared pipe)",
             "active_site_fraction": ex["n_active"] / max(my_sites, 1),

@@ -221,3 +221,6 @@ def test_bench_reads_profile_kernel_traffic_from_the_committed_ncu_summary():
     import bench
     t = bench.profile_traffic("cfg2")
     assert t is not None and 2.0e7 < t < 3.0e7        # 20 MB of rates read once, under 1 MB written (L2-resident profile)
+    u = bench.profile_ncu_utilisation("cfg5")         # the same capture's unit utilisations ride in the roofline object
+    assert u["source"].startswith("profiles/") and 0 < u["dmma_subpipe_pct"] < 100 and 0 < u["l1_data_pipe_pct"] < 100
+    assert u["instruction_cache_hit_pct"] > 90
