@@ -807,13 +807,19 @@ struct MomCfg {
     // Ring length: 2,048-point tiles run twelve warps per SM and have shared memory to spare -- rings of 256 let an
     // item of up to ~250 sites per class finish its rounds first and then drain class by class, every loop's code
     // entered once per item instead of once per group (the kernel is bound by instruction fetch)
-    static constexpr int Ring = Coarse ? 256 : 64;
+#ifndef TAPIR_RING8
+#define TAPIR_RING8 256
+#endif
+#ifndef TAPIR_WARPS8
+#define TAPIR_WARPS8 12
+#endif
+    static constexpr int Ring = Coarse ? TAPIR_RING8 : 64;
     static constexpr int TileQOff = QueueOff + (Coarse ? 2 : 1) * Ring;
     static constexpr bool RateInPad = (WA == 12);
     static constexpr int RateOff = TileQOff + Ring;
     static constexpr int WarpDoubles = RateOff + (RateInPad ? 0 : 4 * 32);
     static constexpr size_t SmemBytes = size_t(kProfWarps) * WarpDoubles * sizeof(double);
-    static constexpr int MinBlocks = (RH == 4 ? 14 : 12) / kProfWarps;  // 144 / 168 registers
+    static constexpr int MinBlocks = (RH == 4 ? 14 : TAPIR_WARPS8) / kProfWarps;  // 144 / 168 registers
     static constexpr int GroupUnroll = (RH == 8) ? TAPIR_G8 : 4;           // pairs of k-steps per loop body of mom_group
     static constexpr bool RolledContract = (RH == 8) && TAPIR_ROLL8;       // fast-site contraction not unrolled
     static_assert(Pow <= FastOff, "16-site power tables fit below the fast-site list");
