@@ -2324,9 +2324,19 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalArgs fa)
     const int lane = threadIdx.x & 31;
     const int64_t l = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (l >= fa.n_loci) return;
+    // One warp per locus and a handful of dependent loads: the kernel is a chain of DRAM round trips, so everything that
+    // does not depend on another load is fetched first (the locus' descriptors), then everything that depends on those
+    // only (tile maxima, the --times picks, the epoch cells), and the arithmetic comes last.
+    const int ns = __ldg(fa.nsplit + l);
+    const int64_t q0 = __ldg(fa.qitem_begin + l), q1 = __ldg(fa.qitem_begin + l + 1);
+    const bool mom = fa.mom_mask != 0ull;
+    const int64_t p0 = mom ? __ldg(fa.part_base + l) : 0, p1 = mom ? __ldg(fa.part_base + l + 1) : 0;
+    const int64_t tix = (lane < fa.K) ? __ldg(fa.time_idx + lane) : 0;
+    const int row = 2 * fa.E + 4;
+
     double best = -1.0;
     int64_t best_t = 0;
-    const int ns = fa.nsplit[l];
+    double pick = 0.0;
     if (ns > 1) {
         double* out = fa.pi_net + l * fa.T;
         for (int tile = 0; tile < fa.n_tiles; ++tile) {
@@ -2341,13 +2351,34 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalArgs fa)
                 if (v > best) { best = v; best_t = t; }
             }
         }
+        __syncwarp();
+        if (lane < fa.K) pick = fa.pi_net[l * fa.T + tix];   // after the row has been written
     } else {
+        if (lane < fa.K) pick = fa.pi_net[l * fa.T + tix];
         for (int tile = lane; tile < fa.n_tiles; tile += 32) {
             const double v = fa.tile_max[l * fa.n_tiles + tile];
             const int64_t t = fa.tile_arg[l * fa.n_tiles + tile];
             if (v > best || (v == best && t < best_t)) { best = v; best_t = t; }
         }
     }
+    // epoch sums over this locus' quad items, in item (= site) order; lanes 0..3 of the last round also take the four
+    // statistics columns (loads issued before the reductions below need anything)
+    double si0 = 0.0, se0 = 0.0, sm0 = 0.0, st = 0.0;
+    const bool first_e = lane < fa.E;
+    if (first_e) {
+#pragma unroll 4
+        for (int64_t q = q0; q < q1; ++q) {
+            si0 += fa.qpart[q * row + 2 * lane];
+            se0 += fa.qpart[q * row + 2 * lane + 1];
+        }
+        if ((fa.mom_mask >> lane) & 1ull)
+            for (int64_t p = p0; p < p1; ++p) sm0 += fa.mom_int[p * fa.E + lane];
+    }
+    if (lane < 4) {
+#pragma unroll 4
+        for (int64_t q = q0; q < q1; ++q) st += fa.qpart[q * row + 2 * fa.E + lane];
+    }
+
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, off);
@@ -2358,26 +2389,26 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalArgs fa)
         fa.max_pi[l] = best;
         fa.argmax_t[l] = best_t;
     }
-    __syncwarp();
-    for (int k = lane; k < fa.K; k += 32) fa.pi_times[l * fa.K + k] = fa.pi_net[l * fa.T + fa.time_idx[k]];
+    if (lane < fa.K) fa.pi_times[l * fa.K + lane] = pick;
+    for (int k = lane + 32; k < fa.K; k += 32) fa.pi_times[l * fa.K + k] = fa.pi_net[l * fa.T + fa.time_idx[k]];
 
-    // epoch sums over this locus' quad items, in item (= site) order
-    const int64_t q0 = fa.qitem_begin[l], q1 = fa.qitem_begin[l + 1];
-    const int row = 2 * fa.E + 4;
     double ebest = 0.0;
     int ebest_idx = 0x7fffffff;
     bool have = false;
     for (int e = lane; e < fa.E; e += 32) {
-        double si = 0.0, se = 0.0;
-        for (int64_t q = q0; q < q1; ++q) {
-            si += fa.qpart[q * row + 2 * e];
-            se += fa.qpart[q * row + 2 * e + 1];
+        double si = si0, se = se0, sm = sm0;
+        if (e != lane) {   // more than 32 epochs: the later rounds as before
+            si = se = sm = 0.0;
+            for (int64_t q = q0; q < q1; ++q) {
+                si += fa.qpart[q * row + 2 * e];
+                se += fa.qpart[q * row + 2 * e + 1];
+            }
+            if ((fa.mom_mask >> e) & 1ull)
+                for (int64_t p = p0; p < p1; ++p) sm += fa.mom_int[p * fa.E + e];
         }
         if ((fa.mom_mask >> e) & 1ull) {
             // the locus' slow sites: sum of their first GK21 panels from the moments; every one of them has the
             // rounding floor 50 eps resabs (= 50 eps result, the integrand is >= 0) as QUADPACK's error estimate
-            double sm = 0.0;
-            for (int64_t p = fa.part_base[l]; p < fa.part_base[l + 1]; ++p) sm += fa.mom_int[p * fa.E + e];
             si += sm;
             se += (kEpmach * 50.0) * sm;
         }
@@ -2395,12 +2426,10 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalArgs fa)
         }
     }
     if (lane < 4) {
-        double s = 0.0;
-        for (int64_t q = q0; q < q1; ++q) s += fa.qpart[q * row + 2 * fa.E + lane];
-        const double rs = __shfl_sync(0x0000000fu, s, 0);
-        if (lane == 1) fa.mean_rate[l] = rs / s;  // 0/0 -> NaN for a locus without any non-NaN rate
-        if (lane == 2) fa.n_finite[l] = int64_t(s);
-        if (lane == 3) fa.n_multi[l] = int64_t(s);
+        const double rs = __shfl_sync(0x0000000fu, st, 0);
+        if (lane == 1) fa.mean_rate[l] = rs / st;  // 0/0 -> NaN for a locus without any non-NaN rate
+        if (lane == 2) fa.n_finite[l] = int64_t(st);
+        if (lane == 3) fa.n_multi[l] = int64_t(st);
         if (lane == 0) fa.argmax_epoch[l] = (fa.E > 0) ? ebest_idx : -1;
     }
 }
