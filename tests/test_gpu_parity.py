@@ -819,3 +819,44 @@ def test_fp32_mode_split_sites_and_error_growth(eng):
         si, se, _ = capi.epochs(rates[off[l]:off[l + 1]][np.isfinite(rates[off[l]:off[l + 1]])], synthetic.EPOCHS)
         assert rel(res.integral[l], si) < F32_RTOL
     assert np.array_equal(res.argmax_epoch, ref.argmax_epoch)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_problems_against_the_oracle(eng, seed):
+    """Randomised batches through whatever variant the cost model picks: locus sizes around the group, ring and quad-item
+    sizes (0 ... 3,000 sites, so that rings drain in the middle of an item and long loci are split), grids around the
+    tile sizes, rates spread over every class of the moment form (whole tile, coarse, fine, fast), zeros and NaN, epochs
+    the moment functional serves and epochs it does not.  Profile, picks, maxima, integrals, error sums, argmax epoch."""
+    from oracle import capi
+    from tapir_b200.engine import pack_csr
+    rng = np.random.default_rng(1000 + seed)
+    T = int(rng.choice([1, 2, 31, 200, 256, 257, 600, 1000, 1024, 1025, 1500, 2048, 2049, 3000, 4096, 5000]))
+    n_loci = int(rng.integers(1, 25))
+    sizes = rng.choice([0, 1, 5, 31, 32, 33, 64, 200, 257, 300, 800, 1500, 3000], size=n_loci)
+    loci = []
+    for n in sizes:
+        scale = 10.0 ** rng.uniform(-4.5, -1.5)                     # mean rate from far below to far above the class bounds
+        lam = rng.gamma(0.5, scale, int(n))
+        kind = rng.random(int(n))
+        lam[kind < 0.25] = 0.0
+        lam[(kind >= 0.25) & (kind < 0.28)] = np.nan
+        big = (kind >= 0.28) & (kind < 0.31)
+        lam[big] = rng.uniform(0.02, 3.0, int(big.sum()))
+        loci.append(lam)
+    n_ep = int(rng.integers(0, 11))
+    epochs = []
+    for _ in range(n_ep):
+        a = float(rng.integers(0, max(1, T + 50)))
+        h = float(rng.choice([0.5, 1, 2, 5, 8, 32, 40]))
+        epochs.append([a, a + 2 * h])
+    times = [int(rng.integers(0, T)) for _ in range(3)] + [-1]
+    off, rates = pack_csr(loci, pinned=False)
+    res = eng.run(off, rates, T, times, epochs, want_profile=True)
+    pi_net, integ, err = capi.batch(off, rates, T, epochs)
+    assert rel(res.pi_net, pi_net) < 5e-11, (T, list(sizes))
+    assert np.array_equal(res.argmax_t, np.argmax(pi_net, axis=1))
+    assert np.array_equal(res.pi_times, res.pi_net[:, [t % T for t in times]])
+    if n_ep:
+        assert rel(res.integral, integ) < RTOL, (T, epochs)
+        np.testing.assert_allclose(res.abserr, err, rtol=ERR_RTOL, atol=1e-300)
+        assert np.array_equal(res.argmax_epoch, np.argmax(integ, axis=1))
