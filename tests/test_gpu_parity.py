@@ -821,13 +821,7 @@ def test_fp32_mode_split_sites_and_error_growth(eng):
     assert np.array_equal(res.argmax_epoch, ref.argmax_epoch)
 
 
-@pytest.mark.parametrize("seed", range(24))
-def test_random_problems_against_the_oracle(eng, seed):
-    """Randomised batches through whatever variant the cost model picks: locus sizes around the group, ring and quad-item
-    sizes (0 ... 3,000 sites, so that rings drain in the middle of an item and long loci are split), grids around the
-    tile sizes, rates spread over every class of the moment form (whole tile, coarse, fine, fast), zeros and NaN, epochs
-    the moment functional serves and epochs it does not.  Profile, picks, maxima, integrals, error sums, argmax epoch."""
-    from oracle import capi
+def _random_problem(seed):
     from tapir_b200.engine import pack_csr
     rng = np.random.default_rng(1000 + seed)
     T = int(rng.choice([1, 2, 31, 200, 256, 257, 600, 1000, 1024, 1025, 1500, 2048, 2049, 3000, 4096, 5000]))
@@ -851,12 +845,44 @@ def test_random_problems_against_the_oracle(eng, seed):
         epochs.append([a, a + 2 * h])
     times = [int(rng.integers(0, T)) for _ in range(3)] + [-1]
     off, rates = pack_csr(loci, pinned=False)
-    res = eng.run(off, rates, T, times, epochs, want_profile=True)
+    return off, rates, T, times, epochs, sizes
+
+
+def _check_random_problem(res, off, rates, T, times, epochs, sizes):
+    from oracle import capi
     pi_net, integ, err = capi.batch(off, rates, T, epochs)
     assert rel(res.pi_net, pi_net) < 5e-11, (T, list(sizes))
     assert np.array_equal(res.argmax_t, np.argmax(pi_net, axis=1))
     assert np.array_equal(res.pi_times, res.pi_net[:, [t % T for t in times]])
-    if n_ep:
+    if epochs:
         assert rel(res.integral, integ) < RTOL, (T, epochs)
         np.testing.assert_allclose(res.abserr, err, rtol=ERR_RTOL, atol=1e-300)
         assert np.array_equal(res.argmax_epoch, np.argmax(integ, axis=1))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_problems_against_the_oracle(eng, seed):
+    """Randomised batches through whatever variant the cost model picks: locus sizes around the group, ring and quad-item
+    sizes (0 ... 3,000 sites, so that rings drain in the middle of an item and long loci are split), grids around the
+    tile sizes, rates spread over every class of the moment form (whole tile, coarse, fine, fast), zeros and NaN, epochs
+    the moment functional serves and epochs it does not.  Profile, picks, maxima, integrals, error sums, argmax epoch."""
+    off, rates, T, times, epochs, sizes = _random_problem(seed)
+    res = eng.run(off, rates, T, times, epochs, want_profile=True)
+    _check_random_problem(res, off, rates, T, times, epochs, sizes)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("rh,km", [(4, 16), (4, 32), (8, 16), (8, 32)])
+def test_random_problems_every_moment_variant(rh, km, seed, monkeypatch):
+    """The same batches with the moment-form variant forced (tile size and moments per block), whatever the grid."""
+    from tapir_b200.engine import Engine
+    monkeypatch.setenv("TAPIR_CUDA_RH", str(rh))
+    monkeypatch.setenv("TAPIR_PROF_MOM", "1")
+    monkeypatch.setenv("TAPIR_MOM_TERMS", str(km))
+    off, rates, T, times, epochs, sizes = _random_problem(100 + 7 * seed + rh + km)
+    e = Engine(0)
+    try:
+        res = e.run(off, rates, T, times, epochs, want_profile=True)
+    finally:
+        e.close()
+    _check_random_problem(res, off, rates, T, times, epochs, sizes)
