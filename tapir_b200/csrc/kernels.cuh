@@ -2,9 +2,12 @@
 //
 //   profile_kernel<RH>   pi_net[l,t] = t * sum_i a_i q_i^t           (compute.py:46-48 + nansum,
 //                        with a_i = 16 r_i^2, q_i = exp(-4 r_i)        bin/tapir_compute.py:119)
-//   profile_mom_kernel<RH>  the same profile for tiles of 1024+ grid points (the shipped default there): slow
-//                        sites as 32 Taylor moments per 128-point block, a quarter of profile_kernel's DMMAs
-//   quad_kernel<NE>      first GK21 panel of every (site, epoch), collapsed (compute.py:50-52, 81-94)
+//   profile_mom_kernel<RH, KM>  the same profile for tiles of 1024+ grid points (the shipped default there): slow
+//                        sites as KM = 16 / 32 Taylor moments per block -- the whole tile, 256 or 128 points by rate
+//                        class -- an eighth of profile_kernel's DMMAs or less; also the slow sites' epoch sums
+//   profile_f32_kernel   FP32 mode of the same (TAPIR_FP32_MODE)
+//   quad_scan_kernel, quad_kernel<NE, CH>   rate statistics; first GK21 panel of every (site, epoch) the moments do
+//                        not serve, collapsed (compute.py:50-52, 81-94)
 //   quad_fix_kernel      full QAGS for the sites QAGS would bisect   (scipy.integrate.quad = QUADPACK dqagse)
 //   finalize_kernel      per-locus reductions, --times picks, maxima (compute.py:76-79, README.rst:178-185)
 //   rank_kernel, epoch_count_kernel   top-N loci per interval, loci per max-PI epoch
@@ -739,7 +742,12 @@ __device__ __forceinline__ void prof_epilogue_lin(const ProfArgs& args, const do
 // same sums (observed <= 1e-12 relative; the parity gate is 1e-9).
 // (KM = 16: sites with 64 c <= 1.25, rate < 0.0048828125, need only 16 moments for the same remainder -- half the
 // DMMAs, multiplies and shared-memory traffic of the moment pass and of the moments -> times step; the host picks KM
-// per batch from a sample of the rates, tapir_cuda.cu choose_tile)
+// per batch from a sample of the rates, tapir_cuda.cu choose_moments)
+// The slower a site, the longer the block on which KM terms suffice: sites below half the class bound are expanded on
+// 256-point blocks (2,048-point tiles: one column tile of DMMAs instead of two), sites with (TT/2) c <= 1.25 on the
+// whole tile with 16 terms, summed per lane in registers without any table or DMMA.  After the pass the coarser sums
+// are shifted onto the 128-point blocks -- an exact change of variable of the truncated polynomials, a few DMMAs per
+// item -- so everything downstream (moments -> times, the epoch functional) sees one set of moments.  DESIGN.md 3.1a.
 // 1/k!, k = 0..31
 __device__ __constant__ double c_inv_fact[32] = {
     1.0, 1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333, 0.001388888888888889,
