@@ -165,3 +165,56 @@ def test_inverse_factorial_table():
     assert len(vals) == 32
     for k, v in enumerate(vals):
         assert v == float(D(1) / D(factorial(k))), k
+
+
+def _table(name, text):
+    m = re.search(r"%s\[[^\]]*\]\s*=\s*\{(.*?)\};" % name, text, re.S)
+    assert m, name
+    return [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", m.group(1))]
+
+
+def test_shift_tables_of_the_moment_classes():
+    """g_tile_shift[n][j] = (2 j - 7)^n / n! (whole tile -> its eight parts), correctly rounded; g_inv_fact is the
+    constant-bank table again; both as written in kernels.cuh."""
+    from fractions import Fraction
+    text = open(os.path.join(ROOT, "tapir_b200", "csrc", "kernels.cuh")).read()
+    shift = _table("g_tile_shift", text)
+    assert len(shift) == 128
+    for n in range(16):
+        for j in range(8):
+            assert shift[8 * n + j] == float(Fraction((2 * j - 7) ** n, factorial(n))), (n, j)
+    inv_c, inv_g = _table("c_inv_fact", text), _table("g_inv_fact", text)
+    assert len(inv_c) == 32 and inv_c == inv_g
+    for k in range(32):
+        assert inv_c[k] == float(Fraction(1, factorial(k)))
+
+
+def test_block_shifts_are_changes_of_variable():
+    """The shifts that move the coarser classes' sums onto the 128-point blocks (profile_mom_kernel):
+    M[m] = sum_{k >= m} s^-k o^(k-m)/(k-m)! N[k] re-expands sum_k N[k]/k! y^k in x, y = (x + o)/s -- exactly, for any
+    polynomial; with the moments of a class at its bound the re-expanded profile is the class's own truncation."""
+    rng = np.random.default_rng(5)
+    for s, offsets, terms in ((2, (-1.0, 1.0), 16), (2, (-1.0, 1.0), 32), (8, tuple(2.0 * j - 7.0 for j in range(8)), 16)):
+        N = rng.standard_normal(terms) * np.array([float(factorial(k)) ** 0.5 for k in range(terms)])
+        for o in offsets:
+            M = [sum(float(s) ** -k * o ** (k - m) / factorial(k - m) * N[k] for k in range(m, terms)) for m in range(terms)]
+            x = np.linspace(-1.0, 1.0, 41)
+            y = (x + o) / s
+            want = sum(N[k] / factorial(k) * y ** k for k in range(terms))
+            got = sum(M[m] / factorial(m) * x ** m for m in range(terms))
+            assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want)) + 1e-13
+    # a site at the whole-tile bound of a 2,048-point tile ((TT/2) c = 1.25): tile -> 256-point parts -> 128-point blocks
+    lam = 0.0048828125 * 128.0 / 2048.0 * (1 - 1e-12)
+    a, c = 16.0 * lam * lam, 4.0 * lam
+    S = np.array([a * np.exp(-c * 1024.0) * (-1024.0 * c) ** k for k in range(16)])
+    worst = 0.0
+    for hb in range(16):
+        j, half = hb // 2, (1.0 if hb % 2 else -1.0)
+        Nc = [sum(8.0 ** -k * (2.0 * j - 7.0) ** (k - m) / factorial(k - m) * S[k] for k in range(m, 16)) for m in range(16)]
+        Mf = [sum(2.0 ** -k * half ** (k - m) / factorial(k - m) * Nc[k] for k in range(m, 16)) for m in range(16)]
+        t = 128.0 * hb + np.arange(128.0)
+        x = (t - (128.0 * hb + 64.0)) / 64.0
+        got = sum(Mf[m] / factorial(m) * x ** m for m in range(16))
+        want = a * np.exp(-c * t)
+        worst = max(worst, float(np.max(np.abs(got - want) / want)))
+    assert worst < 6e-12, worst                     # 1.25^16 / 16! = 1.7e-12 against e^-1.25
