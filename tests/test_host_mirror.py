@@ -224,3 +224,30 @@ def test_bench_reads_profile_kernel_traffic_from_the_committed_ncu_summary():
     u = bench.profile_ncu_utilisation("cfg5")         # the same capture's unit utilisations ride in the roofline object
     assert u["source"].startswith("profiles/") and 0 < u["dmma_subpipe_pct"] < 100 and 0 < u["l1_data_pipe_pct"] < 100
     assert u["instruction_cache_hit_pct"] > 90
+
+
+def test_rate_file_rewrite_is_json_dump_indent4_byte_for_byte(tmp_path):
+    """parse_site_rates rewrites every rate file as the reference does (json.dump(data, handle, indent=4),
+    compute.py:41-43); the writer used here is a faster one that must produce the same bytes for anything a rate file
+    can hold, and hand over to json.dumps for anything else."""
+    import json
+    from tapir_b200.compute import dumps_indent4, parse_site_rates
+    rng = np.random.default_rng(9)
+    lam = rng.gamma(0.5, 4.0, 300)
+    doc = {"sites": {"rates": [{"site": k + 1, "subst": 0.0, "rate": round(float(v), 4), "ll": -1.5e-7} for k, v in enumerate(lam)]},
+           "meta": {"file": "aé\n\"b\"", "n": 300, "ok": True, "none": None, "empty": [], "nested": [[1, 2.5], {}, []]}}
+    cases = [doc,
+             {"a": [{"x": 1, "y": float("nan")}] * 9, "b": [{"x": 1.0, "y": float("inf")}, {"x": 2.5, "y": -float("inf")}] * 5},
+             [{"k%": i, "s": "q\\", "n": None, "t": True} for i in range(10)],
+             [{"a": 1}] * 8 + [{"b": 2}], [{"a": 1, "b": 2}] * 8 + [{"b": 2, "a": 1}], [{"a": 1}] * 7 + [{"a": 1.5}],
+             {"f": -0.0, "g": 1e-300, "h": 1e22, "i": 12345678901234567890}, [{"a": [1]}] * 9, [{}] * 9, [{1: 2}] * 9,
+             (1, 2, 3), "str", 3.5, None, [{"a": True, "b": None}] * 9, [{"a": 1, "b": True}] * 8 + [{"a": 1, "b": None}]]
+    for c in cases:
+        assert dumps_indent4(c) == json.dumps(c, indent=4)
+    path = tmp_path / "locus.rates"
+    path.write_text(json.dumps(doc))
+    got = parse_site_rates(str(path), correction=100)
+    want = json.loads(json.dumps(doc))
+    want["sites"]["corrected_rates"] = [{"site": k + 1, "rate": v} for k, v in enumerate((np.array([r["rate"] for r in doc["sites"]["rates"]]) / 100).tolist())]
+    assert path.read_text() == json.dumps(want, indent=4)
+    assert np.array_equal(got, np.array([r["rate"] for r in doc["sites"]["rates"]]) / 100)
