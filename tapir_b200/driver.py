@@ -7,6 +7,7 @@ The command line, the glob rules, the output directory rule, the Tree_*.newick s
 context per device); without it one GPU is used.  The arithmetic always runs on the GPU.
 """
 import argparse
+import multiprocessing
 import os
 import sys
 import time
@@ -135,7 +136,13 @@ def load_batch(params, threads=1, native_ingest=False):
                 v = v[subsets[base_name][0]:subsets[base_name][1]]
             vectors.append(v)
     else:
-        if threads > 1:
+        if threads > 1 and len(params) >= 64 and "fork" in multiprocessing.get_all_start_methods():
+            # worker processes, as the reference's --multiprocessing (bin/tapir_compute.py:155-159): the JSON work is
+            # pure Python, so threads only queue on the interpreter lock (measured: 8 threads 0.6x, 8 processes 4x one
+            # core).  The children parse, rewrite and return the vectors; they never touch the GPU.
+            with multiprocessing.get_context("fork").Pool(threads) as pool:
+                loaded = pool.map(load_rates, params, chunksize=max(1, min(64, len(params) // (4 * threads))))
+        elif threads > 1:
             from concurrent.futures import ThreadPoolExecutor
             with ThreadPoolExecutor(max_workers=threads) as pool:
                 loaded = list(pool.map(load_rates, params))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Wall time of the command line on many rate files (GPU box): ingest / GPU / sqlite split of tapir_compute.py --site-rates
 for N synthetic *.rates files (500 sites each, tree depth 1000 -> 1000-point grid), in three forms:
-  reference-compatible   json.load + rewrite of every file, `net` table written
+  reference-compatible   json.load + rewrite of every file, `net` table written (also with --multiprocessing)
   --no-rate-rewrite --multiprocessing          batched C++ ingest, every visible GPU
   ... --no-net-table                            without the T-rows-per-locus table
 usage: python tools/cli_walltime.py [n_files=50000] [n_sites=500] > profiles/r02_cli_walltime.txt"""
@@ -49,12 +49,13 @@ def main():
         print("# %d rate files x %d sites written in %.1f s (%d CPUs); tree depth 1000 -> T = 1000, 4 epochs, 4 times" % (
             N, S, time.perf_counter() - t0, os.cpu_count()))
         forms = [("reference-compatible (json.load + rewrite per file, net table)", [], min(N, 5000)),
+                 ("reference-compatible --multiprocessing (worker processes)", ["--multiprocessing"], min(N, 5000)),
                  ("--no-rate-rewrite --multiprocessing", ["--no-rate-rewrite", "--multiprocessing"], N),
                  ("--no-rate-rewrite --multiprocessing --no-net-table", ["--no-rate-rewrite", "--multiprocessing", "--no-net-table"], N)]
         for label, extra, n_use in forms:
             d = src
             if n_use < N:                         # the slow form runs on a prefix of the files (copied: it rewrites them)
-                d = os.path.join(work, "subset")
+                d = os.path.join(work, "subset-%d" % len(os.listdir(work)))
                 os.mkdir(d)
                 for l in range(n_use):
                     shutil.copy(os.path.join(src, "locus-%06d.rates" % l), d)
