@@ -5,10 +5,12 @@ for N synthetic *.rates files (500 sites each, tree depth 1000 -> 1000-point gri
   --no-rate-rewrite --multiprocessing          batched C++ ingest, every visible GPU
   ... --no-net-table                            without the T-rows-per-locus table
 usage: python tools/cli_walltime.py [n_files=50000] [n_sites=500] > profiles/r02_cli_walltime.txt"""
+import json
 import multiprocessing as mp
 import os
 import shutil
 import sqlite3
+import subprocess
 import sys
 import tempfile
 import time
@@ -35,7 +37,6 @@ def write_files(job):
 
 
 def main():
-    from tapir_b200 import driver
     work = tempfile.mkdtemp(prefix="tapir_cli_")
     try:
         src = os.path.join(work, "rates")
@@ -62,16 +63,16 @@ def main():
             out = os.path.join(work, "out-%d" % len(os.listdir(work)))
             os.mkdir(out)
             argv = [d, tree, "--output", out, "--times=37,93,100,170", "--intervals=32-42,88-98,95-105,164-174", "--site-rates"] + extra
-            stdout = sys.stdout
-            sys.stdout = open(os.devnull, "w")
-            t0 = time.perf_counter()
-            try:
-                driver.main(argv)
-            finally:
-                sys.stdout.close()
-                sys.stdout = stdout
-            wall = time.perf_counter() - t0
-            tm = dict(driver.LAST_TIMING)
+            # every form in a process of its own, as a user's command is: the wall time includes the CUDA context, and
+            # the worker processes of --multiprocessing are forked before any context exists
+            code = ("import json, sys, time; sys.path.insert(0, %r); from tapir_b200 import driver; "
+                    "out = sys.stdout; sys.stdout = open('/dev/null', 'w'); t0 = time.perf_counter(); driver.main(%r); "
+                    "w = time.perf_counter() - t0; sys.stdout = out; print(json.dumps([w, driver.LAST_TIMING]))" % (ROOT, argv))
+            proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+            if proc.returncode != 0:
+                print("%-70s failed: %s" % (label, proc.stderr.strip().split("\n")[-1][:200]))
+                continue
+            wall, tm = json.loads(proc.stdout.strip().split("\n")[-1])
             db = os.path.join(out, "phylogenetic-informativeness.sqlite")
             conn = sqlite3.connect(db)
             rows = {t: conn.execute("SELECT COUNT(*) FROM %s" % t).fetchone()[0] for t in ("loci", "net", "discrete", "interval")}
