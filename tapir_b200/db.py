@@ -68,10 +68,71 @@ def insert_pi_data(conn, c, pis):
     return
 
 
-def insert_batch(conn, c, names, result, times, epochs, with_net=True, block=4096):
+_NET_SHARD_ROWS = 2000000          # below this many `net` rows the worker processes are not worth their start-up
+_MAX_SHARDS = 8                    # SQLite attaches at most 10 databases; they cannot be detached before the commit
+
+
+def _write_net_shard(job):
+    """Worker process: one contiguous range of loci -> a database file holding their `net` rows (same DDL)."""
+    path, keys, block = job
+    T = block.shape[1]
+    conn = sqlite3.connect(path)
+    conn.execute("PRAGMA synchronous = OFF")
+    conn.execute("PRAGMA journal_mode = OFF")
+    conn.execute(_DDL[1])
+    tt = list(range(T))
+    step = max(1, 4000000 // max(T, 1))
+    for l0 in range(0, len(keys), step):
+        l1 = min(len(keys), l0 + step)
+        ids = [k for k in keys[l0:l1] for _ in tt]
+        conn.executemany("INSERT INTO net VALUES (?,?,?)", zip(ids, tt * (l1 - l0), block[l0:l1].reshape(-1).tolist()))
+    conn.commit()
+    conn.close()
+    return path
+
+
+def _insert_net_parallel(c, keys, pi_net, workers, tmp_dir):
+    """The `net` table through worker processes: the Python side of executemany (a tuple and three bound values per
+    row, ~1 us) is what limits the plain path, so contiguous ranges of loci are written to shard files in parallel and
+    appended in order with INSERT ... SELECT at C speed.  Same rows, same order, same rowids.  The shards stay attached
+    (as shard0 ...) until the caller has committed; detach_shards() then removes them."""
+    import multiprocessing
+    import numpy
+    import tempfile
+    n, T = pi_net.shape
+    n_shards = min(_MAX_SHARDS, workers, max(1, (n * T) // (_NET_SHARD_ROWS // 2)))
+    bounds = [n * k // n_shards for k in range(n_shards + 1)]
+    work = tempfile.mkdtemp(prefix="tapir-net-", dir=tmp_dir)
+    jobs = ((os.path.join(work, "shard%d.sqlite" % k), keys[bounds[k]:bounds[k + 1]],
+             numpy.array(pi_net[bounds[k]:bounds[k + 1]]))           # a plain copy: the profile may sit in pinned memory
+            for k in range(n_shards))
+    with multiprocessing.get_context("fork").Pool(min(workers, n_shards)) as pool:
+        for k, path in enumerate(pool.imap(_write_net_shard, jobs)):
+            c.execute("ATTACH DATABASE ? AS shard%d" % k, (path,))
+            c.execute("INSERT INTO net SELECT * FROM shard%d.net" % k)
+            os.remove(path)                                           # stays open (attached) until it is detached
+    try:
+        os.rmdir(work)
+    except OSError:
+        pass
+    return n_shards
+
+
+def detach_shards(conn):
+    """After the commit that follows insert_batch(..., workers > 1): detach the shard databases of the `net` table."""
+    names = [row[1] for row in conn.execute("PRAGMA database_list").fetchall() if row[1].startswith("shard")]
+    for name in names:
+        conn.execute("DETACH DATABASE %s" % name)
+    return len(names)
+
+
+def insert_batch(conn, c, names, result, times, epochs, with_net=True, block=4096, workers=0, tmp_dir=None):
     """Bulk form of insert_pi_data straight from an engine.BatchResult (row l = locus l): same rows, same
     order, one executemany per table and block of loci, rows built from whole-array tolist() calls (no per-value
-    Python arithmetic).  `with_net=False` skips the T-rows-per-locus `net` table."""
+    Python arithmetic).  `with_net=False` skips the T-rows-per-locus `net` table.  `workers` > 1: a large `net`
+    table is written through that many worker processes (_insert_net_parallel; call detach_shards(conn) after the
+    commit).  With foreign-key enforcement off on the connection -- the ids are the ones generated here -- the shards
+    are appended by SQLite's table-to-table transfer, four times faster again."""
     labels = ["{0}-{1}".format(s[0], s[1]) for s in epochs]
     n = len(names)
     c.executemany("INSERT INTO loci(locus) VALUES (?)", ((locus_name(name),) for name in names))
@@ -79,7 +140,12 @@ def insert_batch(conn, c, names, result, times, epochs, with_net=True, block=409
     last = c.execute("SELECT MAX(id) FROM loci").fetchone()[0] if n else 0
     keys = list(range(last - n + 1, last + 1))
     import numpy
-    if with_net and result.pi_net is not None and n:
+    parallel = (with_net and result.pi_net is not None and n and workers > 1
+                and n * result.pi_net.shape[1] >= _NET_SHARD_ROWS
+                and "fork" in __import__("multiprocessing").get_all_start_methods())
+    if parallel:
+        _insert_net_parallel(c, keys, result.pi_net, workers, tmp_dir)
+    elif with_net and result.pi_net is not None and n:
         T = result.pi_net.shape[1]
         tt = list(range(T))
         for l0 in range(0, n, max(1, block)):

@@ -239,9 +239,17 @@ def main(argv=None):
     sys.stdout.write("\nStoring results in {0}...".format(db_name))
     sys.stdout.flush()
     conn, c = db.create_probe_db(db_name)
-    # the bulk writer: same rows, same order as insert_pi_data over worker() tuples (tapir/db.py:44-61)
-    db.insert_batch(conn, c, names, res, args.times, args.intervals, with_net=not args.no_net_table)
+    # the bulk writer: same rows, same order as insert_pi_data over worker() tuples (tapir/db.py:44-61).  With
+    # --multiprocessing a large `net` table goes through worker processes; the foreign keys (ids generated by this very
+    # call) are not re-checked row by row while it is filled, which lets SQLite append the shards table to table.
+    if threads > 1:
+        c.execute("PRAGMA foreign_keys = OFF")
+    db.insert_batch(conn, c, names, res, args.times, args.intervals, with_net=not args.no_net_table,
+                    workers=threads, tmp_dir=args.output)
     conn.commit()
+    if threads > 1:
+        db.detach_shards(conn)
+        c.execute("PRAGMA foreign_keys = ON")
     t3 = time.perf_counter()
     LAST_TIMING.update(loci=len(names), skipped=len(skipped), ingest_and_gpu_s=t2 - t0, sqlite_s=t3 - t2)
     sys.stdout.write("DONE")

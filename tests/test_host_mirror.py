@@ -251,3 +251,40 @@ def test_rate_file_rewrite_is_json_dump_indent4_byte_for_byte(tmp_path):
     want["sites"]["corrected_rates"] = [{"site": k + 1, "rate": v} for k, v in enumerate((np.array([r["rate"] for r in doc["sites"]["rates"]]) / 100).tolist())]
     assert path.read_text() == json.dumps(want, indent=4)
     assert np.array_equal(got, np.array([r["rate"] for r in doc["sites"]["rates"]]) / 100)
+
+
+def test_net_table_through_worker_processes_is_row_identical(tmp_path, monkeypatch):
+    """db.insert_batch(..., workers > 1) writes a large `net` table through shard databases built by worker processes
+    and appended in order: same rows, same rowids, same other tables as the plain bulk writer -- with foreign keys on
+    (row-by-row append) and off (SQLite's table-to-table transfer); the shards are detached after the commit."""
+    from tapir_b200 import db
+
+    class Result:
+        pass
+    rng = np.random.default_rng(4)
+    n, T = 300, 200
+    r = Result()
+    r.pi_net, r.pi_times = rng.random((n, T)), rng.random((n, 3))
+    r.integral, r.abserr = rng.random((n, 2)), rng.random((n, 2))
+    names = ["dir/locus-%04d.rates" % i for i in range(n)]
+    monkeypatch.setattr(db, "_NET_SHARD_ROWS", 10000)
+    tables = {}
+    for label, workers, fk in (("plain", 0, True), ("workers", 5, True), ("workers, no fk checks", 5, False)):
+        d = tmp_path / label.replace(" ", "_").replace(",", "")
+        d.mkdir()
+        conn, c = db.create_probe_db(str(d / "pi.sqlite"), overwrite=True)
+        if not fk:
+            c.execute("PRAGMA foreign_keys = OFF")
+        keys = db.insert_batch(conn, c, names, r, [5, 17, 199], [[32, 42], [88, 98]], workers=workers, tmp_dir=str(d))
+        conn.commit()
+        assert db.detach_shards(conn) == (0 if workers == 0 else 5)
+        assert [f for f in os.listdir(d) if f != "pi.sqlite"] == []
+        assert keys == list(range(1, n + 1))
+        tables[label] = {t: conn.execute("SELECT rowid, * FROM %s ORDER BY rowid" % t).fetchall()
+                         for t in ("loci", "net", "discrete", "interval")}
+        if not fk:
+            c.execute("PRAGMA foreign_keys = ON")
+            assert conn.execute("PRAGMA foreign_key_check").fetchall() == []
+        conn.close()
+    assert len(tables["plain"]["net"]) == n * T
+    assert tables["plain"] == tables["workers"] == tables["workers, no fk checks"]
